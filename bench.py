@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Benchmark of the multimodaltraj forecasting hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--prec bf16|f32]
+                  [--variant mc|mcr] [--scenes S] [--agents N]
+
+One "step" = one pass of the whole hot path (obs 8 -> pred 12 rollout: pairwise kernel/adjacency ->
+[edge MLP] -> aggregation -> gate update, 19 cell steps, then K=20-sample decode + ADE/FDE + best-of-K)
+over one batch of synthetic ETH/UCY-shaped crowds.  Workload at N=1: BASELINE config C3,
+4096 scenes x 64 agents, hidden 128.  metric = agent-trajectories/sec (whole job).
+Multi-GPU: scenes shard across ranks with no data-path collective (weak scaling: 4096 scenes per rank).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T_OBS, P_PRED, K_SAMPLES, HIDDEN, EMBED = 8, 12, 20, 128, 64
+R2, INV_2SIGMA2 = 4.0, 0.5
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return None
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_forecast_sample(n_scenes, N, variant, procs):
+    """The oracle (CPU restatement of the path, numpy) on a bounded sample, scene-sharded over processes."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import track_b as o_b  # oracle: bench's cpu_baseline / reference arm only
+    from multimodaltraj_2_b200 import synth
+    pos, vis, valid = synth.make_crowd(n_scenes, N, seed=synth.SEED)
+    p = synth.init_params(seed=0)
+    eps = o_b.philox_eps(0, n_scenes, N, K_SAMPLES, P_PRED)
+    if procs <= 1:
+        t0 = time.perf_counter()
+        o_b.forecast(pos, vis, valid, p, eps, T_OBS, P_PRED, R2, INV_2SIGMA2, relational=(variant == "mcr"))
+        return time.perf_counter() - t0
+    import multiprocessing as mp
+    chunks = np.array_split(np.arange(n_scenes), procs)
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        pool.starmap(_cpu_worker, [(pos[c], vis[c], valid[c], eps[c], variant) for c in chunks if len(c)])
+        return time.perf_counter() - t0
+
+
+def _cpu_worker(pos, vis, valid, eps, variant):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import track_b as o_b
+    from multimodaltraj_2_b200 import synth
+    p = synth.init_params(seed=0)
+    o_b.forecast(pos, vis, valid, p, eps, T_OBS, P_PRED, R2, INV_2SIGMA2, relational=(variant == "mcr"))
+    return 0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.14 cannot be
+    installed offline, so this is the oracle port of its algebra on all host cores (kind 'port')."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_scenes = max(cores, 8) * 2
+    N = args.agents
+    for _ in range(min(args.warmup, 1)):
+        cpu_forecast_sample(max(cores, 2), N, args.variant, cores)
+    ts = [cpu_forecast_sample(n_scenes, N, args.variant, cores) for _ in range(max(1, min(args.steps, 5)))]
+    t = float(np.mean(ts))
+    val = n_scenes * N / t
+    line = {"impl": "reference", "metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": val,
+            "unit": "agent-trajectories/s", "n_gpus": world, "steps": len(ts), "warmup": min(args.warmup, 1),
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config(args, n_scenes),
+            "cpu_baseline": {"value": val, "unit": "agent-trajectories/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_scenes} scenes x {N} agents per step, numpy fp32 oracle of the whole path, "
+                                       f"scene-sharded over {cores} processes (TF 1.14 reference not installable offline)"},
+            "e2e": {"value": val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config(args, scenes_per_rank):
+    return {"workload": f"C3 synthetic crowds: {scenes_per_rank} scenes x {args.agents} agents per GPU, hidden {HIDDEN}, "
+                        f"obs {T_OBS} / pred {P_PRED}, K={K_SAMPLES}, g2k_lstm_{args.variant} batched inference",
+            "variant": f"g2k_lstm_{args.variant}", "precision_mode": args.prec, "scenes_per_gpu": scenes_per_rank,
+            "agents_per_scene": args.agents, "noise": "in-kernel Philox4x32-10",
+            "l2": "per-step working set (~1 GB of state/workspace) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from multimodaltraj_2_b200 import _lib, ops, synth
+
+    S, N = args.scenes, args.agents
+    prec = ops.PREC_BF16 if args.prec == "bf16" else ops.PREC_F32
+    pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
+    params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
+    fc = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(args.variant == "mcr"),
+                        prec=prec, seed=0xB200, agent_offset=rank * S * N, device=dev)
+    pos_p, vis_p, valid_p = (torch.from_numpy(a).pin_memory() for a in (pos_h, vis_h, valid_h))
+    pos, vis, valid = pos_p.to(dev), vis_p.to(dev), valid_p.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return fc(pos, vis, valid)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    n_valid = int(valid_h.sum())
+    units = n_valid * world          # every rank holds the same number of valid agents (all valid)
+    value = units / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers in, scores out, copies inside the timed region
+    res_h = torch.empty((2,), dtype=torch.float32).pin_memory()
+    pos_d, vis_d, valid_d = torch.empty_like(pos), torch.empty_like(vis), torch.empty_like(valid)
+
+    def e2e_step():
+        pos_d.copy_(pos_p, non_blocking=True)
+        vis_d.copy_(vis_p, non_blocking=True)
+        valid_d.copy_(valid_p, non_blocking=True)
+        o = fc(pos_d, vis_d, valid_d)
+        res = torch.stack([o["best_ade"].sum(), o["best_fde"].sum()]) / n_valid
+        res_h.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res_h
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = units / float(te.item())
+    h2d = pos_p.numel() * 4 + vis_p.numel() * 4 + valid_p.numel()
+    ade, fde = float(res_h[0]), float(res_h[1])
+
+    # ---- roofline of the dominant kernel (gate update): same shapes, timed alone with CUDA events
+    R = S * N
+    x = torch.randn((R, 4), device=dev) * 0.3
+    h, c, mh, mc = (torch.randn((R, HIDDEN), device=dev) * 0.5 for _ in range(4))
+    vflat = valid.reshape(-1).contiguous()
+    cur = torch.randn((R, 2), device=dev)
+    for _ in range(3):
+        ops.gsk_cell(x, h, c, mh, mc, vflat, params, prec, cur_pos=cur, want_head=True)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    k0.record()
+    for _ in range(reps):
+        ops.gsk_cell(x, h, c, mh, mc, vflat, params, prec, cur_pos=cur, want_head=True)
+    k1.record()
+    torch.cuda.synchronize()
+    cell_ms = k0.elapsed_time(k1) / reps
+    pk = peaks()
+    flops = 2.0 * R * (EMBED + 2 * HIDDEN) * 3 * HIDDEN
+    achieved = flops / (cell_ms * 1e-3) / 1e12
+    peak = pk["bf16_sustained"]
+    roof = {"kernel": "gsk_cell_tc_kernel" if prec == ops.PREC_BF16 else "gsk_cell_f32_kernel", "bound": "tensor",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"{pk['src']} (sustained bf16 cuBLAS)", "ms_per_launch": cell_ms,
+            "algorithmic_flops_per_launch": flops, "launches_per_step": T_OBS + P_PRED - 1}
+    # pairwise kernel: HBM roofline (5N^2 + 9N bytes per scene-frame)
+    fc_pos = pos[:, :, 0].contiguous()
+    for _ in range(3):
+        ops.pairwise_adj(fc_pos, valid, R2, INV_2SIGMA2, want_deg=False)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(reps):
+        ops.pairwise_adj(fc_pos, valid, R2, INV_2SIGMA2, want_deg=False)
+    k1.record()
+    torch.cuda.synchronize()
+    pw_ms = k0.elapsed_time(k1) / reps
+    pw_bytes = S * (5.0 * N * N + 9.0 * N)
+    roof_pw = {"kernel": "pairwise_adj_kernel", "bound": "hbm", "achieved": pw_bytes / (pw_ms * 1e-3) / 1e9,
+               "peak": pk["hbm"], "unit": "GB/s", "frac": pw_bytes / (pw_ms * 1e-3) / 1e9 / pk["hbm"],
+               "traffic": None, "ms_per_launch": pw_ms, "note": "output (84 MB) fits in L2 when timed alone"}
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        n_cpu = 8
+        t_cpu = cpu_forecast_sample(n_cpu, N, args.variant, 1)
+        line = {"metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": value, "unit": "agent-trajectories/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if prec == ops.PREC_BF16 else "f32", "data": "synthetic", "config": config(args, S),
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 8},
+                "gpu_launches": int(launches), "roofline": roof, "roofline_pairwise": roof_pw,
+                "cpu_baseline": {"value": n_cpu * N / t_cpu, "unit": "agent-trajectories/s", "cores": 1, "kind": "port",
+                                 "sample": f"{n_cpu} scenes x {N} agents, numpy fp32 oracle of the whole path "
+                                           f"(host has {cores} cores; TF 1.14 reference not installable offline)"},
+                "ade_fde": {"best_of_k_ade": ade, "best_of_k_fde": fde, "note": "random-init weights, synthetic data"},
+                "lib": str(_lib.lib_path().relative_to(ROOT))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--variant", default="mc", choices=["mc", "mcr"])
+    ap.add_argument("--scenes", type=int, default=4096)
+    ap.add_argument("--agents", type=int, default=64)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

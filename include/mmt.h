@@ -1,0 +1,207 @@
+/* libmmt -- C-ABI of the B200-native multimodaltraj forecasting hot path.
+ *
+ * Drop-in boundary for serenetech90/multimodaltraj_2's per-timestep g2k_lstm_mc / g2k_lstm_mcr
+ * step.  The reference is pure Python/TensorFlow-1.14 and has no FFI; each entry
+ * point below names the reference lines whose arithmetic it replaces (paths relative to the
+ * reference root).  Conventions:
+ *   - every pointer is a DEVICE pointer to caller-owned, contiguous, row-major memory, 16-byte
+ *     aligned; the library never allocates or frees device memory and keeps no global state
+ *     except a thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the device;
+ *   - return 0 on success; <0 on error: -1 bad argument/shape, -2 misaligned pointer,
+ *     -3 workspace too small, -4 CUDA error (text via mmt_last_error()), -5 NCCL error;
+ *   - nothing throws or exits across the ABI.
+ * Symbols: S scenes, N agents per scene (padded; valid[S,N]), T obs frames, P pred frames,
+ * U hidden units (128), E embedding (64), K samples, D = neighborhood_size/grid_size.
+ */
+#ifndef MMT_H_
+#define MMT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMT_VERSION 100
+#define MMT_OK 0
+#define MMT_EARG (-1)
+#define MMT_EALIGN (-2)
+#define MMT_EWORKSPACE (-3)
+#define MMT_ECUDA (-4)
+#define MMT_ENCCL (-5)
+
+/* precision modes of the gate / aggregation contractions */
+#define MMT_PREC_F32 0   /* fp32 CUDA-core FMA, parity mode (1e-4 rel vs oracle)             */
+#define MMT_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
+
+int mmt_version(void);
+const char* mmt_last_error(void);
+
+/* ---- pairwise distance kernel + adjacency ------------------------------------------------
+ * Replaces networkx_graph.py:71 (dist_mat, never filled) and :83-85 (L2 edge norm) with the
+ * N x N kernel the north_star names.  Per scene-frame s:
+ *   d2 = (xi-xj)^2 + (yi-yj)^2 (fp32, no FMA); adj = d2 < r2 && i != j && valid_i && valid_j;
+ *   kern = adj ? exp(-d2 * inv_2sigma2) : 0; deg_i = sum_j adj_ij.
+ * pos[S,N,2] f32, valid[S,N] u8; outputs kern[S,N,N] f32 (or NULL), adj[S,N,N] u8 (or NULL),
+ * deg[S,N] i32 (or NULL).  N % 4 == 0, N <= 1024. */
+int mmt_pairwise_adj_f32(const float* pos, const uint8_t* valid, int S, int N, float r2,
+                         float inv_2sigma2, float* kern, uint8_t* adj, int32_t* deg, void* stream);
+
+/* Neighbour index lists from the adjacency mask: nbr[S,N,max_nbr] i32 ascending j, padded -1;
+ * cnt[S,N] = min(deg, max_nbr).  (north_star: "neighbour indexing ... bit-exact") */
+int mmt_neighbor_index_i32(const uint8_t* adj, int S, int N, int max_nbr, int32_t* nbr,
+                           int32_t* cnt, void* stream);
+
+/* ---- graph aggregation --------------------------------------------------------------------
+ * Generalises train.py:240-247 (attn = row softmax; Hs = attn @ Hs).  a = softmax over
+ * {j : adj_ij} of logits_ij (rows without neighbours -> 0); out = a @ feat.
+ * logits[S,N,N] f32, adj[S,N,N] u8, feat[S,N,C] f32 -> attn[S,N,N] (or NULL), out[S,N,C]. */
+int mmt_aggregate_f32(const float* logits, const uint8_t* adj, const float* feat, int S, int N,
+                      int C, float* attn, float* out, void* stream);
+
+/* ---- relational edge MLP (g2k_lstm_mcr only) ------------------------------------------------
+ * Replaces relational_inf_models/nri_learned.py:5-28 (infer_rlns sigmoid gate) with the fNRI
+ * node2edge -> 2-layer ELU MLP -> score it stubs out.
+ *   score_ij = adj_ij ? sigmoid(w_out . elu(W2^T elu(W1a^T h_i + W1b^T h_j + b1) + b2) + b_out) : 0
+ * h[S,N,U]; W1[2U,He] b1[He] W2[He,He] b2[He] w_out[He] b_out[1] -> score[S,N,N] f32.
+ * work: >= 2*S*N*He floats. */
+int mmt_edge_mlp_f32(const float* h, const uint8_t* adj, const float* W1, const float* b1,
+                     const float* W2, const float* b2, const float* w_out, const float* b_out,
+                     int S, int N, int U, int He, float* score, float* work, size_t work_bytes,
+                     void* stream);
+
+/* ---- gsk_lstm_cell: fused gate update ---------------------------------------------------------
+ * Replaces models/gsk_lstm_cell.py:4-65 (dead Hadamard stub) with the GridLSTMCell gate
+ * equations of helper.py:31-39 at U units over the graph neighbourhood:
+ *   e = relu(x W_e + b_e); z = [e|h|mh] W + b; (i,j,o) = split(z)
+ *   g = sig(i + w_If*mc + w_It*c); c_f = (1-g)mc + g tanh j; c_t = (1-g)c + g tanh j
+ *   q = sig(o + w_Of*c_f + w_Ot*c_t); m_f = q tanh c_f; m_t = q tanh c_t
+ * x[R,4] h,c,mh,mc[R,U] valid[R] (R = S*N rows) -> h_out=m_t, c_out=c_t, mf_out=m_f [R,U].
+ * If W_h != NULL also the head: y = [m_t|m_f] W_h + b_h -> params_out[R*params_stride .. +5]
+ * = (mu_x, mu_y, exp(.), exp(.), tanh(.)) and next_pos[R,2] = cur_pos + (mu_x, mu_y).
+ * prec = MMT_PREC_F32 (W fp32 [E+2U,3U]) or MMT_PREC_BF16 (W_packed from mmt_pack_gate_weights_bf16).
+ * In-place h_out==h, c_out==c is allowed. */
+typedef struct mmt_cell_weights {
+  const float* W_e;   /* [4,E]      */
+  const float* b_e;   /* [E]        */
+  const float* W;     /* [E+2U,3U] fp32 row-major                                     */
+  const float* b;     /* [3U]       */
+  const float* w_If;  /* [U] peephole diagonals                                        */
+  const float* w_It;
+  const float* w_Of;
+  const float* w_Ot;
+  const float* W_h;   /* [2U,5] or NULL */
+  const float* b_h;   /* [5]   or NULL */
+  const void* W_packed_bf16; /* tcgen05 operand image of W (mmt_pack_gate_weights_bf16) or NULL */
+  int E;
+  int U;
+} mmt_cell_weights;
+
+int mmt_gsk_cell(const float* x, const float* h, const float* c, const float* mh, const float* mc,
+                 const uint8_t* valid, const mmt_cell_weights* w, int R, int prec, float* h_out,
+                 float* c_out, float* mf_out, const float* cur_pos, float* params_out,
+                 int params_stride, float* next_pos, void* stream);
+
+/* bytes of the packed bf16 operand image for W[E+2U,3U] */
+size_t mmt_gate_weights_packed_bytes(int E, int U);
+int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* packed, void* stream);
+
+/* ---- GridLSTMCell exactly as helper.py:31-39 / :131-139 instantiate it -------
+ * inputs[B, in_stride] (first 4F columns used), state[B, st_stride] (first 2UF used),
+ * W_f[4+2U,3U], B_f[3U], peephole diagonals [U] (ignored when peepholes == 0)
+ * -> m_out[B,2UF], state_out[B,2UF].  U <= 16. */
+int mmt_gridlstm_step_f32(const float* inputs, int in_stride, const float* state, int st_stride,
+                          const float* W_f, const float* B_f, const float* w_If, const float* w_It,
+                          const float* w_Of, const float* w_Ot, int B, int U, int F, int peepholes,
+                          float* m_out, float* state_out, void* stream);
+
+/* ---- Track-A batched g2k_lstm_mcr step -----------------------------------------------------------
+ * Replaces models/g2k_lstm_mcr.py:99-124 + train.py:178-183,194-195,240-254 for S scenes at once:
+ *   I = W_ii (X W_i); vemb = V W_i; vrel = vemb_prev * vemb; outputs = [I; vemb]
+ *   ngh = (lam C) stat_mask; ngh' = lam ngh; Eo = W_v outputs + b_v
+ *   attn = ngh' (Eo * (W_r vrel)); cost = Eo ngh'; band = reshape((W_c cost) W_o, (2,P,n))
+ *   a = softmax(exp(attn)/cumsum0(exp(attn))); Hs = a softmax(Hs); adj = rowsum(softmax(Hs)); Hs *= adj
+ * variant 0 = g2k_lstm_mcr, 1 = g2k_lstm_mc (cost := 0 -> band == 0, models/g2k_lstm_mc.py:59-69).
+ * Per scene: X[T,n] V[2,n] C[D,D] Hs[D,H] vemb_prev[2,D] (or NULL: first step).
+ * Shared: W_i[n,D] W_ii[D,T] W_v[T,D+2] b_v[D] W_r[T,2] W_c[2P,T] W_o[T,n].
+ * Outputs per scene: attn[D,D] cost[T,T] band[2,P,n] Hs_out[D,H] adj[D] vemb_out[2,D] (any may be NULL
+ * except Hs_out).  D <= 16, T <= 16, n <= 64, H <= 128, 2P <= 32. */
+typedef struct mmt_mcr_weights {
+  const float *W_i, *W_ii, *W_v, *b_v, *W_r, *W_c, *W_o;
+} mmt_mcr_weights;
+
+int mmt_mcr_step_f32(const float* X, const float* V, const float* C, const float* Hs,
+                     const float* vemb_prev, const mmt_mcr_weights* w, int S, int n, int D, int T,
+                     int P, int H, float lam, int variant, float* attn, float* cost, float* band,
+                     float* Hs_out, float* adj, float* vemb_out, void* stream);
+
+/* ---- K-sample bivariate-Gaussian decode + ADE/FDE + best-of-K (one fused epilogue) ---------------
+ * Replaces the scoring of train.py:639-674 / sample.py:21-82 (which score tf.random_normal,
+ * SURVEY F4) with the decode the north_star names.  params[S,N,P,5] activated
+ * (mu_x,mu_y,sig_x,sig_y,rho); eps[S,N,K,P,2] or NULL (then Philox4x32-10 keyed
+ * (seed, agent_offset + s*N+i, k, t) + Box-Muller in-kernel); last_obs[S,N,2]; gt[S,N,P,2];
+ * valid[S,N] -> ade[S,N,K], fde[S,N,K] (either may be NULL), best_k[S,N] i32 (argmin ADE, ties ->
+ * lowest k, -1 invalid), best_ade[S,N], best_fde[S,N] (may be NULL), best_traj[S,N,P,2] (may be NULL).
+ * P <= 32, K <= 32. */
+int mmt_decode_score_f32(const float* params, const float* eps, uint64_t seed, uint64_t agent_offset,
+                         const float* last_obs, const float* gt, const uint8_t* valid, int S, int N,
+                         int P, int K, float* ade, float* fde, int32_t* best_k, float* best_ade,
+                         float* best_fde, float* best_traj, void* stream);
+
+/* Diagnostic variant of the above in Philox mode that also writes the noise it used to
+ * eps_out[S,N,K,P,2] (tests compare it with the oracle's Philox/Box-Muller restatement). */
+int mmt_decode_score_dump_eps_f32(const float* params, uint64_t seed, uint64_t agent_offset,
+                                  const float* last_obs, const float* gt, const uint8_t* valid, int S, int N,
+                                  int P, int K, int32_t* best_k, float* best_ade, float* eps_out, void* stream);
+
+/* ---- device-side padded scene batching ---------------------------------------------------------------
+ * Replaces load_traj.py:153-224 (next_step dict walking) + networkx_graph.py:30-73,114-129
+ * (ConstructGraph / setNodes) for window extraction: rows sorted by (frame, ped) as
+ * frame_id[M] i32, ped_id[M] i32, xy[M,2] f32 (+ vis[M,2] or NULL); windows start at
+ * win_start[S] (frame ids) and span F frames with stride `fstride`.  A pedestrian is given a
+ * slot (ascending ped id order of first appearance in the window's first frame) if present in
+ * ALL F frames and the scene has < N slots used.  Outputs pos[S,N,F,2], visout[S,N,F,2] (or NULL),
+ * valid[S,N] u8, ped_of_slot[S,N] i32 (-1 empty).  frame_row_start[n_frames+1] is the CSR offset of
+ * each distinct frame id in frame_ids_sorted[n_frames]. */
+int mmt_scene_batch_f32(const int32_t* frame_ids_sorted, const int32_t* frame_row_start, int n_frames,
+                        const int32_t* ped_id, const float* xy, const float* vis,
+                        const int32_t* win_start, int S, int N, int F, int fstride, float* pos,
+                        float* visout, uint8_t* valid, int32_t* ped_of_slot, void* stream);
+
+/* ---- the whole hot path: obs T -> pred P rollout + decode + score -------------------------------------
+ * One call = one batch of scenes through T+P-1 cell steps (pairwise -> [edge MLP] -> aggregation ->
+ * gate update -> head), then decode/score.  pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N].
+ * relational = 0 (g2k_lstm_mc: logits = kern) or 1 (g2k_lstm_mcr: logits = kern + edge score).
+ * Outputs as mmt_decode_score_f32 plus params[S,N,P,5] (may be NULL -> uses workspace).
+ * Workspace: mmt_forecast_workspace_bytes(). */
+typedef struct mmt_edge_weights {
+  const float *W1, *b1, *W2, *b2, *w_out, *b_out;
+  int He;
+} mmt_edge_weights;
+
+typedef struct mmt_forecast_cfg {
+  int S, N, T, P, K;
+  float r2, inv_2sigma2;
+  int relational;
+  int prec;            /* MMT_PREC_* */
+  uint64_t seed;       /* Philox seed when eps == NULL */
+  uint64_t agent_offset;
+} mmt_forecast_cfg;
+
+size_t mmt_forecast_workspace_bytes(const mmt_forecast_cfg* cfg, int U, int He);
+
+int mmt_forecast_f32(const float* pos, const float* vis, const uint8_t* valid,
+                     const mmt_cell_weights* cw, const mmt_edge_weights* ew, const mmt_forecast_cfg* cfg,
+                     const float* eps, float* params, float* ade, float* fde, int32_t* best_k,
+                     float* best_ade, float* best_fde, float* best_traj, void* work, size_t work_bytes,
+                     void* stream);
+
+/* number of kernel launches issued by this process through the library (bench's gpu_launches) */
+uint64_t mmt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMT_H_ */

@@ -1,0 +1,456 @@
+// gsk_lstm_cell on the 5th-generation tensor cores (sm_100a): bf16 operands, fp32 accumulation in
+// TMEM, gate update + head fused as the epilogue (include/mmt.h mmt_gsk_cell
+// with MMT_PREC_BF16).
+//
+// Tile = 128 rows (agents) x 384 gate columns x K = E + 2U = 320.
+//   * A operand [e | h | mh] is built in shared memory by the worker warps (e = relu(x W_e + b_e)
+//     computed on the fly, h / mh converted fp32 -> bf16) in the canonical K-major SWIZZLE_128B
+//     layout (5 blocks of [128 rows x 128 B]).  It is never written to HBM.
+//   * B operand (the gate weights) is pre-packed once by mmt_pack_gate_weights_bf16 into the exact
+//     shared-memory image, ordered [pass][k-chunk]; a producer thread streams 12 KB stages with
+//     cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on mbarriers.  The image is 240 KB and
+//     stays L2-resident.
+//   * The 384 gate columns are processed as 4 passes of 32 units; the packed column order puts the
+//     i, j, o columns of a pass next to each other so one tcgen05.mma (M=128, N=96, K=16) per
+//     k-step feeds a 96-column accumulator; two accumulators (TMEM columns 0 and 128) are
+//     double-buffered so the epilogue of pass p overlaps the MMAs of pass p+1.
+//   * Epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).. (its rows) and units 16*(w/4).. of the
+//     pass with tcgen05.ld.32x32b.x8, applies the peephole gates, writes h', c' (and m_f) and
+//     accumulates the 5-wide head.  2 CTAs are resident per SM (256 TMEM columns, ~105 KB smem each)
+//     so one CTA's operand build overlaps the other's MMA/epilogue.
+#include <cuda_bf16.h>
+
+#include "mmt_common.cuh"
+
+namespace mmt {
+
+constexpr int TC_E = 64, TC_U = 128, TC_K = TC_E + 2 * TC_U;  // 320
+constexpr int TC_M = 128;                                     // rows per tile
+constexpr int TC_UN = 32;                                     // units per pass
+constexpr int TC_NP = TC_U / TC_UN;                           // 4 passes
+constexpr int TC_N = 3 * TC_UN;                               // 96 accumulator columns per pass
+constexpr int TC_KC = 64;                                     // k-chunk (one 128-byte swizzle row)
+constexpr int TC_NKC = TC_K / TC_KC;                          // 5
+constexpr int TC_STAGE_BYTES = TC_N * TC_KC * 2;              // 12288
+constexpr int TC_NSTAGE = 2;
+constexpr int TC_A_BLOCK = TC_M * TC_KC * 2;                  // 16384 bytes per k-chunk block
+constexpr int TC_A_BYTES = TC_NKC * TC_A_BLOCK;               // 81920
+constexpr int TC_WORKERS = 256;
+constexpr int TC_THREADS = TC_WORKERS + 64;                   // + producer warp + MMA warp
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_ACC_STRIDE = 128;                            // TMEM column stride between the two accumulators
+
+// shared memory map (dynamic, 1024-aligned)
+constexpr int SM_A = 0;
+constexpr int SM_W = SM_A + TC_A_BYTES;                       // stages
+constexpr int SM_BAR = SM_W + TC_NSTAGE * TC_STAGE_BYTES;     // mbarriers (16 x 8 B)
+constexpr int SM_TMEM = SM_BAR + 128;                         // tmem base address
+constexpr int SM_BIAS = SM_TMEM + 16;                         // b[384] w_If,w_It,w_Of,w_Ot [4][128]
+constexpr int SM_WE = SM_BIAS + (384 + 512) * 4;              // W_e[4][64], b_e[64]
+constexpr int SM_HEAD = SM_WE + (256 + 64) * 4;               // head partials [128][5]
+constexpr int SM_TOTAL = SM_HEAD + 128 * 5 * 4;
+static_assert(SM_TOTAL + 1024 <= 113 * 1024, "two CTAs per SM must fit");
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, float v[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=96
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B block
+__host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
+  return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)k & 7u) << 1);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
+struct TcArgs {
+  const float *x, *h, *c, *mh, *mc;
+  const uint8_t* valid;
+  const float *W_e, *b_e, *b, *w_If, *w_It, *w_Of, *w_Ot, *W_h, *b_h;
+  const uint8_t* Wp;  // packed bf16 operand image
+  float *h_out, *c_out, *mf_out;
+  const float* cur_pos;
+  float *params_out, *next_pos;
+  int R, ld, ld_mf, params_stride, num_tiles;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  // SWIZZLE_128B atoms need a 1024-byte aligned base; the launch adds 1 KB of slack for this
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SM_BAR;
+  // barrier indices
+  const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * TC_NSTAGE, ACC_FULL = bar0 + 8 * 2 * TC_NSTAGE,
+                 ACC_EMPTY = ACC_FULL + 16, A_READY = ACC_EMPTY + 16;
+  float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float* s_we = reinterpret_cast<float*>(smem + SM_WE);
+  float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_NSTAGE; ++s) {
+      mbar_init(W_FULL + 8 * s, 1);
+      mbar_init(W_EMPTY + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ACC_FULL + 8 * b, 1);
+      mbar_init(ACC_EMPTY + 8 * b, TC_WORKERS);
+    }
+    mbar_init(A_READY, TC_WORKERS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(sbase + SM_TMEM, TC_TMEM_COLS);
+  for (int i = tid; i < 384; i += TC_THREADS) s_bias[i] = a.b[i];
+  for (int i = tid; i < 128; i += TC_THREADS) {
+    s_bias[384 + i] = a.w_If[i];
+    s_bias[512 + i] = a.w_It[i];
+    s_bias[640 + i] = a.w_Of[i];
+    s_bias[768 + i] = a.w_Ot[i];
+  }
+  for (int i = tid; i < 256; i += TC_THREADS) s_we[i] = a.W_e[i];
+  for (int i = tid; i < 64; i += TC_THREADS) s_we[256 + i] = a.b_e[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 8) {
+    // =============================== weight-stage producer ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int p = 0; p < TC_NP; ++p)
+          for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
+            const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
+            mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(W_FULL + 8 * s, TC_STAGE_BYTES);
+            bulk_g2s(sbase + SM_W + s * TC_STAGE_BYTES, a.Wp + (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES,
+                     TC_STAGE_BYTES, W_FULL + 8 * s);
+          }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t it = 0, pc = 0, tc = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tc) {
+        mbar_wait(A_READY, tc & 1u);
+        tc_fence_after();
+        for (int p = 0; p < TC_NP; ++p, ++pc) {
+          const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+          mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + b * TC_ACC_STRIDE;
+          for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
+            const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
+            mbar_wait(W_FULL + 8 * s, ph);
+            tc_fence_after();
+            const uint64_t da = make_desc_sw128(sbase + SM_A + kc * TC_A_BLOCK);
+            const uint64_t db = make_desc_sw128(sbase + SM_W + s * TC_STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < TC_KC / 16; ++ks)  // advance 32 B (16 bf16) inside the swizzle row
+              umma_bf16(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdesc, (kc | ks) ? 1u : 0u);
+            umma_commit(W_EMPTY + 8 * s);  // stage reusable once these MMAs have read it
+          }
+          umma_commit(ACC_FULL + 8 * b);  // accumulator (and, on the last pass, the A operand) done
+        }
+      }
+    }
+  } else {
+    // =============================== workers: operand build + epilogue ===============================
+    const int q = warp & 3, hsel = warp >> 2;
+    uint32_t pc = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int row0 = tile * TC_M;
+      // ---- e = relu(x W_e + b_e) -> block 0.  thread -> (row tid/2, 32 k's)
+      {
+        const int r = tid >> 1, k0 = (tid & 1) * 32;
+        const int gr = row0 + r;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = gr < a.R;
+        if (ok) xv = __ldg(reinterpret_cast<const float4*>(a.x) + gr);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float e2[2];
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+              const int k = k0 + kk + j + z;
+              float s = s_we[256 + k];
+              s = fmaf(xv.x, s_we[k], s);
+              s = fmaf(xv.y, s_we[64 + k], s);
+              s = fmaf(xv.z, s_we[128 + k], s);
+              s = fmaf(xv.w, s_we[192 + k], s);
+              e2[z] = ok ? fmaxf(s, 0.f) : 0.f;
+            }
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(e2[0], e2[1]);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(smem + SM_A + sw128_off(r, k0 + kk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      // ---- h -> blocks 1,2 ; mh -> blocks 3,4.  one warp per row, lane -> 4 consecutive k
+      for (int rr = warp; rr < TC_M; rr += 8) {
+        const int gr = row0 + rr;
+        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), mv = hv;
+        if (gr < a.R) {
+          hv = *reinterpret_cast<const float4*>(a.h + (size_t)gr * a.ld + lane * 4);
+          mv = *reinterpret_cast<const float4*>(a.mh + (size_t)gr * a.ld + lane * 4);
+        }
+        const int k = lane * 4;                   // 0..124 within the 128-wide part
+        const int blk = k >> 6, kk = k & 63;
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(hv.x, hv.y), h23 = __floats2bfloat162_rn(hv.z, hv.w);
+        __nv_bfloat162 m01 = __floats2bfloat162_rn(mv.x, mv.y), m23 = __floats2bfloat162_rn(mv.z, mv.w);
+        *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+        *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&m01), *reinterpret_cast<uint32_t*>(&m23));
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(A_READY);
+
+      // ---- epilogue
+      const int r = q * 32 + lane;  // row within tile == TMEM lane
+      const int gr = row0 + r;
+      const bool rok = gr < a.R;
+      const bool v = rok && a.valid[gr] != 0;
+      float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < TC_NP; ++p, ++pc) {
+        const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+        mbar_wait(ACC_FULL + 8 * b, bph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + b * TC_ACC_STRIDE;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int ul = hsel * 16 + sub * 8;        // unit within pass
+          const int u = p * TC_UN + ul;              // global unit
+          float zi[8], zj[8], zo[8];
+          tmem_ld8(t_row + ul, zi);
+          tmem_ld8(t_row + TC_UN + ul, zj);
+          tmem_ld8(t_row + 2 * TC_UN + ul, zo);
+          float cv[8], mcv[8];
+          if (v) {
+            const float4* cp = reinterpret_cast<const float4*>(a.c + (size_t)gr * a.ld + u);
+            const float4* mp = reinterpret_cast<const float4*>(a.mc + (size_t)gr * a.ld + u);
+            const float4 c0 = cp[0], c1 = cp[1], m0 = mp[0], m1 = mp[1];
+            cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+            mcv[0] = m0.x; mcv[1] = m0.y; mcv[2] = m0.z; mcv[3] = m0.w; mcv[4] = m1.x; mcv[5] = m1.y; mcv[6] = m1.z; mcv[7] = m1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cv[i] = mcv[i] = 0.f;
+          }
+          tmem_wait_ld();
+          float ho[8], co[8], fo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int uu = u + i;
+            const float gi = zi[i] + s_bias[uu], gj = zj[i] + s_bias[128 + uu], go = zo[i] + s_bias[256 + uu];
+            const float g = sigmoid_fast(gi + s_bias[384 + uu] * mcv[i] + s_bias[512 + uu] * cv[i]);
+            const float tj = tanh_fast(gj);
+            const float cf = fmaf(g, tj - mcv[i], mcv[i]);   // (1-g)*mc + g*tj
+            const float ct = fmaf(g, tj - cv[i], cv[i]);
+            const float qq = sigmoid_fast(go + s_bias[640 + uu] * cf + s_bias[768 + uu] * ct);
+            fo[i] = v ? qq * tanh_fast(cf) : 0.f;
+            ho[i] = v ? qq * tanh_fast(ct) : 0.f;
+            co[i] = v ? ct : 0.f;
+          }
+          if (rok) {
+            float4* hp = reinterpret_cast<float4*>(a.h_out + (size_t)gr * a.ld + u);
+            float4* cp = reinterpret_cast<float4*>(a.c_out + (size_t)gr * a.ld + u);
+            hp[0] = make_float4(ho[0], ho[1], ho[2], ho[3]);
+            hp[1] = make_float4(ho[4], ho[5], ho[6], ho[7]);
+            cp[0] = make_float4(co[0], co[1], co[2], co[3]);
+            cp[1] = make_float4(co[4], co[5], co[6], co[7]);
+            if (a.mf_out) {
+              float4* fp = reinterpret_cast<float4*>(a.mf_out + (size_t)gr * a.ld_mf + u);
+              fp[0] = make_float4(fo[0], fo[1], fo[2], fo[3]);
+              fp[1] = make_float4(fo[4], fo[5], fo[6], fo[7]);
+            }
+          }
+          if (a.params_out) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float* wa = a.W_h + (size_t)(u + i) * 5;
+              const float* wb = a.W_h + (size_t)(TC_U + u + i) * 5;
+#pragma unroll
+              for (int z = 0; z < 5; ++z) y[z] = fmaf(ho[i], __ldg(wa + z), fmaf(fo[i], __ldg(wb + z), y[z]));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(ACC_EMPTY + 8 * b);
+      }
+      // ---- head: combine the two column halves of each row
+      if (a.params_out) {
+        if (hsel == 1) {
+#pragma unroll
+          for (int z = 0; z < 5; ++z) s_head[r * 5 + z] = y[z];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (hsel == 0 && rok) {
+          float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          if (v) {
+#pragma unroll
+            for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + __ldg(a.b_h + z);
+            o[2] = __expf(o[2]);
+            o[3] = __expf(o[3]);
+            o[4] = tanh_fast(o[4]);
+          }
+          float* po = a.params_out + (size_t)gr * a.params_stride;
+#pragma unroll
+          for (int z = 0; z < 5; ++z) po[z] = o[z];
+          if (a.next_pos) {
+            const float2 cp = *reinterpret_cast<const float2*>(a.cur_pos + (size_t)gr * 2);
+            *reinterpret_cast<float2*>(a.next_pos + (size_t)gr * 2) = make_float2(cp.x + o[0], cp.y + o[1]);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// W[E+2U, 3U] fp32 row-major -> bf16 operand image [pass][k-chunk][96 rows][64 k], SWIZZLE_128B.
+// Row n = g*32 + ul of a pass holds gate column g*U + pass*32 + ul.
+__global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TC_K * 3 * TC_U) return;
+  const int k = idx / (3 * TC_U), col = idx - k * (3 * TC_U);
+  const int g = col / TC_U, u = col - g * TC_U;
+  const int p = u / TC_UN, ul = u - p * TC_UN;
+  const int n = g * TC_UN + ul;
+  const int kc = k / TC_KC, kk = k - kc * TC_KC;
+  const size_t off = (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES + sw128_off(n, kk);
+  *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(W[idx]);
+}
+
+int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
+                   const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   cudaStream_t stream) {
+  TcArgs a;
+  a.x = x; a.h = h; a.c = c; a.mh = mh; a.mc = mc; a.valid = valid;
+  a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
+  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
+  a.h_out = h_out; a.c_out = c_out; a.mf_out = mf_out; a.cur_pos = cur_pos; a.params_out = params_out;
+  a.next_pos = next_pos; a.R = R; a.ld = ld; a.ld_mf = ld_mf; a.params_stride = params_stride;
+  a.num_tiles = (R + TC_M - 1) / TC_M;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gsk_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < 2 * kNumSMs ? a.num_tiles : 2 * kNumSMs;
+  gsk_cell_tc_kernel<<<grid, TC_THREADS, SM_TOTAL + 1024, stream>>>(a);
+  count_launch();
+  return check_launch("gsk_cell_tc_kernel");
+}
+
+}  // namespace mmt
+
+extern "C" size_t mmt_gate_weights_packed_bytes(int E, int U) {
+  if (E != mmt::TC_E || U != mmt::TC_U) return 0;
+  return (size_t)mmt::TC_NP * mmt::TC_NKC * mmt::TC_STAGE_BYTES;
+}
+
+extern "C" int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* packed, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(W && packed, "W/packed must not be NULL");
+  MMT_REQUIRE(E == TC_E && U == TC_U, "packing is built for E = 64, U = 128");
+  MMT_ALIGNED(packed);
+  const int n = TC_K * 3 * TC_U;
+  pack_gate_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
+  count_launch();
+  return check_launch("pack_gate_weights_kernel");
+}

@@ -1,0 +1,172 @@
+// The whole hot path: obs T -> pred P rollout + K-sample decode + ADE/FDE (include/mmt.h
+// mmt_forecast_f32).  Host-side orchestration of the per-step kernels on the caller's stream;
+// no host synchronisation, no allocation -- everything lives in the caller's workspace.
+#include "mmt_common.cuh"
+
+namespace mmt {
+
+int launch_aggregate(const float* logits, const float* logits2, const uint8_t* adj, const float* feat, int S, int N,
+                     int C, int ld_feat, float* attn, float* out, int ld_out, cudaStream_t stream);
+int launch_cell_f32(const float* x, const float* h, const float* c, const float* mh, const float* mc,
+                    const uint8_t* valid, const mmt_cell_weights* w, int R, int ld, float* h_out, float* c_out,
+                    float* mf_out, int ld_mf, cudaStream_t stream);
+int launch_head(const float* mt, int ld, const float* mf, int ld_mf, const uint8_t* valid, const mmt_cell_weights* w, int R,
+                const float* cur_pos, float* params_out, int params_stride, float* next_pos, cudaStream_t stream);
+int launch_edge_mlp_f32(const float* h, int ld_h, const uint8_t* adj, const mmt_edge_weights* w, int S, int N, int U,
+                        float* score, float* work, cudaStream_t stream);
+int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
+                   const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   cudaStream_t stream);
+
+// x = [cur - prev | vis_t]; for observed frames cur is gathered from pos[:, :, t]
+__global__ void __launch_bounds__(256) prep_step_kernel(const float* __restrict__ pos, const float* __restrict__ vis,
+                                                        int R, int F, int T, int t, float* __restrict__ cur,
+                                                        const float* __restrict__ prev, float* __restrict__ x) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float2 c;
+  if (t < T) {
+    c = __ldg(reinterpret_cast<const float2*>(pos) + (size_t)r * F + t);
+    reinterpret_cast<float2*>(cur)[r] = c;
+  } else {
+    c = reinterpret_cast<const float2*>(cur)[r];
+  }
+  float2 d = make_float2(0.f, 0.f);
+  if (t > 0) {
+    const float2 p = reinterpret_cast<const float2*>(prev)[r];
+    d = make_float2(__fsub_rn(c.x, p.x), __fsub_rn(c.y, p.y));
+  }
+  const int tv = t < T ? t : T - 1;
+  const float2 v = __ldg(reinterpret_cast<const float2*>(vis) + (size_t)r * T + tv);
+  reinterpret_cast<float4*>(x)[r] = make_float4(d.x, d.y, v.x, v.y);
+}
+
+__global__ void __launch_bounds__(256) gather_frames_kernel(const float* __restrict__ pos, int R, int F, int T, int P,
+                                                            float* __restrict__ last_obs, float* __restrict__ gt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * (P + 1)) return;
+  const int r = i / (P + 1), k = i - r * (P + 1);
+  const float2 v = __ldg(reinterpret_cast<const float2*>(pos) + (size_t)r * F + (T - 1 + k));
+  if (k == 0) reinterpret_cast<float2*>(last_obs)[r] = v;
+  else reinterpret_cast<float2*>(gt)[(size_t)r * P + (k - 1)] = v;
+}
+
+struct Workspace {
+  float *pbuf[3], *x, *hc[2], *mhc, *mf, *kern, *score, *ework, *params, *last_obs, *gt;
+  uint8_t* adj;
+  size_t bytes;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
+  Workspace w;
+  const size_t R = (size_t)cfg->S * cfg->N, NN = (size_t)cfg->S * cfg->N * cfg->N;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
+  w.x = (float*)take(R * 4 * 4);
+  w.hc[0] = (float*)take(R * 2 * U * 4);
+  w.hc[1] = (float*)take(R * 2 * U * 4);
+  w.mhc = (float*)take(R * 2 * U * 4);
+  w.mf = (float*)take(R * U * 4);
+  w.kern = (float*)take(NN * 4);
+  w.adj = (uint8_t*)take(NN);
+  w.score = (float*)take(cfg->relational ? NN * 4 : 0);
+  w.ework = (float*)take(cfg->relational ? 2 * R * He * 4 : 0);
+  w.params = (float*)take(R * cfg->P * 5 * 4);
+  w.last_obs = (float*)take(R * 2 * 4);
+  w.gt = (float*)take(R * cfg->P * 2 * 4);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace mmt
+
+extern "C" size_t mmt_forecast_workspace_bytes(const mmt_forecast_cfg* cfg, int U, int He) {
+  if (!cfg) return 0;
+  return mmt::carve(nullptr, cfg, U, He).bytes;
+}
+
+extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
+                                const mmt_edge_weights* ew, const mmt_forecast_cfg* cfg, const float* eps,
+                                float* params, float* ade, float* fde, int32_t* best_k, float* best_ade,
+                                float* best_fde, float* best_traj, void* work, size_t work_bytes, void* stream_) {
+  using namespace mmt;
+  MMT_REQUIRE(pos && vis && valid && cw && cfg && best_k && work, "pos/vis/valid/weights/cfg/best_k/work required");
+  MMT_REQUIRE(cfg->S >= 0 && cfg->N > 0 && cfg->N % 4 == 0 && cfg->N <= 1024, "need 0 < N <= 1024, N % 4 == 0");
+  MMT_REQUIRE(cfg->T >= 1 && cfg->P >= 1 && cfg->P <= 32 && cfg->K >= 1 && cfg->K <= 32, "need T >= 1, P, K in [1,32]");
+  MMT_REQUIRE(cw->U == 128 && cw->E == 64, "cell is built for U = 128, E = 64");
+  MMT_REQUIRE(cw->W_h && cw->b_h, "head weights required");
+  MMT_REQUIRE(!cfg->relational || (ew && ew->He > 0), "relational mode needs edge weights");
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16, "unknown precision mode");
+  MMT_REQUIRE(cfg->prec != MMT_PREC_BF16 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
+  MMT_ALIGNED(pos);
+  MMT_ALIGNED(vis);
+  MMT_ALIGNED(work);
+  const int U = cw->U, He = ew ? ew->He : 0;
+  Workspace w = carve((char*)work, cfg, U, He);
+  if (work_bytes < w.bytes) {
+    set_error("mmt_forecast_f32: workspace too small (%zu < %zu)", work_bytes, w.bytes);
+    return MMT_EWORKSPACE;
+  }
+  if (cfg->S == 0) return MMT_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int S = cfg->S, N = cfg->N, T = cfg->T, P = cfg->P, F = T + P;
+  const int R = S * N;
+  float* par = params ? params : w.params;
+
+  cudaMemsetAsync(w.hc[0], 0, (size_t)R * 2 * U * 4, stream);
+  int ic = 0, ip = 1, in = 2, hb = 0;
+  int rc;
+  for (int t = 0; t < T + P - 1; ++t) {
+    prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
+    count_launch();
+    if ((rc = check_launch("prep_step_kernel"))) return rc;
+    if ((rc = mmt_pairwise_adj_f32(w.pbuf[ic], valid, S, N, cfg->r2, cfg->inv_2sigma2, w.kern, w.adj, nullptr, stream)))
+      return rc;
+    const float* l2 = nullptr;
+    if (cfg->relational) {
+      if ((rc = launch_edge_mlp_f32(w.hc[hb], 2 * U, w.adj, ew, S, N, U, w.score, w.ework, stream))) return rc;
+      l2 = w.score;
+    }
+    if ((rc = launch_aggregate(w.kern, l2, w.adj, w.hc[hb], S, N, 2 * U, 2 * U, nullptr, w.mhc, 2 * U, stream)))
+      return rc;
+    const bool emit = t >= T - 1;
+    float* po = par + (size_t)(t - (T - 1)) * 5;
+    if (cfg->prec == MMT_PREC_F32) {
+      const float* hc = w.hc[hb];
+      float* hco = w.hc[hb ^ 1];
+      if ((rc = launch_cell_f32(w.x, hc, hc + U, w.mhc, w.mhc + U, valid, cw, R, 2 * U, hco, hco + U, w.mf, U, stream)))
+        return rc;
+      if (emit && (rc = launch_head(hco, 2 * U, w.mf, U, valid, cw, R, w.pbuf[ic], po, P * 5, w.pbuf[in], stream)))
+        return rc;
+    } else {
+      const float* hc = w.hc[hb];
+      float* hco = w.hc[hb ^ 1];
+      if ((rc = launch_cell_tc(w.x, hc, hc + U, w.mhc, w.mhc + U, 2 * U, valid, cw, R, hco, hco + U, nullptr, 0,
+                               w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr, stream)))
+        return rc;
+    }
+    hb ^= 1;
+    // rotate position buffers: prev <- cur; cur <- next (predicted) or a fresh buffer (observed)
+    const int old_p = ip;
+    ip = ic;
+    if (emit) {
+      ic = in;
+      in = old_p;
+    } else {
+      ic = old_p;
+    }
+  }
+  gather_frames_kernel<<<(R * (P + 1) + 255) / 256, 256, 0, stream>>>(pos, R, F, T, P, w.last_obs, w.gt);
+  count_launch();
+  if ((rc = check_launch("gather_frames_kernel"))) return rc;
+  return mmt_decode_score_f32(par, eps, cfg->seed, cfg->agent_offset, w.last_obs, w.gt, valid, S, N, P, cfg->K, ade,
+                              fde, best_k, best_ade, best_fde, best_traj, stream);
+}

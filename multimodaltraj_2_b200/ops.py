@@ -1,0 +1,286 @@
+"""Torch-tensor wrappers over the C-ABI (``include/mmt.h``).  PyTorch only supplies device memory
+and the current stream; every operation is a hand-written CUDA kernel in ``csrc/``.
+
+All functions require CUDA tensors and raise if the extension cannot be loaded -- there is no
+eager/CPU fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+
+PREC_F32, PREC_BF16 = 0, 1
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libmmt has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().mmt_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+def pairwise_adj(pos, valid, r2, inv_2sigma2, want_kern=True, want_adj=True, want_deg=True):
+    """pos[S,N,2] f32, valid[S,N] u8 -> (kern[S,N,N] f32, adj[S,N,N] u8, deg[S,N] i32)."""
+    lib = _lib.load()
+    _chk(pos, torch.float32, "pos"); _chk(valid, torch.uint8, "valid")
+    S, N, _ = pos.shape
+    kern = torch.empty((S, N, N), dtype=torch.float32, device=pos.device) if want_kern else None
+    adj = torch.empty((S, N, N), dtype=torch.uint8, device=pos.device) if want_adj else None
+    deg = torch.empty((S, N), dtype=torch.int32, device=pos.device) if want_deg else None
+    _lib.check(lib.mmt_pairwise_adj_f32(_p(pos), _p(valid), S, N, r2, inv_2sigma2, _p(kern), _p(adj), _p(deg),
+                                        _stream()), "mmt_pairwise_adj_f32")
+    return kern, adj, deg
+
+
+def neighbor_index(adj, max_nbr):
+    lib = _lib.load()
+    _chk(adj, torch.uint8, "adj")
+    S, N, _ = adj.shape
+    nbr = torch.empty((S, N, max_nbr), dtype=torch.int32, device=adj.device)
+    cnt = torch.empty((S, N), dtype=torch.int32, device=adj.device)
+    _lib.check(lib.mmt_neighbor_index_i32(_p(adj), S, N, max_nbr, _p(nbr), _p(cnt), _stream()),
+               "mmt_neighbor_index_i32")
+    return nbr, cnt
+
+
+def aggregate(logits, adj, feat, want_attn=True):
+    lib = _lib.load()
+    _chk(logits, torch.float32, "logits"); _chk(adj, torch.uint8, "adj"); _chk(feat, torch.float32, "feat")
+    S, N, Cc = feat.shape
+    attn = torch.empty((S, N, N), dtype=torch.float32, device=feat.device) if want_attn else None
+    out = torch.empty_like(feat)
+    _lib.check(lib.mmt_aggregate_f32(_p(logits), _p(adj), _p(feat), S, N, Cc, _p(attn), _p(out), _stream()),
+               "mmt_aggregate_f32")
+    return attn, out
+
+
+def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out):
+    lib = _lib.load()
+    for n, t in dict(h=h, W1=W1, b1=b1, W2=W2, b2=b2, w_out=w_out, b_out=b_out).items():
+        _chk(t, torch.float32, n)
+    _chk(adj, torch.uint8, "adj")
+    S, N, U = h.shape
+    He = W2.shape[0]
+    score = torch.empty((S, N, N), dtype=torch.float32, device=h.device)
+    work = torch.empty((2 * S * N * He,), dtype=torch.float32, device=h.device)
+    _lib.check(lib.mmt_edge_mlp_f32(_p(h), _p(adj), _p(W1), _p(b1), _p(W2), _p(b2), _p(w_out), _p(b_out), S, N, U, He,
+                                    _p(score), _p(work), work.numel() * 4, _stream()), "mmt_edge_mlp_f32")
+    return score
+
+
+# --------------------------------------------------------------------------------------------
+@dataclass
+class CellParams:
+    """Device-resident weights of the fused gsk cell (+ head, + relational edge MLP)."""
+    W_e: torch.Tensor; b_e: torch.Tensor; W: torch.Tensor; b: torch.Tensor
+    w_If: torch.Tensor; w_It: torch.Tensor; w_Of: torch.Tensor; w_Ot: torch.Tensor
+    W_h: torch.Tensor = None; b_h: torch.Tensor = None
+    W1: torch.Tensor = None; b1: torch.Tensor = None; W2: torch.Tensor = None; b2: torch.Tensor = None
+    w_out: torch.Tensor = None; b_out: torch.Tensor = None
+    W_packed: torch.Tensor = field(default=None, repr=False)
+
+    @property
+    def E(self):
+        return self.W_e.shape[1]
+
+    @property
+    def U(self):
+        return self.w_If.shape[0]
+
+    def pack(self):
+        """Build the bf16 tcgen05 operand image of W once (mmt_pack_gate_weights_bf16)."""
+        lib = _lib.load()
+        nbytes = lib.mmt_gate_weights_packed_bytes(self.E, self.U)
+        if nbytes == 0:
+            raise RuntimeError("bf16 packing is built for E=64, U=128")
+        self.W_packed = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
+        _lib.check(lib.mmt_pack_gate_weights_bf16(_p(self.W), self.E, self.U, _p(self.W_packed), _stream()),
+                   "mmt_pack_gate_weights_bf16")
+        return self
+
+    def c_cell(self):
+        w = _lib.CellWeights()
+        for n in ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h"):
+            t = getattr(self, n)
+            setattr(w, n, None if t is None else t.data_ptr())
+        w.W_packed_bf16 = None if self.W_packed is None else self.W_packed.data_ptr()
+        w.E, w.U = self.E, self.U
+        return w
+
+    def c_edge(self):
+        if self.W1 is None:
+            return None
+        w = _lib.EdgeWeights()
+        for n in ("W1", "b1", "W2", "b2", "w_out", "b_out"):
+            setattr(w, n, getattr(self, n).data_ptr())
+        w.He = self.W2.shape[0]
+        return w
+
+    @staticmethod
+    def from_numpy(p: dict, device="cuda"):
+        kw = {k: torch.as_tensor(v, dtype=torch.float32).contiguous().to(device) for k, v in p.items()
+              if k in CellParams.__dataclass_fields__}
+        if "b_out" in kw:
+            kw["b_out"] = kw["b_out"].reshape(1)
+        return CellParams(**kw)
+
+
+def gsk_cell(x, h, c, mh, mc, valid, params: CellParams, prec=PREC_F32, cur_pos=None, want_head=False):
+    """One fused cell step on R rows.  Returns (h', c', m_f[, params[R,5], next_pos[R,2]])."""
+    lib = _lib.load()
+    for n, t in dict(x=x, h=h, c=c, mh=mh, mc=mc).items():
+        _chk(t, torch.float32, n)
+    _chk(valid, torch.uint8, "valid")
+    R = x.shape[0]
+    h_out, c_out, mf = torch.empty_like(h), torch.empty_like(c), torch.empty_like(h)
+    par = nxt = None
+    if want_head:
+        par = torch.empty((R, 5), dtype=torch.float32, device=x.device)
+        nxt = torch.empty((R, 2), dtype=torch.float32, device=x.device)
+        _chk(cur_pos, torch.float32, "cur_pos")
+    if prec == PREC_BF16 and params.W_packed is None:
+        params.pack()
+    w = params.c_cell()
+    _lib.check(lib.mmt_gsk_cell(_p(x), _p(h), _p(c), _p(mh), _p(mc), _p(valid), C.byref(w), R, prec, _p(h_out),
+                                _p(c_out), _p(mf), _p(cur_pos), _p(par), 5, _p(nxt), _stream()), "mmt_gsk_cell")
+    return (h_out, c_out, mf, par, nxt) if want_head else (h_out, c_out, mf)
+
+
+def gridlstm_step(inputs, state, W_f, B_f, w_If, w_It, w_Of, w_Ot, U, F, peepholes=True):
+    """GridLSTMCell as helper.py instantiates it.  inputs[B,>=4F], state[B,>=2UF] -> (m_out, state_out)."""
+    lib = _lib.load()
+    _chk(inputs, torch.float32, "inputs"); _chk(state, torch.float32, "state")
+    B = inputs.shape[0]
+    m_out = torch.empty((B, 2 * U * F), dtype=torch.float32, device=inputs.device)
+    st_out = torch.empty((B, 2 * U * F), dtype=torch.float32, device=inputs.device)
+    _lib.check(lib.mmt_gridlstm_step_f32(_p(inputs), inputs.shape[1], _p(state), state.shape[1], _p(W_f), _p(B_f),
+                                         _p(w_If), _p(w_It), _p(w_Of), _p(w_Ot), B, U, F, int(peepholes), _p(m_out),
+                                         _p(st_out), _stream()), "mmt_gridlstm_step_f32")
+    return m_out, st_out
+
+
+def mcr_step(X, V, Cc, Hs, w: dict, lam, P=12, variant=0, vemb_prev=None):
+    """Track-A batched scene-frame step.  X[S,T,n] V[S,2,n] C[S,D,D] Hs[S,D,H]; w: dict of device tensors
+    W_i[n,D] W_ii[D,T] W_v[T,D+2] b_v[D] W_r[T,2] W_c[2P,T] W_o[T,n].  Returns dict."""
+    lib = _lib.load()
+    for n, t in dict(X=X, V=V, C=Cc, Hs=Hs).items():
+        _chk(t, torch.float32, n)
+    S, T, n = X.shape
+    D, H = Hs.shape[1], Hs.shape[2]
+    dev = X.device
+    out = dict(attn=torch.empty((S, D, D), dtype=torch.float32, device=dev),
+               cost=torch.empty((S, T, T), dtype=torch.float32, device=dev),
+               band=torch.empty((S, 2, P, n), dtype=torch.float32, device=dev),
+               Hs=torch.empty((S, D, H), dtype=torch.float32, device=dev),
+               adj=torch.empty((S, D), dtype=torch.float32, device=dev),
+               vemb=torch.empty((S, 2, D), dtype=torch.float32, device=dev))
+    cw = _lib.McrWeights()
+    for k in ("W_i", "W_ii", "W_v", "b_v", "W_r", "W_c", "W_o"):
+        setattr(cw, k, _chk(w[k], torch.float32, k).data_ptr())
+    _lib.check(lib.mmt_mcr_step_f32(_p(X), _p(V), _p(Cc), _p(Hs), _p(vemb_prev), C.byref(cw), S, n, D, T, P, H,
+                                    float(lam), variant, _p(out["attn"]), _p(out["cost"]), _p(out["band"]),
+                                    _p(out["Hs"]), _p(out["adj"]), _p(out["vemb"]), _stream()), "mmt_mcr_step_f32")
+    out["pred"] = out["band"].permute(0, 3, 2, 1)          # train.py:254  [S,n,P,2] (view)
+    return out
+
+
+def decode_score(params, last_obs, gt, valid, K, eps=None, seed=0, agent_offset=0, want_all=True, want_traj=True,
+                 dump_eps=False):
+    """params[S,N,P,5] activated; returns dict(ade, fde [S,N,K], best_k, best_ade, best_fde, best_traj)."""
+    lib = _lib.load()
+    _chk(params, torch.float32, "params"); _chk(last_obs, torch.float32, "last_obs")
+    _chk(gt, torch.float32, "gt"); _chk(valid, torch.uint8, "valid")
+    S, N, P, _ = params.shape
+    dev = params.device
+    o = dict(best_k=torch.empty((S, N), dtype=torch.int32, device=dev),
+             best_ade=torch.empty((S, N), dtype=torch.float32, device=dev))
+    if dump_eps:
+        o["eps"] = torch.empty((S, N, K, P, 2), dtype=torch.float32, device=dev)
+        _lib.check(lib.mmt_decode_score_dump_eps_f32(_p(params), seed, agent_offset, _p(last_obs), _p(gt), _p(valid),
+                                                     S, N, P, K, _p(o["best_k"]), _p(o["best_ade"]), _p(o["eps"]),
+                                                     _stream()), "mmt_decode_score_dump_eps_f32")
+        return o
+    o["best_fde"] = torch.empty((S, N), dtype=torch.float32, device=dev)
+    o["ade"] = torch.empty((S, N, K), dtype=torch.float32, device=dev) if want_all else None
+    o["fde"] = torch.empty((S, N, K), dtype=torch.float32, device=dev) if want_all else None
+    o["best_traj"] = torch.empty((S, N, P, 2), dtype=torch.float32, device=dev) if want_traj else None
+    if eps is not None:
+        _chk(eps, torch.float32, "eps")
+    _lib.check(lib.mmt_decode_score_f32(_p(params), _p(eps), seed, agent_offset, _p(last_obs), _p(gt), _p(valid), S,
+                                        N, P, K, _p(o["ade"]), _p(o["fde"]), _p(o["best_k"]), _p(o["best_ade"]),
+                                        _p(o["best_fde"]), _p(o["best_traj"]), _stream()), "mmt_decode_score_f32")
+    return o
+
+
+def scene_batch(frame_ids, frame_row_start, ped_id, xy, vis, win_start, N, F, fstride):
+    """Device-side padded scene batching -> (pos[S,N,F,2], vis[S,N,F,2]|None, valid[S,N], ped_of_slot[S,N])."""
+    lib = _lib.load()
+    for n, t in dict(frame_ids=frame_ids, frame_row_start=frame_row_start, ped_id=ped_id, win_start=win_start).items():
+        _chk(t, torch.int32, n)
+    _chk(xy, torch.float32, "xy")
+    S = win_start.shape[0]
+    dev = xy.device
+    pos = torch.empty((S, N, F, 2), dtype=torch.float32, device=dev)
+    vo = torch.empty((S, N, F, 2), dtype=torch.float32, device=dev) if vis is not None else None
+    valid = torch.empty((S, N), dtype=torch.uint8, device=dev)
+    slot = torch.empty((S, N), dtype=torch.int32, device=dev)
+    _lib.check(lib.mmt_scene_batch_f32(_p(frame_ids), _p(frame_row_start), frame_ids.shape[0], _p(ped_id), _p(xy),
+                                       _p(vis), _p(win_start), S, N, F, fstride, _p(pos), _p(vo), _p(valid), _p(slot),
+                                       _stream()), "mmt_scene_batch_f32")
+    return pos, vo, valid, slot
+
+
+# --------------------------------------------------------------------------------------------
+class Forecaster:
+    """The whole hot path behind one call (mmt_forecast_f32): workspace and outputs are allocated
+    once and reused, so a step is pure kernel launches on the current stream."""
+
+    def __init__(self, params: CellParams, S, N, T=8, P=12, K=20, r2=4.0, inv_2sigma2=0.5, relational=False,
+                 prec=PREC_F32, seed=0, agent_offset=0, device="cuda", want_all=False):
+        self.lib = _lib.load()
+        self.p = params
+        if prec == PREC_BF16 and params.W_packed is None:
+            params.pack()
+        self.cfg = _lib.ForecastCfg(S, N, T, P, K, r2, inv_2sigma2, int(relational), prec, seed, agent_offset)
+        He = params.W2.shape[0] if (relational and params.W2 is not None) else 0
+        nbytes = self.lib.mmt_forecast_workspace_bytes(C.byref(self.cfg), params.U, He)
+        self.work = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        self.out = dict(params=torch.empty((S, N, P, 5), dtype=torch.float32, device=device),
+                        best_k=torch.empty((S, N), dtype=torch.int32, device=device),
+                        best_ade=torch.empty((S, N), dtype=torch.float32, device=device),
+                        best_fde=torch.empty((S, N), dtype=torch.float32, device=device),
+                        best_traj=torch.empty((S, N, P, 2), dtype=torch.float32, device=device))
+        self.out["ade"] = torch.empty((S, N, K), dtype=torch.float32, device=device) if want_all else None
+        self.out["fde"] = torch.empty((S, N, K), dtype=torch.float32, device=device) if want_all else None
+        self._cw = params.c_cell()
+        self._ew = params.c_edge()
+
+    def __call__(self, pos, vis, valid, eps=None):
+        _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis"); _chk(valid, torch.uint8, "valid")
+        o = self.out
+        ew = C.byref(self._ew) if self._ew is not None else None
+        _lib.check(self.lib.mmt_forecast_f32(_p(pos), _p(vis), _p(valid), C.byref(self._cw), ew, C.byref(self.cfg),
+                                             _p(eps), _p(o["params"]), _p(o["ade"]), _p(o["fde"]), _p(o["best_k"]),
+                                             _p(o["best_ade"]), _p(o["best_fde"]), _p(o["best_traj"]), _p(self.work),
+                                             self.work.numel(), _stream()), "mmt_forecast_f32")
+        return o

@@ -1,0 +1,343 @@
+"""GPU parity tests: every CUDA kernel (called through the C-ABI via ops.py) against the CPU oracle
+on the same seeded inputs.  Integer / index outputs are bit-exact; floats carry their tolerance.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import gridlstm as o_gl  # noqa: E402
+import scene_batch as o_sb  # noqa: E402
+import track_a as o_a  # noqa: E402
+import track_b as o_b  # noqa: E402
+
+from multimodaltraj_2_b200 import ops, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = ROOT / "tests" / "golden"
+
+
+def dev(a, cuda):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(cuda)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,N,ragged", [(7, 64, False), (5, 16, True), (3, 256, True), (2, 4, False), (3, 12, True),
+                                        (1, 160, False)])
+def test_pairwise_adjacency_bit_exact(cuda, S, N, ragged):
+    pos, _, valid = synth.make_crowd(S, N, seed=11 + N, half_extent=4.0 if N < 100 else 8.0, ragged=ragged)
+    p0 = np.ascontiguousarray(pos[:, :, 3])
+    kern, adj, deg = ops.pairwise_adj(dev(p0, cuda), dev(valid, cuda), 4.0, 0.5)
+    ok, oa, od = o_b.pairwise_adj(p0, valid, 4.0, 0.5)
+    assert np.array_equal(npy(adj), oa)
+    assert np.array_equal(npy(deg), od)
+    assert od.sum() > 0
+    np.testing.assert_allclose(npy(kern), ok, rtol=2e-6, atol=1e-7)
+    nbr, cnt = ops.neighbor_index(adj, 8)
+    onbr, ocnt = o_b.neighbor_index(oa, 8)
+    assert np.array_equal(npy(nbr), onbr) and np.array_equal(npy(cnt), ocnt)
+
+
+def test_pairwise_empty_and_optional_outputs(cuda):
+    pos = torch.zeros((0, 8, 2), device=cuda)
+    valid = torch.zeros((0, 8), dtype=torch.uint8, device=cuda)
+    kern, adj, deg = ops.pairwise_adj(pos, valid, 1.0, 1.0)
+    assert kern.shape == (0, 8, 8)
+    p, _, v = synth.make_crowd(4, 32, seed=3, half_extent=3.0)
+    _, adj, _ = ops.pairwise_adj(dev(p[:, :, 0], cuda), dev(v, cuda), 4.0, 0.5, want_kern=False, want_deg=False)
+    assert np.array_equal(npy(adj), o_b.pairwise_adj(p[:, :, 0], v, 4.0, 0.5)[1])
+    with pytest.raises(RuntimeError):
+        ops.pairwise_adj(torch.zeros((1, 6, 2), device=cuda), torch.zeros((1, 6), dtype=torch.uint8, device=cuda), 1., 1.)
+    with pytest.raises(RuntimeError):
+        ops.pairwise_adj(torch.zeros((1, 8, 2)), torch.zeros((1, 8), dtype=torch.uint8), 1., 1.)  # CPU tensor
+
+
+def test_pairwise_full_size_properties(cuda):
+    """C3 size (4096 x 64): symmetry, zero diagonal, deg == row sums, kern in (0,1] exactly on edges."""
+    pos, _, valid = synth.make_crowd(4096, 64)
+    kern, adj, deg = ops.pairwise_adj(dev(pos[:, :, 0], cuda), dev(valid, cuda), 4.0, 0.5)
+    assert torch.equal(adj, adj.transpose(1, 2))
+    assert int(torch.diagonal(adj, dim1=1, dim2=2).sum()) == 0
+    assert torch.equal(adj.sum(-1, dtype=torch.int32), deg)
+    assert torch.equal(kern > 0, adj.bool())
+    assert float(kern.max()) <= 1.0
+    # a checksum of the same thing on a sample of scenes against the oracle
+    ok, oa, od = o_b.pairwise_adj(pos[:64, :, 0], valid[:64], 4.0, 0.5)
+    assert np.array_equal(npy(adj[:64]), oa) and np.array_equal(npy(deg[:64]), od)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,N,C", [(5, 64, 256), (3, 16, 128), (2, 256, 256), (4, 12, 32)])
+def test_aggregate(cuda, S, N, C):
+    rng = np.random.default_rng(5)
+    pos, _, valid = synth.make_crowd(S, N, seed=21, half_extent=4.0 if N < 100 else 8.0, ragged=True)
+    kern, adj, _ = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
+    feat = rng.standard_normal((S, N, C)).astype(np.float32)
+    a, out = ops.aggregate(dev(kern, cuda), dev(adj, cuda), dev(feat, cuda))
+    oa, oo = o_b.aggregate(kern, adj, feat)
+    np.testing.assert_allclose(npy(a), oa, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(npy(out), oo, rtol=1e-4, atol=1e-5)
+    # rows without neighbours aggregate to exactly zero
+    iso = adj.sum(-1) == 0
+    assert iso.any() and np.all(npy(out)[iso] == 0)
+
+
+def test_edge_mlp(cuda):
+    S, N, U = 4, 32, 128
+    p = synth.init_params(seed=2)
+    rng = np.random.default_rng(6)
+    pos, _, valid = synth.make_crowd(S, N, seed=23, half_extent=4.0, ragged=True)
+    _, adj, _ = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
+    h = (rng.standard_normal((S, N, U)) * 0.5).astype(np.float32)
+    sc = ops.edge_mlp(dev(h, cuda), dev(adj, cuda), dev(p["W1"], cuda), dev(p["b1"], cuda), dev(p["W2"], cuda),
+                      dev(p["b2"], cuda), dev(p["w_out"], cuda), dev(p["b_out"].reshape(1), cuda))
+    osc = o_b.edge_mlp(h, adj, p)
+    assert adj.sum() > 0
+    np.testing.assert_allclose(npy(sc), osc, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+def _cell_inputs(R, seed=0):
+    rng = np.random.default_rng(seed)
+    U = 128
+    x = (rng.standard_normal((R, 4)) * 0.3).astype(np.float32)
+    h, c, mh, mc = ((rng.standard_normal((R, U)) * 0.5).astype(np.float32) for _ in range(4))
+    valid = (rng.random(R) > 0.1).astype(np.uint8)
+    cur = rng.standard_normal((R, 2)).astype(np.float32)
+    return x, h, c, mh, mc, valid, cur
+
+
+@pytest.mark.parametrize("R", [64, 200, 1000])
+def test_gsk_cell_fp32(cuda, R):
+    """fp32 parity mode: 1e-4 relative (north_star tolerance) against the fp32 oracle."""
+    p = synth.init_params(seed=1)
+    x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R)
+    P = ops.CellParams.from_numpy(p, cuda)
+    ho, co, mf, par, nxt = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, ops.PREC_F32,
+                                        cur_pos=dev(cur, cuda), want_head=True)
+    oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
+    for got, want in ((ho, oh), (co, oc), (mf, of)):
+        assert rel_err(npy(got), want[0]) < 1e-4
+    oy = o_b.head(oh, of, p)[0] * valid[:, None]
+    assert rel_err(npy(par), oy) < 1e-4
+    np.testing.assert_allclose(npy(nxt), cur + oy[:, :2], rtol=1e-5, atol=1e-6)
+    assert np.all(npy(ho)[valid == 0] == 0)
+
+
+@pytest.mark.parametrize("R", [128, 200, 1000, 128 * 300 + 17])
+def test_gsk_cell_bf16_tensor_core(cuda, R):
+    """tcgen05 path: bf16 operands, fp32 accumulate, approx tanh -- tolerance stated separately
+    (north_star): |err| <= 2e-2 absolute on O(1) states, and it must agree with an oracle that
+    rounds the GEMM operands to bf16 to 5e-3."""
+    p = synth.init_params(seed=1)
+    x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R + 1)
+    P = ops.CellParams.from_numpy(p, cuda)
+    ho, co, mf, par, nxt = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, ops.PREC_BF16,
+                                        cur_pos=dev(cur, cuda), want_head=True)
+    torch.cuda.synchronize()
+    oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
+    for got, want in ((ho, oh), (co, oc), (mf, of)):
+        assert np.abs(npy(got) - want[0]).max() < 2e-2
+
+    def bf(a):
+        return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
+    # oracle with bf16-rounded operands (e is rounded after the relu, as the kernel does)
+    e = np.maximum(x @ p["W_e"] + p["b_e"], 0).astype(np.float32)
+    u = np.concatenate([bf(e), bf(h), bf(mh)], -1)
+    z = u @ bf(p["W"]) + p["b"]
+    U = 128
+    g = o_b.sigmoid(z[:, :U] + p["w_If"] * mc + p["w_It"] * c)
+    tj = np.tanh(z[:, U:2 * U])
+    c_t = (1 - g) * c + g * tj
+    c_f = (1 - g) * mc + g * tj
+    q = o_b.sigmoid(z[:, 2 * U:] + p["w_Of"] * c_f + p["w_Ot"] * c_t)
+    m_t = q * np.tanh(c_t) * valid[:, None]
+    assert np.abs(npy(ho) - m_t).max() < 5e-3
+    assert np.abs(npy(co) - c_t * valid[:, None]).max() < 5e-3
+    oy = o_b.head(oh, of, p)[0] * valid[:, None]
+    assert np.abs(npy(par) - oy).max() < 2e-2
+
+
+def test_gridlstm_reference_instantiation(cuda):
+    """GridLSTMCell exactly as helper.py:31-39 builds it (U=2, F = D/4) with the checkpoint's parameters."""
+    g = np.load(GOLD / "track_a_ckpt.npz")
+    W_f, B_f = g["glstm_W_f_0_0"], g["glstm_B_f_0"]
+    pe = [g["glstm_W_I_diag_freqf_0"], g["glstm_W_I_diag_freqt_0"], g["glstm_W_O_diag_freqf_0"],
+          g["glstm_W_O_diag_freqt_0"]]
+    rng = np.random.default_rng(0)
+    for D, F, peep in ((16, 4, True), (10, 2, True), (16, 2, False)):
+        inputs = rng.standard_normal((D, D))
+        state = rng.standard_normal((D, 128)) * 0.5
+        om, os_ = o_gl.gridlstm_step(inputs, state, W_f, B_f, *pe, U=2, F=F, peepholes=peep)
+        f32 = lambda a: dev(np.asarray(a, np.float32), cuda)  # noqa: E731
+        m, s = ops.gridlstm_step(f32(inputs), f32(state), f32(W_f), f32(B_f), *(f32(a) for a in pe), U=2, F=F,
+                                 peepholes=peep)
+        assert rel_err(npy(m), om) < 1e-4 and rel_err(npy(s), os_) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+def _track_a_weights(n, D, T, P, rng, gold=None):
+    if gold is not None:   # TF-1.14 seed-0 tensors from the reference's checkpoints (D=10, T=8, P=12)
+        w = dict(W_v=gold["seed0_weight_v"], b_v=gold["seed0_bias_v"], W_r=gold["seed0_weight_r"],
+                 W_c=gold["seed0_weight_c"], W_ii=gold["seed0_weight_ii"])
+    else:
+        w = dict(W_v=rng.standard_normal((T, D + 2)), b_v=rng.standard_normal(D), W_r=rng.standard_normal((T, 2)),
+                 W_c=rng.standard_normal((2 * P, T)), W_ii=rng.standard_normal((D, T)))
+    w["W_i"] = rng.standard_normal((n, D))
+    w["W_o"] = rng.standard_normal((T, n))
+    return w
+
+
+@pytest.mark.parametrize("S,n,D,use_gold", [(6, 9, 10, True), (33, 64, 16, False), (4, 8, 16, False)])
+def test_track_a_mcr_step(cuda, S, n, D, use_gold):
+    T, P, H, lam = 8, 12, 128, 0.0005
+    rng = np.random.default_rng(S)
+    gold = np.load(GOLD / "track_a_ckpt.npz") if use_gold else None
+    w = _track_a_weights(n, D, T, P, rng, gold)
+    X = np.abs(rng.standard_normal((S, T, n)))
+    V = rng.standard_normal((S, 2, n))
+    Cm = rng.standard_normal((S, D, D)) * 100
+    Hs = rng.standard_normal((S, D, H))
+    want = o_a.mcr_scene_loop(X, V, Cm, Hs, w, lam, P)
+    f32 = lambda a: dev(np.asarray(a, np.float32), cuda)  # noqa: E731
+    got = ops.mcr_step(f32(X), f32(V), f32(Cm), f32(Hs), {k: f32(v) for k, v in w.items()}, lam, P, variant=0)
+    for k in ("attn", "cost", "band", "Hs", "vemb"):
+        assert rel_err(npy(got[k]), want[k]) < 1e-4, k
+    np.testing.assert_allclose(npy(got["adj"]), want["adj"][..., 0], rtol=1e-5)
+    assert np.abs(npy(got["adj"]) - 1).max() < 1e-5          # defect F-10: adjacency == 1
+    assert rel_err(npy(got["pred"]), want["pred"]) < 1e-4     # [S,n,P,2]
+    # second frame: carried vemb_prev and Hs
+    want2 = np.stack([o_a.mcr_scene_step(X[s], V[s] * 0.5, Cm[s], want["Hs"][s], w, lam, P, vemb_prev=want["vemb"][s])["attn"]
+                      for s in range(S)])
+    got2 = ops.mcr_step(f32(X), f32(V * 0.5), f32(Cm), got["Hs"], {k: f32(v) for k, v in w.items()}, lam, P,
+                        variant=0, vemb_prev=got["vemb"])
+    assert rel_err(npy(got2["attn"]), want2) < 1e-4
+    # g2k_lstm_mc variant: cost == 0, band == 0 exactly (models/g2k_lstm_mc.py:59-69)
+    mc = ops.mcr_step(f32(X), f32(V), f32(Cm), f32(Hs), {k: f32(v) for k, v in w.items()}, lam, P, variant=1)
+    assert float(mc["band"].abs().max()) == 0.0 and float(mc["cost"].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+def _decode_inputs(S, N, P, K, seed):
+    rng = np.random.default_rng(seed)
+    par = np.zeros((S, N, P, 5), np.float32)
+    par[..., :2] = rng.standard_normal((S, N, P, 2)) * 0.2
+    par[..., 2:4] = np.exp(rng.standard_normal((S, N, P, 2)) * 0.3 - 1.5)
+    par[..., 4] = np.tanh(rng.standard_normal((S, N, P)))
+    eps = rng.standard_normal((S, N, K, P, 2)).astype(np.float32)
+    last = rng.standard_normal((S, N, 2)).astype(np.float32)
+    gt = (last[:, :, None] + np.cumsum(rng.standard_normal((S, N, P, 2)) * 0.2, 2)).astype(np.float32)
+    valid = (rng.random((S, N)) > 0.15).astype(np.uint8)
+    return par.astype(np.float32), eps, last, gt, valid
+
+
+@pytest.mark.parametrize("S,N,P,K", [(9, 64, 12, 20), (3, 16, 12, 1), (5, 20, 8, 32), (2, 7, 12, 20)])
+def test_decode_score_bit_exact(cuda, S, N, P, K):
+    par, eps, last, gt, valid = _decode_inputs(S, N, P, K, seed=S * 7 + K)
+    o = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, eps=dev(eps, cuda))
+    ade, fde, best, bt, _ = o_b.decode_score(par, eps, last, gt, valid)
+    assert np.array_equal(npy(o["best_k"]), best)                       # bit-exact best-of-K
+    assert np.array_equal(npy(o["ade"]), ade) and np.array_equal(npy(o["fde"]), fde)   # fp32 bit-exact too
+    assert np.array_equal(npy(o["best_traj"]), bt)
+    bsel = np.take_along_axis(ade, np.maximum(best, 0)[..., None], -1)[..., 0] * valid
+    assert np.array_equal(npy(o["best_ade"]), bsel)
+
+
+def test_decode_ties_pick_lowest_k(cuda):
+    S, N, P, K = 1, 8, 12, 20
+    par, eps, last, gt, valid = _decode_inputs(S, N, P, K, seed=1)
+    eps[:] = eps[:, :, :1]       # all samples identical -> every ADE ties -> k* = 0
+    valid[:] = 1
+    o = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, eps=dev(eps, cuda))
+    assert np.all(npy(o["best_k"]) == 0)
+
+
+def test_decode_philox_matches_oracle_noise(cuda):
+    S, N, P, K = 6, 32, 12, 20
+    par, _, last, gt, valid = _decode_inputs(S, N, P, K, seed=4)
+    seed, off = 0x1234_5678_9ABC, 1000
+    d = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, seed=seed,
+                         agent_offset=off, dump_eps=True)
+    eps_gpu = npy(d["eps"])
+    eps_cpu = o_b.philox_eps(seed, S, N, K, P, agent_offset=off)
+    np.testing.assert_allclose(eps_gpu, eps_cpu, rtol=0, atol=2e-5)     # integer stream exact; logf/sincosf ulps
+    assert abs(float(eps_gpu.mean())) < 0.02 and abs(float(eps_gpu.std()) - 1) < 0.02
+    # Philox mode == fed mode on the noise the kernel itself drew (same code path -> bit-exact)
+    a = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, seed=seed, agent_offset=off)
+    b = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, eps=d["eps"])
+    assert torch.equal(a["best_k"], b["best_k"]) and torch.equal(a["ade"], b["ade"])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_scene_batch_matches_oracle_and_reference_loader(cuda):
+    g = np.load(GOLD / "zara01_slice.npz")
+    csv = g["csv"][:, :int(g["max"])]                 # the reference's 70% training split (load_traj.py:125-134)
+    fid, rs, ped, xy, vis = o_sb.table_from_csv(csv)
+    # the table holds exactly the rows the reference's own DataLoader put in its frame dictionary
+    ref = g["traj_rows"]
+    order = np.lexsort((ref[:, 1], ref[:, 0]))
+    assert np.array_equal(ref[order, 1].astype(np.int32), ped)
+    np.testing.assert_allclose(ref[order, 2:4], xy, rtol=1e-6)
+    F, N, stride = 20, 16, 8
+    wins = fid[:-F:3].astype(np.int32)
+    want = o_sb.scene_batch(fid, rs, ped, xy, vis, wins, N, F, stride)
+    got = ops.scene_batch(dev(fid, cuda), dev(rs, cuda), dev(ped, cuda), dev(xy, cuda), dev(vis, cuda),
+                          dev(wins, cuda), N, F, stride)
+    assert want[2].sum() > 0
+    assert np.array_equal(npy(got[2]), want[2]) and np.array_equal(npy(got[3]), want[3])     # mask, slots bit-exact
+    assert np.array_equal(npy(got[0]), want[0]) and np.array_equal(npy(got[1]), want[1])
+    # N smaller than the crowd: slot overflow is truncated identically
+    want = o_sb.scene_batch(fid, rs, ped, xy, None, wins, 2, 8, stride)
+    got = ops.scene_batch(dev(fid, cuda), dev(rs, cuda), dev(ped, cuda), dev(xy, cuda), None, dev(wins, cuda), 2, 8, stride)
+    assert np.array_equal(npy(got[2]), want[2]) and np.array_equal(npy(got[0]), want[0])
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("relational", [False, True])
+@pytest.mark.parametrize("S,N", [(6, 64), (3, 16)])
+def test_forecast_fp32_matches_oracle(cuda, S, N, relational):
+    """Whole path, fp32 mode: predicted positions within 1e-4 relative, ADE/FDE within 1e-3, best-of-K exact
+    when the GPU's own parameters are scored (noise supplied)."""
+    T, P, K = 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=77, half_extent=4.0, ragged=True)
+    p = synth.init_params(seed=3)
+    eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
+    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=relational, prec=ops.PREC_F32,
+                        device=cuda, want_all=True)
+    o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+    torch.cuda.synchronize()
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=relational)
+    got_par = npy(o["params"])
+    assert rel_err(np.cumsum(got_par[..., :2], 2) + pos[:, :, T - 1:T], want["pred_mean"]) < 1e-4
+    assert rel_err(got_par, want["params"]) < 2e-4
+    assert np.abs(npy(o["ade"]) - want["ade"]).max() < 1e-3 and np.abs(npy(o["fde"]) - want["fde"]).max() < 1e-3
+    # integer parity: score the GPU's parameters with the oracle's decode -> identical argmin
+    _, _, best, bt, _ = o_b.decode_score(got_par, eps, pos[:, :, T - 1], pos[:, :, T:], valid)
+    assert np.array_equal(npy(o["best_k"]), best) and np.array_equal(npy(o["best_traj"]), bt)
+
+
+def test_forecast_bf16_tensor_core(cuda):
+    """bf16/tcgen05 mode, stated separately: mean-trajectory error vs the fp32 oracle."""
+    S, N, T, P, K = 8, 64, 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0, ragged=True)
+    p = synth.init_params(seed=3)
+    eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
+    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, prec=ops.PREC_BF16, device=cuda, want_all=True)
+    o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+    torch.cuda.synchronize()
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P)
+    got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
+    assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
+    assert np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max() < 5e-2
