@@ -82,7 +82,7 @@ int mmt_edge_mlp_f32(const float* h, const uint8_t* adj, const float* W1, const 
  * If W_h != NULL also the head: y = [m_t|m_f] W_h + b_h -> params_out[R*params_stride .. +5]
  * = (mu_x, mu_y, exp(.), exp(.), tanh(.)) and next_pos[R,2] = cur_pos + (mu_x, mu_y).
  * prec = MMT_PREC_F32 (W fp32 [E+2U,3U]) or MMT_PREC_BF16 (W_packed from mmt_pack_gate_weights_bf16).
- * In-place h_out==h, c_out==c is allowed. */
+ * h_out / c_out must not alias h / c (other CTAs re-read the input rows). */
 typedef struct mmt_cell_weights {
   const float* W_e;   /* [4,E]      */
   const float* b_e;   /* [E]        */

@@ -101,8 +101,9 @@ int launch_aggregate(const float* logits, const float* logits2, const uint8_t* a
 extern "C" int mmt_aggregate_f32(const float* logits, const uint8_t* adj, const float* feat, int S, int N, int C,
                                  float* attn, float* out, void* stream) {
   using namespace mmt;
-  MMT_REQUIRE(logits && adj && feat && out, "logits/adj/feat/out must not be NULL");
   MMT_REQUIRE(S >= 0 && N > 0 && N <= 1024 && C > 0 && C % 4 == 0, "need 0 < N <= 1024, C % 4 == 0");
+  if (S == 0) return MMT_OK;
+  MMT_REQUIRE(logits && adj && feat && out, "logits/adj/feat/out must not be NULL");
   MMT_ALIGNED(feat);
   MMT_ALIGNED(out);
   if (S == 0) return MMT_OK;

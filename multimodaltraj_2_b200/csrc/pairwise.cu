@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(256) neighbor_index_kernel(const uint8_t* __re
 extern "C" int mmt_pairwise_adj_f32(const float* pos, const uint8_t* valid, int S, int N, float r2,
                                     float inv_2sigma2, float* kern, uint8_t* adj, int32_t* deg, void* stream) {
   using namespace mmt;
-  MMT_REQUIRE(pos && valid, "pos/valid must not be NULL");
   MMT_REQUIRE(S >= 0 && N > 0 && N % 4 == 0 && N <= 1024, "need S >= 0, 0 < N <= 1024, N % 4 == 0");
+  if (S == 0) return MMT_OK;  // empty batch: nothing to read or write
+  MMT_REQUIRE(pos && valid, "pos/valid must not be NULL");
   MMT_ALIGNED(pos);
   MMT_ALIGNED(kern);
   if (adj && (reinterpret_cast<uintptr_t>(adj) & 3u)) {
@@ -152,8 +153,9 @@ extern "C" int mmt_pairwise_adj_f32(const float* pos, const uint8_t* valid, int 
 extern "C" int mmt_neighbor_index_i32(const uint8_t* adj, int S, int N, int max_nbr, int32_t* nbr, int32_t* cnt,
                                       void* stream) {
   using namespace mmt;
-  MMT_REQUIRE(adj && nbr && cnt, "adj/nbr/cnt must not be NULL");
   MMT_REQUIRE(S >= 0 && N > 0 && max_nbr > 0, "need S >= 0, N > 0, max_nbr > 0");
+  if (S == 0) return MMT_OK;
+  MMT_REQUIRE(adj && nbr && cnt, "adj/nbr/cnt must not be NULL");
   if (S == 0) return MMT_OK;
   const long rows = (long)S * N;
   long blocks = (rows + 7) / 8;

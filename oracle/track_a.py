@@ -58,7 +58,8 @@ def embeddings(X, V, W_i, W_ii, vemb_prev=None):
 
 def stat_mask(D, T, dtype=np.float64):
     """A.3 (train.py:154-155): every row = [0, 1/T, ..., (T-1)/T]."""
-    return np.zeros((D, T), dtype) + (np.arange(T, dtype=dtype) / dtype(T))[None, :]
+    dt = np.dtype(dtype)
+    return np.zeros((D, T), dt) + (np.arange(T, dtype=dt) / dt.type(T))[None, :]
 
 
 def static_context(C, lam, T):
