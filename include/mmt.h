@@ -137,6 +137,29 @@ int mmt_mcr_step_f32(const float* X, const float* V, const float* C, const float
                      int P, int H, float lam, int variant, float* attn, float* cost, float* band,
                      float* Hs_out, float* adj, float* vemb_out, void* stream);
 
+/* g2k_lstm_mcr.forward alone (models/g2k_lstm_mcr.py:99-124) on caller-built placeholders, S scenes:
+ * outputs[S,D+2,D] rel[S,2,D] ngh[S,D,T] -> attn[S,D,D] cost[S,T,T] band[S,2,P,n] (any may be NULL).
+ * variant 1 = g2k_lstm_mc (cost := 0). */
+int mmt_mcr_forward_f32(const float* outputs, const float* rel, const float* ngh, const mmt_mcr_weights* w,
+                        int S, int n, int D, int T, int P, float lam, int variant, float* attn, float* cost,
+                        float* band, void* stream);
+
+/* ---- reference-compatible scores -----------------------------------------------------------------------
+ * mmt_mean_error_f32: sample.get_mean_error (sample.py:21-82) value for value.  predicted/truth [n,L,2]
+ * agent-major; out3 = (ade, fde, counter): signed errors are summed over the first maxNumPeds agents per
+ * step before the norm (reference defect F-8), steps observed_length..L-1 only.
+ * mmt_train_val_scores_f32: train.py:639-674 per agent: euc_i = sigma_max(pred_i[:L_i]-tgt_i[:L_i])/12
+ * (np.linalg.norm(M, ord=2) of a matrix is the spectral norm; short tracks also / n_targets),
+ * err_i = last row of the difference.  pred/tgt [n,P,2], len[n]. */
+int mmt_mean_error_f32(const float* predicted, const float* truth, int n, int L, int observed_length,
+                       int maxNumPeds, float* out3, void* stream);
+int mmt_train_val_scores_f32(const float* pred, const float* tgt, const int32_t* len, int n, int P,
+                             int n_targets, float* euc, float* err, void* stream);
+
+/* nri_learned.infer_rlns (sigmoid, nri_learned.py:16-21) and eval_rln_ngh (row softmax, :23-28) */
+int mmt_sigmoid_f32(const float* x, float* y, size_t n, void* stream);
+int mmt_rowsoftmax_f32(const float* x, float* y, int rows, int cols, void* stream);
+
 /* ---- K-sample bivariate-Gaussian decode + ADE/FDE + best-of-K (one fused epilogue) ---------------
  * Replaces the scoring of train.py:639-674 / sample.py:21-82 (which score tf.random_normal,
  * SURVEY F4) with the decode the north_star names.  params[S,N,P,5] activated

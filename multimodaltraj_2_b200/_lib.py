@@ -54,6 +54,12 @@ SIGNATURES = {
                                         C.c_int, vp, vp, vp]),
     "mmt_mcr_step_f32": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(McrWeights), C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "mmt_mcr_forward_f32": (C.c_int, [vp, vp, vp, C.POINTER(McrWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, C.c_int, vp, vp, vp, vp]),
+    "mmt_mean_error_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "mmt_train_val_scores_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "mmt_sigmoid_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "mmt_rowsoftmax_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "mmt_decode_score_f32": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                        C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "mmt_decode_score_dump_eps_f32": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_int, C.c_int, C.c_int,

@@ -284,3 +284,65 @@ class Forecaster:
                                              _p(o["best_ade"]), _p(o["best_fde"]), _p(o["best_traj"]), _p(self.work),
                                              self.work.numel(), _stream()), "mmt_forecast_f32")
         return o
+
+
+# --------------------------------------------------------------------------------------------
+# reference-compatible pieces (Track A forward alone, scores, relational helpers)
+def mcr_forward(outputs, rel, ngh, w: dict, lam, n, P=12, variant=0):
+    """g2k_lstm_mcr.forward alone on caller-built placeholders.  outputs[S,D+2,D] rel[S,2,D] ngh[S,D,T]."""
+    lib = _lib.load()
+    for nm, t in dict(outputs=outputs, rel=rel, ngh=ngh).items():
+        _chk(t, torch.float32, nm)
+    S, D = outputs.shape[0], outputs.shape[2]
+    T = ngh.shape[2]
+    dev = outputs.device
+    out = dict(attn=torch.empty((S, D, D), dtype=torch.float32, device=dev),
+               cost=torch.empty((S, T, T), dtype=torch.float32, device=dev),
+               band=torch.empty((S, 2, P, n), dtype=torch.float32, device=dev))
+    cw = _lib.McrWeights()
+    for k in ("W_v", "b_v", "W_r", "W_c", "W_o"):
+        setattr(cw, k, _chk(w[k], torch.float32, k).data_ptr())
+    _lib.check(lib.mmt_mcr_forward_f32(_p(outputs), _p(rel), _p(ngh), C.byref(cw), S, n, D, T, P, float(lam), variant,
+                                       _p(out["attn"]), _p(out["cost"]), _p(out["band"]), _stream()),
+               "mmt_mcr_forward_f32")
+    return out
+
+
+def mean_error(predicted, truth, observed_length, maxNumPeds):
+    """sample.get_mean_error on device: predicted/truth [n,L,2] -> tensor (ade, fde, counter)."""
+    lib = _lib.load()
+    _chk(predicted, torch.float32, "predicted"); _chk(truth, torch.float32, "truth")
+    n, L, _ = predicted.shape
+    out = torch.empty((3,), dtype=torch.float32, device=predicted.device)
+    _lib.check(lib.mmt_mean_error_f32(_p(predicted), _p(truth), n, L, observed_length, maxNumPeds, _p(out), _stream()),
+               "mmt_mean_error_f32")
+    return out
+
+
+def train_val_scores(pred, tgt, lens, n_targets):
+    """train.py:639-674 per-agent scores: pred/tgt [n,P,2], lens[n] i32 -> (euc[n], err[n,2])."""
+    lib = _lib.load()
+    _chk(pred, torch.float32, "pred"); _chk(tgt, torch.float32, "tgt"); _chk(lens, torch.int32, "lens")
+    n, P, _ = pred.shape
+    euc = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    err = torch.empty((n, 2), dtype=torch.float32, device=pred.device)
+    _lib.check(lib.mmt_train_val_scores_f32(_p(pred), _p(tgt), _p(lens), n, P, n_targets, _p(euc), _p(err), _stream()),
+               "mmt_train_val_scores_f32")
+    return euc, err
+
+
+def sigmoid(x):
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    _lib.check(lib.mmt_sigmoid_f32(_p(x), _p(y), x.numel(), _stream()), "mmt_sigmoid_f32")
+    return y
+
+
+def rowsoftmax(x):
+    lib = _lib.load()
+    _chk(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    _lib.check(lib.mmt_rowsoftmax_f32(_p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], _stream()),
+               "mmt_rowsoftmax_f32")
+    return y

@@ -1,0 +1,109 @@
+"""CPU tests of the host-side logic: DataLoader mirror vs what the reference's own DataLoader
+produced (golden fixture), the scene-batching oracle, sharding, graph construction, and a
+world_size-2 gloo run of the scene-sharded scoring."""
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import scene_batch as o_sb  # noqa: E402
+
+G = np.load(ROOT / "tests" / "golden" / "zara01_slice.npz")
+ARGS = types.SimpleNamespace(batch_size=16, seq_length=12, pred_len=12, obs_len=8)
+
+
+def _loader():
+    from multimodaltraj_2_b200.load_traj import DataLoader
+    return DataLoader(ARGS, datasets=[0, 1, 2, 3, 4], sel=0, start=2, csv=G["csv"])
+
+
+def test_dataloader_matches_reference_dataloader():
+    dl = _loader()
+    assert dl.num_batches == int(G["num_batches"]) and dl.max == int(G["max"]) and dl.val_max == int(G["val_max"])
+    assert dl.seed == float(G["seed"]) and dl.len == G["csv"].shape[1]
+    rows = np.array([(fr, p, pos[0], pos[1]) for fr, lst in dl.trajectories.items() for it in lst
+                     for p, pos in it.items()])
+    ref = G["traj_rows"]
+    assert np.array_equal(rows[np.lexsort((rows[:, 1], rows[:, 0]))], ref[np.lexsort((ref[:, 1], ref[:, 0]))])
+    for c in range(3):
+        batch, targets, fp = dl.next_step()
+        assert np.array_equal(np.array(sorted(batch), float), G[f"batch{c}_frames"])
+        assert fp == float(G[f"batch{c}_fp"]) and len(targets) == int(G[f"batch{c}_n_targets"])
+        assert np.array_equal(np.array([len(v) for v in targets.values()]), G[f"batch{c}_target_lens"])
+    dl.reset_data_pointer()
+    assert dl.frame_pointer == dl.seed
+
+
+def test_construct_graph_node_arrays():
+    from multimodaltraj_2_b200.networkx_graph import online_graph
+    dl = _loader()
+    batch, targets, _ = dl.next_step()
+    g = online_graph(ARGS).ConstructGraph(current_batch=batch, framenum=1, future_traj=targets)
+    pl = g.get_node_attr('node_pos_list')
+    arr = np.array(list(pl.values()))
+    assert arr.ndim == 3 and arr.shape[1:] == (8, 2) and len(pl) == len(set(pl))
+    # first sighting leaves a zero row (reference defect F-5): frame 0's row is zero for peds first seen in frame 0
+    first = next(iter(batch.values()))
+    (ped0, _), = first[0].items()
+    assert np.all(pl[int(ped0)][0] == 0)
+
+
+def test_scene_batch_oracle_rules():
+    csv = G["csv"][:, :int(G["max"])]
+    fid, rs, ped, xy, vis = o_sb.table_from_csv(csv)
+    assert np.all(np.diff(fid) > 0) and rs[-1] == csv.shape[1]
+    pos, vo, valid, slot = o_sb.scene_batch(fid, rs, ped, xy, vis, fid[:5], 8, 4, 8)
+    for s in range(5):
+        ids = slot[s][valid[s] == 1]
+        assert np.all(np.diff(ids) > 0)                         # ascending ped id
+        for k, p in enumerate(ids):                              # every slot really is that ped in every frame
+            for f in range(4):
+                col = np.where((csv[0] == fid[s] + 8 * f) & (csv[1] == p))[0]
+                assert len(col) == 1 and np.allclose(pos[s, k, f], csv[2:4, col[0]])
+    # a window that runs off the end has no valid agents
+    _, _, v, _ = o_sb.scene_batch(fid, rs, ped, xy, None, fid[-1:], 8, 4, 8)
+    assert v.sum() == 0
+
+
+def test_shard_range_partitions_scenes():
+    from multimodaltraj_2_b200.train import shard_range
+    for n in (0, 1, 7, 4096):
+        for w in (1, 2, 4, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def _gloo_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import track_b as o_b
+    from multimodaltraj_2_b200 import synth
+    from multimodaltraj_2_b200.train import shard_range
+    S, N, T, P, K = 6, 8, 8, 12, 4
+    pos, vis, valid = synth.make_crowd(S, N, seed=3, half_extent=3.0, ragged=True)
+    p = synth.init_params(seed=2)
+    lo, hi = shard_range(S, rank, world)
+    eps = o_b.philox_eps(9, S, N, K, P)[lo:hi]                  # global agent indexing == agent_offset = lo*N
+    o = o_b.forecast(pos[lo:hi], vis[lo:hi], valid[lo:hi], p, eps, T, P)
+    sel = np.take_along_axis(o["ade"], np.maximum(o["best_k"], 0)[..., None], -1)[..., 0]
+    sums = torch.tensor([float(sel.sum()), float(valid[lo:hi].sum())], dtype=torch.float64)
+    torch.distributed.all_reduce(sums)
+    if rank == 0:
+        full = o_b.forecast(pos, vis, valid, p, o_b.philox_eps(9, S, N, K, P), T, P)
+        fsel = np.take_along_axis(full["ade"], np.maximum(full["best_k"], 0)[..., None], -1)[..., 0]
+        ret["ok"] = bool(abs(float(sums[0]) - float(fsel.sum())) < 1e-4 and int(sums[1]) == int(valid.sum()))
+    torch.distributed.destroy_process_group()
+
+
+def test_scene_sharding_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_gloo_worker, args=(2, 29533, ret), nprocs=2, join=True)
+        assert ret.get("ok") is True

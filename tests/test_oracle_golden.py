@@ -1,0 +1,152 @@
+"""CPU tests: the oracle against the golden vectors decoded from the reference's own checkpoints,
+against published known-answer vectors (Philox), and against its structural identities."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import gridlstm as o_gl  # noqa: E402
+import scores as o_sc  # noqa: E402
+import track_a as o_a  # noqa: E402
+import track_b as o_b  # noqa: E402
+
+GOLD = np.load(ROOT / "tests" / "golden" / "track_a_ckpt.npz")
+
+
+def test_band_first_matmul_matches_tf_evaluated_checkpoint():
+    """models/g2k_lstm_mcr.py:122: the checkpoint holds W_c, cost and TF's own W_c @ cost."""
+    n = int(GOLD["n_wc"])
+    assert n == 5
+    for k in range(n):
+        W_c, cost, want = GOLD[f"wc_{k}_W_c"], GOLD[f"wc_{k}_cost"], GOLD[f"wc_{k}_out"]
+        W_o = np.eye(8)                                # isolate the first matmul of the band
+        got = o_a.mcr_forward(np.zeros((12, 10)), np.zeros((2, 10)), np.zeros((10, 8)), np.zeros((8, 12)),
+                              np.zeros(10), np.zeros((8, 2)), W_c, W_o, 0.0005)
+        # cost is recomputed inside mcr_forward from Eo/ngh; check the matmul itself on the saved cost
+        assert np.abs(W_c @ cost - want).max() < 1e-15
+        assert got["band"].shape == (2, 12, 8)
+
+
+def test_mcr_forward_chain_and_shapes_with_seed0_weights():
+    rng = np.random.default_rng(0)
+    D, T, P, n, lam = 10, 8, 12, 9, 0.0005
+    w = dict(W_v=GOLD["seed0_weight_v"], b_v=GOLD["seed0_bias_v"], W_r=GOLD["seed0_weight_r"],
+             W_c=GOLD["seed0_weight_c"], W_ii=GOLD["seed0_weight_ii"], W_i=GOLD["seed0_weight_i_9x10"],
+             W_o=rng.standard_normal((T, n)))
+    assert w["W_v"].shape == (T, D + 2) and w["W_c"].shape == (2 * P, T) and w["W_r"].shape == (T, 2)
+    X, V = np.abs(rng.standard_normal((T, n))), rng.standard_normal((2, n))
+    C, Hs = rng.standard_normal((D, D)) * 100, rng.standard_normal((D, 128))
+    r = o_a.mcr_scene_step(X, V, C, Hs, w, lam, P)
+    # the as-written algebra, spelled out independently
+    I = w["W_ii"] @ (X @ w["W_i"])
+    vemb = V @ w["W_i"]
+    outputs = np.vstack([I, vemb])
+    ngh = lam * ((lam * C) @ o_a.stat_mask(D, T))
+    Eo = w["W_v"] @ outputs + w["b_v"]
+    np.testing.assert_allclose(r["attn"], ngh @ (Eo * (w["W_r"] @ (vemb * vemb))), rtol=1e-12)
+    np.testing.assert_allclose(r["cost"], Eo @ ngh, rtol=1e-12)
+    np.testing.assert_allclose(r["band"].reshape(2 * P, n), (w["W_c"] @ (Eo @ ngh)) @ w["W_o"], rtol=1e-12)
+    assert r["pred"].shape == (n, P, 2) and np.array_equal(r["pred"][3, 5], r["band"][:, 5, 3])
+    # scale statistics recorded in the checkpoint: ngh' = lambda * N(0,1) placeholder -> std ~ 6e-4
+    assert abs(GOLD["fwd_ngh_scaled"].std() / 0.0005 - 1.0) < 0.3
+    # structural identities of the per-frame state step (defects F-9/F-10)
+    assert np.abs(r["adj"] - 1).max() < 1e-12
+    np.testing.assert_allclose(r["a"].sum(-1), 1.0, rtol=1e-12)
+    a2, Hs2, adj2 = o_a.frame_state_step(r["attn"], r["Hs"])
+    np.testing.assert_allclose(Hs2.sum(-1), 1.0, rtol=1e-9)          # rows of a @ softmax(Hs) stay stochastic
+
+
+def test_mc_band_is_zero_as_in_the_saved_checkpoint():
+    assert float(np.abs(GOLD["mc_temp_path_0"]).max()) == 0.0 and float(np.abs(GOLD["mc_temp_path_1"]).max()) == 0.0
+    rng = np.random.default_rng(1)
+    r = o_a.mc_forward(rng.standard_normal((12, 10)), rng.standard_normal((10, 8)), GOLD["seed0_weight_v"],
+                       GOLD["seed0_bias_v"], GOLD["seed0_weight_c"], rng.standard_normal((8, 7)))
+    assert r["band"].shape == (2, 12, 7) and float(np.abs(r["band"]).max()) == 0.0
+
+
+def test_gsk_forward_only_consistent_shape():
+    rng = np.random.default_rng(2)
+    D, n = 10, 6
+    r = o_a.gsk_forward(rng.standard_normal((D, D)), rng.standard_normal((12, D)), rng.standard_normal((12, D)),
+                        rng.standard_normal(D), rng.standard_normal((16, 12)), rng.standard_normal((D, n)))
+    assert r["band"].shape == (2, 8, n) and np.all(r["cost"] == 1.0)
+
+
+def test_gridlstm_with_checkpoint_parameters():
+    W_f, B_f = GOLD["glstm_W_f_0_0"], GOLD["glstm_B_f_0"]
+    assert W_f.shape == (8, 6) and np.all(B_f == 0)
+    pe = [GOLD[k] for k in ("glstm_W_I_diag_freqf_0", "glstm_W_I_diag_freqt_0", "glstm_W_O_diag_freqf_0",
+                            "glstm_W_O_diag_freqt_0")]
+    rng = np.random.default_rng(3)
+    x, st = rng.standard_normal((16, 16)), rng.standard_normal((16, 128))
+    m, s = o_gl.gridlstm_step(x, st, W_f, B_f, *pe, U=2, F=4)
+    assert m.shape == (16, 16) and s.shape == (16, 16)
+    # block 0 by hand (m_f = c_f = 0)
+    z = np.concatenate([x[:, :4], st[:, 2:4], np.zeros((16, 2))], 1) @ W_f
+    g = o_gl.sigmoid(z[:, :2] + pe[1] * st[:, :2])
+    c_time = (1 - g) * st[:, :2] + g * np.tanh(z[:, 2:4])
+    np.testing.assert_allclose(s[:, :2], c_time, rtol=1e-12)
+    q = o_gl.sigmoid(z[:, 4:6] + pe[2] * (g * np.tanh(z[:, 2:4])) + pe[3] * c_time)
+    np.testing.assert_allclose(m[:, :2], q * np.tanh(c_time), rtol=1e-12)
+    # peepholes off == zero diagonals
+    z4 = [np.zeros(2)] * 4
+    a = o_gl.gridlstm_step(x, st, W_f, B_f, *pe, U=2, F=2, peepholes=False)
+    b = o_gl.gridlstm_step(x, st, W_f, B_f, *z4, U=2, F=2, peepholes=True)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+
+
+def test_philox_known_answer_vectors():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = o_b.philox4x32_10(*(np.array([c], np.uint32) for c in ctr), *key)
+        assert tuple(int(g[0]) for g in got) == want
+    e = o_b.philox_eps(7, 4, 8, 20, 12)
+    assert e.shape == (4, 8, 20, 12, 2) and abs(e.mean()) < 0.03 and abs(e.std() - 1) < 0.03
+
+
+def test_reference_scores():
+    rng = np.random.default_rng(4)
+    n, L, obs = 5, 20, 8
+    pred, true = rng.standard_normal((n, L, 2)), rng.standard_normal((n, L, 2))
+    ade, fde, counter = o_sc.get_mean_error(pred, true, obs, n)
+    err = (true - pred)[:, obs:].sum(0)                       # signed sum over agents per step
+    assert counter == (L - obs) * n
+    np.testing.assert_allclose(ade, np.mean(np.linalg.norm(err, axis=1) / counter), rtol=1e-12)
+    np.testing.assert_allclose(fde, np.mean(np.linalg.norm((true - pred)[:, -1], axis=1) / n), rtol=1e-12)
+    tg = [rng.standard_normal((12, 2)) for _ in range(n - 1)] + [rng.standard_normal((7, 2))]
+    p12 = rng.standard_normal((n, 12, 2))
+    a, f, euc, e = o_sc.train_val_scores(p12, tg)
+    assert euc[0] == pytest.approx(np.linalg.svd(p12[0] - tg[0], compute_uv=False)[0] / 12)
+    assert euc[-1] == pytest.approx(np.linalg.svd(p12[-1][:7] - tg[-1], compute_uv=False)[0] / n / 12)
+    assert f == pytest.approx(np.linalg.norm(e) / n)
+
+
+def test_track_b_invariants():
+    sys.path.insert(0, str(ROOT))
+    from multimodaltraj_2_b200 import synth
+    S, N, T, P, K = 3, 16, 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=5, half_extent=3.0, ragged=True)
+    kern, adj, deg = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
+    assert np.array_equal(adj, adj.transpose(0, 2, 1)) and adj[:, np.arange(N), np.arange(N)].sum() == 0
+    assert np.array_equal(deg, adj.sum(-1)) and np.all(adj[valid == 0] == 0)
+    a = o_b.masked_softmax(kern, adj)
+    np.testing.assert_allclose(a.sum(-1)[deg > 0], 1.0, rtol=1e-6)
+    assert np.all(a.sum(-1)[deg == 0] == 0)
+    p = synth.init_params(seed=1)
+    eps = o_b.philox_eps(1, S, N, K, P)
+    o = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=True)
+    assert np.all(o["best_k"][valid == 0] == -1) and np.all(o["best_k"][valid == 1] >= 0)
+    assert np.all(o["params"][valid == 0] == 0)
+    sel = np.take_along_axis(o["ade"], np.maximum(o["best_k"], 0)[..., None], -1)[..., 0]
+    assert np.all(sel[valid == 1] == o["ade"].min(-1)[valid == 1])
+    # scene-at-a-time (the reference's execution shape) == batched
+    lo = o_b.forecast_scene_loop(pos, vis, valid, p, eps, T=T, P=P, relational=True)
+    assert np.array_equal(lo["best_k"], o["best_k"])
+    np.testing.assert_allclose(lo["params"], o["params"], rtol=1e-5, atol=1e-6)
