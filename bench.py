@@ -155,7 +155,7 @@ def run_ours(args, rank, world, local_rank):
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
     fc = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(args.variant == "mcr"),
-                        prec=prec, seed=0xB200, agent_offset=rank * S * N, device=dev)
+                        prec=prec, seed=0xB200, agent_offset=rank * S * N, device=dev, use_graph=not args.no_graph)
     pos_p, vis_p, valid_p = (torch.from_numpy(a).pin_memory() for a in (pos_h, vis_h, valid_h))
     pos, vis, valid = pos_p.to(dev), vis_p.to(dev), valid_p.to(dev)
 
@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--variant", default="mc", choices=["mc", "mcr"])
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

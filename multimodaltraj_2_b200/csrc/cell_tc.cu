@@ -149,6 +149,8 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0
 
 struct TcArgs {
   const float *x, *h, *c, *mh, *mc;
+  const __nv_bfloat16 *hb, *mhb, *mcb;  // bf16-state mode: h, mh, mc as [R,U] bf16 (c stays fp32, row stride ld)
+  __nv_bfloat16* hb_out;
   const uint8_t* valid;
   const float *W_e, *b_e, *b, *w_If, *w_It, *w_Of, *w_Ot, *W_h, *b_h;
   const uint8_t* Wp;  // packed bf16 operand image
@@ -158,7 +160,25 @@ struct TcArgs {
   int R, ld, ld_mf, params_stride, num_tiles;
 };
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// State layouts.  LAY 0: fp32 row-major [R,ld] in/out (the mmt_gsk_cell API).  LAY 1: bf16 h/mh/mc, fp32 c,
+// row-major [R,U].  LAY 2: same types, TILE-BLOCKED [tile][U/8][128 rows][8 units]: the 8 units a thread owns
+// in the epilogue are contiguous and consecutive lanes (= consecutive rows) are adjacent, so every warp-level
+// global access of the epilogue and of the operand build is one contiguous 512 B / 1 KB segment instead of 32
+// scattered 16/32 B pieces (the L1TEX wavefront count was the limiter of the row-major version).
+__host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  // element offset, u % 8 == 0
+  return ((size_t)(tile * (TC_U / 8) + (u >> 3)) * TC_M + r) * 8;
+}
+
+template <int LAY>
 __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
+  constexpr bool BF = LAY != 0;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   // SWIZZLE_128B atoms need a 1024-byte aligned base; the launch adds 1 KB of slack for this
   uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -277,96 +297,176 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           *reinterpret_cast<uint4*>(smem + SM_A + sw128_off(r, k0 + kk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      // ---- h -> blocks 1,2 ; mh -> blocks 3,4.  one warp per row, lane -> 4 consecutive k
-      for (int rr = warp; rr < TC_M; rr += 8) {
-        const int gr = row0 + rr;
-        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), mv = hv;
-        if (gr < a.R) {
-          hv = *reinterpret_cast<const float4*>(a.h + (size_t)gr * a.ld + lane * 4);
-          mv = *reinterpret_cast<const float4*>(a.mh + (size_t)gr * a.ld + lane * 4);
-        }
-        const int k = lane * 4;                   // 0..124 within the 128-wide part
-        const int blk = k >> 6, kk = k & 63;
-        __nv_bfloat162 h01 = __floats2bfloat162_rn(hv.x, hv.y), h23 = __floats2bfloat162_rn(hv.z, hv.w);
-        __nv_bfloat162 m01 = __floats2bfloat162_rn(mv.x, mv.y), m23 = __floats2bfloat162_rn(mv.z, mv.w);
-        *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-        *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&m01), *reinterpret_cast<uint32_t*>(&m23));
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(A_READY);
-
-      // ---- epilogue
-      const int r = q * 32 + lane;  // row within tile == TMEM lane
+      const int r = q * 32 + lane;  // epilogue row within tile == TMEM lane
       const int gr = row0 + r;
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
-      float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < TC_NP; ++p, ++pc) {
-        const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
-        mbar_wait(ACC_FULL + 8 * b, bph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + b * TC_ACC_STRIDE;
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int ul = hsel * 16 + sub * 8;        // unit within pass
-          const int u = p * TC_UN + ul;              // global unit
-          float zi[8], zj[8], zo[8];
-          tmem_ld8(t_row + ul, zi);
-          tmem_ld8(t_row + TC_UN + ul, zj);
-          tmem_ld8(t_row + 2 * TC_UN + ul, zo);
-          float cv[8], mcv[8];
-          if (v) {
-            const float4* cp = reinterpret_cast<const float4*>(a.c + (size_t)gr * a.ld + u);
-            const float4* mp = reinterpret_cast<const float4*>(a.mc + (size_t)gr * a.ld + u);
-            const float4 c0 = cp[0], c1 = cp[1], m0 = mp[0], m1 = mp[1];
-            cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
-            mcv[0] = m0.x; mcv[1] = m0.y; mcv[2] = m0.z; mcv[3] = m0.w; mcv[4] = m1.x; mcv[5] = m1.y; mcv[6] = m1.z; mcv[7] = m1.w;
+      // epilogue operands of sub-chunk idx (pass idx/2, half idx%2): 8 units of c (fp32) and mc
+      struct CM { float4 c0, c1, m0, m1; };
+      auto load_cm = [&](int idx) {
+        CM o;
+        o.c0 = o.c1 = o.m0 = o.m1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v) {
+          const int u = (idx >> 1) * TC_UN + hsel * 16 + (idx & 1) * 8;
+          const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
+          const float4* cp = reinterpret_cast<const float4*>(a.c + so);
+          o.c0 = cp[0];
+          o.c1 = cp[1];
+          if constexpr (BF) {
+            const uint4 m = *reinterpret_cast<const uint4*>(a.mcb + so);
+            o.m0 = make_float4(bf16_lo(m.x), bf16_hi(m.x), bf16_lo(m.y), bf16_hi(m.y));
+            o.m1 = make_float4(bf16_lo(m.z), bf16_hi(m.z), bf16_lo(m.w), bf16_hi(m.w));
           } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cv[i] = mcv[i] = 0.f;
+            const float4* mp = reinterpret_cast<const float4*>(a.mc + (size_t)gr * a.ld + u);
+            o.m0 = mp[0];
+            o.m1 = mp[1];
           }
-          tmem_wait_ld();
-          float ho[8], co[8], fo[8];
+        }
+        return o;
+      };
+      // ---- h -> blocks 1,2 ; mh -> blocks 3,4
+      if constexpr (LAY == 2) {
+        // blocked bf16 state: piece (g, row) is 16 B; thread t takes pieces t + 256k -> consecutive lanes read
+        // consecutive rows of one group: 512 B contiguous per warp instruction; 8 loads in flight per array
+        const uint4* hsrc = reinterpret_cast<const uint4*>(a.hb + (size_t)tile * TC_M * TC_U);
+        const uint4* msrc = reinterpret_cast<const uint4*>(a.mhb + (size_t)tile * TC_M * TC_U);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int uu = u + i;
-            const float gi = zi[i] + s_bias[uu], gj = zj[i] + s_bias[128 + uu], go = zo[i] + s_bias[256 + uu];
-            const float g = sigmoid_fast(gi + s_bias[384 + uu] * mcv[i] + s_bias[512 + uu] * cv[i]);
-            const float tj = tanh_fast(gj);
-            const float cf = fmaf(g, tj - mcv[i], mcv[i]);   // (1-g)*mc + g*tj
-            const float ct = fmaf(g, tj - cv[i], cv[i]);
-            const float qq = sigmoid_fast(go + s_bias[640 + uu] * cf + s_bias[768 + uu] * ct);
-            fo[i] = v ? qq * tanh_fast(cf) : 0.f;
-            ho[i] = v ? qq * tanh_fast(ct) : 0.f;
-            co[i] = v ? ct : 0.f;
+        for (int arr = 0; arr < 2; ++arr) {
+          const uint4* src = arr ? msrc : hsrc;
+          uint4 v8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v8[k] = src[tid + 256 * k];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int pidx = tid + 256 * k, g = pidx >> 7, rr = pidx & 127;
+            const uint32_t off = (uint32_t)rr * 128u + (uint32_t)(((g & 7) ^ (rr & 7)) << 4);
+            *reinterpret_cast<uint4*>(smem + SM_A + (1 + 2 * arr + (g >> 3)) * TC_A_BLOCK + off) = v8[k];
           }
-          if (rok) {
+        }
+      } else if constexpr (LAY == 1) {
+        // bf16 state: a warp owns 16 rows; lane -> (row parity, 16-byte unit); 8 independent 16 B loads in flight
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint4 hv[4], mv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = warp * 16 + half * 8 + i * 2 + (lane >> 4);
+            const int g2 = row0 + rr;
+            hv[i] = mv[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (g2 < a.R) {
+              hv[i] = *reinterpret_cast<const uint4*>(a.hb + (size_t)g2 * TC_U + (lane & 15) * 8);
+              mv[i] = *reinterpret_cast<const uint4*>(a.mhb + (size_t)g2 * TC_U + (lane & 15) * 8);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = warp * 16 + half * 8 + i * 2 + (lane >> 4);
+            const int un = lane & 15, blk = un >> 3;
+            const uint32_t off = (uint32_t)rr * 128u + (uint32_t)(((un & 7) ^ (rr & 7)) << 4);
+            *reinterpret_cast<uint4*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + off) = hv[i];
+            *reinterpret_cast<uint4*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + off) = mv[i];
+          }
+        }
+      } else {
+        // fp32 state: one warp per row, lane -> 4 consecutive k, converted to bf16 on the way
+        for (int rr = warp; rr < TC_M; rr += 8) {
+          const int g2 = row0 + rr;
+          float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), mv = hv;
+          if (g2 < a.R) {
+            hv = *reinterpret_cast<const float4*>(a.h + (size_t)g2 * a.ld + lane * 4);
+            mv = *reinterpret_cast<const float4*>(a.mh + (size_t)g2 * a.ld + lane * 4);
+          }
+          const int k = lane * 4;  // 0..124 within the 128-wide part
+          const int blk = k >> 6, kk = k & 63;
+          *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+              make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
+          *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+              make_uint2(pack_bf16x2(mv.x, mv.y), pack_bf16x2(mv.z, mv.w));
+        }
+      }
+      CM pre = load_cm(0);  // in flight while the MMAs of pass 0 run
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(A_READY);
+
+      // ---- epilogue: 8 sub-chunks (4 passes x 2 halves), operands prefetched one sub-chunk ahead
+      float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int idx = 0; idx < 2 * TC_NP; ++idx) {
+        const int p = idx >> 1, sub = idx & 1;
+        const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+        if (sub == 0) {
+          mbar_wait(ACC_FULL + 8 * b, bph);
+          tc_fence_after();
+        }
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + b * TC_ACC_STRIDE;
+        const int ul = hsel * 16 + sub * 8;  // unit within pass
+        const int u = p * TC_UN + ul;        // global unit
+        float zi[8], zj[8], zo[8];
+        tmem_ld8(t_row + ul, zi);
+        tmem_ld8(t_row + TC_UN + ul, zj);
+        tmem_ld8(t_row + 2 * TC_UN + ul, zo);
+        const CM cur = pre;
+        if (idx + 1 < 2 * TC_NP) pre = load_cm(idx + 1);
+        const float cv[8] = {cur.c0.x, cur.c0.y, cur.c0.z, cur.c0.w, cur.c1.x, cur.c1.y, cur.c1.z, cur.c1.w};
+        const float mcv[8] = {cur.m0.x, cur.m0.y, cur.m0.z, cur.m0.w, cur.m1.x, cur.m1.y, cur.m1.z, cur.m1.w};
+        tmem_wait_ld();
+        float ho[8], co[8], fo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int uu = u + i;
+          const float gi = zi[i] + s_bias[uu], gj = zj[i] + s_bias[128 + uu], go = zo[i] + s_bias[256 + uu];
+          const float g = sigmoid_fast(gi + s_bias[384 + uu] * mcv[i] + s_bias[512 + uu] * cv[i]);
+          const float tj = tanh_fast(gj);
+          const float cf = fmaf(g, tj - mcv[i], mcv[i]);  // (1-g)*mc + g*tj
+          const float ct = fmaf(g, tj - cv[i], cv[i]);
+          const float qq = sigmoid_fast(go + s_bias[640 + uu] * cf + s_bias[768 + uu] * ct);
+          fo[i] = v ? qq * tanh_fast(cf) : 0.f;
+          ho[i] = v ? qq * tanh_fast(ct) : 0.f;
+          co[i] = v ? ct : 0.f;
+        }
+        if (rok || LAY == 2) {
+          const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
+          float4* cp = reinterpret_cast<float4*>(a.c_out + so);
+          cp[0] = make_float4(co[0], co[1], co[2], co[3]);
+          cp[1] = make_float4(co[4], co[5], co[6], co[7]);
+          if constexpr (BF) {
+            *reinterpret_cast<uint4*>(a.hb_out + so) =
+                make_uint4(pack_bf16x2(ho[0], ho[1]), pack_bf16x2(ho[2], ho[3]), pack_bf16x2(ho[4], ho[5]),
+                           pack_bf16x2(ho[6], ho[7]));
+          } else {
             float4* hp = reinterpret_cast<float4*>(a.h_out + (size_t)gr * a.ld + u);
-            float4* cp = reinterpret_cast<float4*>(a.c_out + (size_t)gr * a.ld + u);
             hp[0] = make_float4(ho[0], ho[1], ho[2], ho[3]);
             hp[1] = make_float4(ho[4], ho[5], ho[6], ho[7]);
-            cp[0] = make_float4(co[0], co[1], co[2], co[3]);
-            cp[1] = make_float4(co[4], co[5], co[6], co[7]);
             if (a.mf_out) {
               float4* fp = reinterpret_cast<float4*>(a.mf_out + (size_t)gr * a.ld_mf + u);
               fp[0] = make_float4(fo[0], fo[1], fo[2], fo[3]);
               fp[1] = make_float4(fo[4], fo[5], fo[6], fo[7]);
             }
           }
-          if (a.params_out) {
+        }
+        if (a.params_out) {
+          // head partial sums: W_h rows u..u+7 are 40 contiguous floats (160 B, 16-byte aligned): 10 uniform
+          // 128-bit loads per half instead of 40 scalar ones (the scalar version saturated L1TEX)
+          float wv[40];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float* wa = a.W_h + (size_t)(u + i) * 5;
-              const float* wb = a.W_h + (size_t)(TC_U + u + i) * 5;
+          for (int hsrc = 0; hsrc < 2; ++hsrc) {
+            const float4* wp = reinterpret_cast<const float4*>(a.W_h + (size_t)(hsrc * TC_U + u) * 5);
 #pragma unroll
-              for (int z = 0; z < 5; ++z) y[z] = fmaf(ho[i], __ldg(wa + z), fmaf(fo[i], __ldg(wb + z), y[z]));
+            for (int k4 = 0; k4 < 10; ++k4) {
+              const float4 t4 = __ldg(wp + k4);
+              wv[4 * k4] = t4.x; wv[4 * k4 + 1] = t4.y; wv[4 * k4 + 2] = t4.z; wv[4 * k4 + 3] = t4.w;
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int z = 0; z < 5; ++z) y[z] = fmaf(hsrc ? fo[i] : ho[i], wv[i * 5 + z], y[z]);
           }
         }
-        tc_fence_before();
-        mbar_arrive(ACC_EMPTY + 8 * b);
+        if (sub == 1) {
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY + 8 * b);
+          ++pc;
+        }
       }
       // ---- head: combine the two column halves of each row
       if (a.params_out) {
@@ -415,26 +515,52 @@ __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* _
   *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(W[idx]);
 }
 
+static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
+  a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
+  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
+}
+
+template <int LAY>
+static int tc_launch(TcArgs& a, cudaStream_t stream) {
+  a.num_tiles = (a.R + TC_M - 1) / TC_M;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gsk_cell_tc_kernel<LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < 2 * kNumSMs ? a.num_tiles : 2 * kNumSMs;
+  gsk_cell_tc_kernel<LAY><<<grid, TC_THREADS, SM_TOTAL + 1024, stream>>>(a);
+  count_launch();
+  return check_launch("gsk_cell_tc_kernel");
+}
+
+// bf16-state variant used by the rollout: h, mh, mc as bf16 [R,U]; c fp32 [R,U]
+int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
+                        const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
+                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
+                        cudaStream_t stream) {
+  TcArgs a = {};
+  a.x = x; a.c = c; a.valid = valid;
+  a.hb = reinterpret_cast<const __nv_bfloat16*>(hb);
+  a.mhb = reinterpret_cast<const __nv_bfloat16*>(mhb);
+  a.mcb = reinterpret_cast<const __nv_bfloat16*>(mcb);
+  a.hb_out = reinterpret_cast<__nv_bfloat16*>(hb_out);
+  tc_fill_weights(a, w);
+  a.c_out = c_out; a.cur_pos = cur_pos; a.params_out = params_out; a.next_pos = next_pos;
+  a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = params_stride;
+  return blocked ? tc_launch<2>(a, stream) : tc_launch<1>(a, stream);
+}
+
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
                    const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
                    int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
                    cudaStream_t stream) {
-  TcArgs a;
+  TcArgs a = {};
   a.x = x; a.h = h; a.c = c; a.mh = mh; a.mc = mc; a.valid = valid;
-  a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
-  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
+  tc_fill_weights(a, w);
   a.h_out = h_out; a.c_out = c_out; a.mf_out = mf_out; a.cur_pos = cur_pos; a.params_out = params_out;
   a.next_pos = next_pos; a.R = R; a.ld = ld; a.ld_mf = ld_mf; a.params_stride = params_stride;
-  a.num_tiles = (R + TC_M - 1) / TC_M;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gsk_cell_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
-    attr_set = true;
-  }
-  const int grid = a.num_tiles < 2 * kNumSMs ? a.num_tiles : 2 * kNumSMs;
-  gsk_cell_tc_kernel<<<grid, TC_THREADS, SM_TOTAL + 1024, stream>>>(a);
-  count_launch();
-  return check_launch("gsk_cell_tc_kernel");
+  return tc_launch<0>(a, stream);
 }
 
 }  // namespace mmt

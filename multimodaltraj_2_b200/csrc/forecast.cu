@@ -19,6 +19,15 @@ int launch_cell_tc(const float* x, const float* h, const float* c, const float* 
                    int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
                    cudaStream_t stream);
 
+int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
+                        const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
+                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
+                        cudaStream_t stream);
+int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
+                                   float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
+                                int U, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+
 // x = [cur - prev | vis_t]; for observed frames cur is gathered from pos[:, :, t]
 __global__ void __launch_bounds__(256) prep_step_kernel(const float* __restrict__ pos, const float* __restrict__ vis,
                                                         int R, int F, int T, int t, float* __restrict__ cur,
@@ -55,6 +64,10 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const float* __restr
 struct Workspace {
   float *pbuf[3], *x, *hc[2], *mhc, *mf, *kern, *score, *ework, *params, *last_obs, *gt;
   uint8_t* adj;
+  // bf16-state fast path (non-relational bf16 mode): h, mh, mc bf16 [R,U]; c fp32 [R,U]
+  void *hb[2], *mhb, *mcb;
+  float* cf[2];
+  bool fast, blocked;   // blocked: tile-blocked state layout (needs 128 % N == 0)
   size_t bytes;
 };
 
@@ -69,14 +82,28 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
     off += align_up(bytes);
     return p;
   };
+  w.fast = cfg->prec == MMT_PREC_BF16 && !cfg->relational;
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
-  w.hc[0] = (float*)take(R * 2 * U * 4);
-  w.hc[1] = (float*)take(R * 2 * U * 4);
-  w.mhc = (float*)take(R * 2 * U * 4);
-  w.mf = (float*)take(R * U * 4);
-  w.kern = (float*)take(NN * 4);
-  w.adj = (uint8_t*)take(NN);
+  w.blocked = w.fast && (128 % cfg->N == 0);
+  if (w.fast) {
+    const size_t Rp = (R + 127) / 128 * 128;   // state rows padded to whole 128-row tiles
+    for (int i = 0; i < 2; ++i) {
+      w.hb[i] = take(Rp * U * 2);
+      w.cf[i] = (float*)take(Rp * U * 4);
+    }
+    w.mhb = take(Rp * U * 2);
+    w.mcb = take(Rp * U * 2);
+    w.hc[0] = w.hc[1] = w.mhc = w.mf = w.kern = nullptr;
+    w.adj = nullptr;
+  } else {
+    w.hc[0] = (float*)take(R * 2 * U * 4);
+    w.hc[1] = (float*)take(R * 2 * U * 4);
+    w.mhc = (float*)take(R * 2 * U * 4);
+    w.mf = (float*)take(R * U * 4);
+    w.kern = (float*)take(NN * 4);
+    w.adj = (uint8_t*)take(NN);
+  }
   w.score = (float*)take(cfg->relational ? NN * 4 : 0);
   w.ework = (float*)take(cfg->relational ? 2 * R * He * 4 : 0);
   w.params = (float*)take(R * cfg->P * 5 * 4);
@@ -121,13 +148,45 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   const int R = S * N;
   float* par = params ? params : w.params;
 
-  cudaMemsetAsync(w.hc[0], 0, (size_t)R * 2 * U * 4, stream);
+  if (w.fast) {
+    const size_t Rp = ((size_t)R + 127) / 128 * 128;
+    cudaMemsetAsync(w.hb[0], 0, Rp * U * 2, stream);
+    cudaMemsetAsync(w.cf[0], 0, Rp * U * 4, stream);
+  } else {
+    cudaMemsetAsync(w.hc[0], 0, (size_t)R * 2 * U * 4, stream);
+  }
   int ic = 0, ip = 1, in = 2, hb = 0;
   int rc;
   for (int t = 0; t < T + P - 1; ++t) {
     prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
     count_launch();
     if ((rc = check_launch("prep_step_kernel"))) return rc;
+    if (w.fast) {
+      // bf16 fast path: [pairwise + softmax + aggregation] and [gate GEMM + gates + head], two kernels per step
+      const bool emit = t >= T - 1;
+      float* po = par + (size_t)(t - (T - 1)) * 5;
+      if (w.blocked)
+        rc = launch_graph_aggregate_blocked(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2,
+                                            w.mhb, w.mcb, stream);
+      else
+        rc = launch_graph_aggregate_bf16(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, U, cfg->r2, cfg->inv_2sigma2,
+                                         w.mhb, w.mcb, stream);
+      if (rc) return rc;
+      if ((rc = launch_cell_tc_bf16(w.x, w.hb[hb], w.cf[hb], w.mhb, w.mcb, valid, cw, R, w.hb[hb ^ 1], w.cf[hb ^ 1],
+                                    w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr,
+                                    w.blocked ? 1 : 0, stream)))
+        return rc;
+      hb ^= 1;
+      const int old_p = ip;
+      ip = ic;
+      if (emit) {
+        ic = in;
+        in = old_p;
+      } else {
+        ic = old_p;
+      }
+      continue;
+    }
     if ((rc = mmt_pairwise_adj_f32(w.pbuf[ic], valid, S, N, cfg->r2, cfg->inv_2sigma2, w.kern, w.adj, nullptr, stream)))
       return rc;
     const float* l2 = nullptr;

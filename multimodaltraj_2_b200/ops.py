@@ -34,8 +34,12 @@ def _chk(t, dtype, name):
     return t
 
 
+_graph_launches = 0   # kernel launches replayed through CUDA graphs (not seen by the library's own counter)
+
+
 def launch_count() -> int:
-    return int(_lib.load().mmt_launch_count())
+    """Kernels launched by this process through libmmt (direct launches + CUDA-graph replays)."""
+    return int(_lib.load().mmt_launch_count()) + _graph_launches
 
 
 # --------------------------------------------------------------------------------------------
@@ -256,8 +260,11 @@ class Forecaster:
     once and reused, so a step is pure kernel launches on the current stream."""
 
     def __init__(self, params: CellParams, S, N, T=8, P=12, K=20, r2=4.0, inv_2sigma2=0.5, relational=False,
-                 prec=PREC_F32, seed=0, agent_offset=0, device="cuda", want_all=False):
+                 prec=PREC_F32, seed=0, agent_offset=0, device="cuda", want_all=False, use_graph=False):
         self.lib = _lib.load()
+        self.use_graph = use_graph
+        self._graph = self._graph_key = None
+        self._graph_n = 0
         self.p = params
         if prec == PREC_BF16 and params.W_packed is None:
             params.pack()
@@ -276,6 +283,26 @@ class Forecaster:
         self._ew = params.c_edge()
 
     def __call__(self, pos, vis, valid, eps=None):
+        """Run the path.  With ``use_graph`` the ~60 launches of a rollout are captured once into a CUDA
+        graph (keyed on the input pointers) and replayed, removing the per-launch host overhead."""
+        if not self.use_graph:
+            return self._launch(pos, vis, valid, eps)
+        global _graph_launches
+        key = (pos.data_ptr(), vis.data_ptr(), valid.data_ptr(), None if eps is None else eps.data_ptr())
+        if self._graph_key != key:
+            self._launch(pos, vis, valid, eps)          # eager warm-up: sets kernel attributes, validates arguments
+            torch.cuda.synchronize()
+            n0 = int(self.lib.mmt_launch_count())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(pos, vis, valid, eps)
+            self._graph_n = int(self.lib.mmt_launch_count()) - n0
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+        _graph_launches += self._graph_n
+        return self.out
+
+    def _launch(self, pos, vis, valid, eps=None):
         _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis"); _chk(valid, torch.uint8, "valid")
         o = self.out
         ew = C.byref(self._ew) if self._ew is not None else None

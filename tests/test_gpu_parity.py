@@ -328,9 +328,11 @@ def test_forecast_fp32_matches_oracle(cuda, S, N, relational):
     assert np.array_equal(npy(o["best_k"]), best) and np.array_equal(npy(o["best_traj"]), bt)
 
 
-def test_forecast_bf16_tensor_core(cuda):
-    """bf16/tcgen05 mode, stated separately: mean-trajectory error vs the fp32 oracle."""
-    S, N, T, P, K = 8, 64, 8, 12, 20
+@pytest.mark.parametrize("S,N", [(8, 64), (5, 16), (3, 12), (2, 128), (1, 256)])
+def test_forecast_bf16_tensor_core(cuda, S, N):
+    """bf16/tcgen05 mode, stated separately: mean-trajectory error vs the fp32 oracle.  N | 128 takes the
+    tile-blocked state layout, other N the row-major bf16 layout; S*N % 128 != 0 exercises the tail tile."""
+    T, P, K = 8, 12, 20
     pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0, ragged=True)
     p = synth.init_params(seed=3)
     eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
