@@ -23,6 +23,8 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
                         const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
                         const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
                         cudaStream_t stream);
+int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
+                               float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
                                    float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
 int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
@@ -165,7 +167,10 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       // bf16 fast path: [pairwise + softmax + aggregation] and [gate GEMM + gates + head], two kernels per step
       const bool emit = t >= T - 1;
       float* po = par + (size_t)(t - (T - 1)) * 5;
-      if (w.blocked)
+      if (w.blocked && N >= 16)
+        rc = launch_graph_aggregate_mma(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2, w.mhb,
+                                        w.mcb, stream);
+      else if (w.blocked)
         rc = launch_graph_aggregate_blocked(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2,
                                             w.mhb, w.mcb, stream);
       else
