@@ -65,6 +65,7 @@ struct TcArgs {
   const float* cur_pos;
   float *params_out, *next_pos;
   int R, ld, ld_mf, params_stride, num_tiles;
+  long long* dbg;  // optional [CTA][tile_iter][16] clock64 timestamps of worker thread 0 (diagnostics)
 };
 
 // State layouts.  LAY 0: fp32 row-major [R,ld] in/out (the mmt_gsk_cell API).  LAY 1: bf16 h/mh/mc, fp32 c,
@@ -106,12 +107,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) tmem_alloc(sbase + SM_TMEM, TC_TMEM_COLS);
-  for (int i = tid; i < 384; i += TC_THREADS) s_bias[i] = a.b[i];
+  // sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 is folded into everything that feeds the i and o gates
+  // (their packed weight columns, biases and peephole diagonals), so a gate is one MUFU.TANH + one FMA
+  for (int i = tid; i < 384; i += TC_THREADS) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
   for (int i = tid; i < 128; i += TC_THREADS) {
-    s_bias[384 + i] = a.w_If[i];
-    s_bias[512 + i] = a.w_It[i];
-    s_bias[640 + i] = a.w_Of[i];
-    s_bias[768 + i] = a.w_Ot[i];
+    s_bias[384 + i] = 0.5f * a.w_If[i];
+    s_bias[512 + i] = 0.5f * a.w_It[i];
+    s_bias[640 + i] = 0.5f * a.w_Of[i];
+    s_bias[768 + i] = 0.5f * a.w_Ot[i];
   }
   for (int i = tid; i < 256; i += TC_THREADS) s_we[i] = a.W_e[i];
   for (int i = tid; i < 64; i += TC_THREADS) s_we[256 + i] = a.b_e[i];
@@ -168,6 +171,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
     uint32_t pc = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int row0 = tile * TC_M;
+      long long* dbg = (a.dbg && tid == 0) ? a.dbg + ((size_t)blockIdx.x * 16 + (tile / gridDim.x)) * 16 : nullptr;
+      if (dbg) dbg[0] = clock64();
       // ---- e = relu(x W_e + b_e) -> block 0.  thread -> (row tid/2, 32 k's)
       {
         const int r = tid >> 1, k0 = (tid & 1) * 32;
@@ -202,10 +207,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
       // epilogue operands of sub-chunk idx (pass idx/2, half idx%2): 8 units of c (fp32) and mc
-      struct CM { float4 c0, c1, m0, m1; };
+      struct CM { float4 c0, c1; uint4 m; float4 mf0, mf1; };   // m: 8 bf16 (bf16 state); mf0/mf1: fp32 state only
       auto load_cm = [&](int idx) {
         CM o;
-        o.c0 = o.c1 = o.m0 = o.m1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        o.c0 = o.c1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        o.m = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (!BF) o.mf0 = o.mf1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (v) {
           const int u = (idx >> 1) * TC_UN + hsel * 16 + (idx & 1) * 8;
           const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
@@ -213,13 +220,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           o.c0 = cp[0];
           o.c1 = cp[1];
           if constexpr (BF) {
-            const uint4 m = *reinterpret_cast<const uint4*>(a.mcb + so);
-            o.m0 = make_float4(bf16_lo(m.x), bf16_hi(m.x), bf16_lo(m.y), bf16_hi(m.y));
-            o.m1 = make_float4(bf16_lo(m.z), bf16_hi(m.z), bf16_lo(m.w), bf16_hi(m.w));
+            o.m = *reinterpret_cast<const uint4*>(a.mcb + so);
           } else {
             const float4* mp = reinterpret_cast<const float4*>(a.mc + (size_t)gr * a.ld + u);
-            o.m0 = mp[0];
-            o.m1 = mp[1];
+            o.mf0 = mp[0];
+            o.mf1 = mp[1];
           }
         }
         return o;
@@ -284,7 +289,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
               make_uint2(pack_bf16x2(mv.x, mv.y), pack_bf16x2(mv.z, mv.w));
         }
       }
-      CM pre = load_cm(0);  // in flight while the MMAs of pass 0 run
+      if (dbg) dbg[1] = clock64();
+      CM pre = load_cm(0), pre2 = load_cm(1);  // two sub-chunks in flight while the MMAs of pass 0 run
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       mbar_arrive(A_READY);
 
@@ -295,7 +301,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         const int p = idx >> 1, sub = idx & 1;
         const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
         if (sub == 0) {
+          if (dbg) dbg[2 + 3 * p] = clock64();
           mbar_wait(ACC_FULL + 8 * b, bph);
+          if (dbg) dbg[3 + 3 * p] = clock64();
           tc_fence_after();
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + b * TC_ACC_STRIDE;
@@ -306,23 +314,56 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         tmem_ld8(t_row + TC_UN + ul, zj);
         tmem_ld8(t_row + 2 * TC_UN + ul, zo);
         const CM cur = pre;
-        if (idx + 1 < 2 * TC_NP) pre = load_cm(idx + 1);
-        const float cv[8] = {cur.c0.x, cur.c0.y, cur.c0.z, cur.c0.w, cur.c1.x, cur.c1.y, cur.c1.z, cur.c1.w};
-        const float mcv[8] = {cur.m0.x, cur.m0.y, cur.m0.z, cur.m0.w, cur.m1.x, cur.m1.y, cur.m1.z, cur.m1.w};
+        pre = pre2;
+        if (idx + 2 < 2 * TC_NP) pre2 = load_cm(idx + 2);
         tmem_wait_ld();
         float ho[8], co[8], fo[8];
+        if (v) {
+          const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int uu = u + i;
-          const float gi = zi[i] + s_bias[uu], gj = zj[i] + s_bias[128 + uu], go = zo[i] + s_bias[256 + uu];
-          const float g = sigmoid_fast(gi + s_bias[384 + uu] * mcv[i] + s_bias[512 + uu] * cv[i]);
-          const float tj = tanh_fast(gj);
-          const float cf = fmaf(g, tj - mcv[i], mcv[i]);  // (1-g)*mc + g*tj
-          const float ct = fmaf(g, tj - cv[i], cv[i]);
-          const float qq = sigmoid_fast(go + s_bias[640 + uu] * cf + s_bias[768 + uu] * ct);
-          fo[i] = v ? qq * tanh_fast(cf) : 0.f;
-          ho[i] = v ? qq * tanh_fast(ct) : 0.f;
-          co[i] = v ? ct : 0.f;
+          for (int hq = 0; hq < 2; ++hq) {   // 4 units at a time: parameters come as 128-bit smem loads
+            const int uu = u + hq * 4;
+            const float4 bI = *reinterpret_cast<const float4*>(s_bias + uu);
+            const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + uu);
+            const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + uu);
+            const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + uu);
+            const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + uu);
+            const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + uu);
+            const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + uu);
+            const float4 c4 = hq ? cur.c1 : cur.c0;
+            float4 m4;
+            if constexpr (BF) {
+              const uint32_t w0 = hq ? cur.m.z : cur.m.x, w1 = hq ? cur.m.w : cur.m.y;
+              m4 = make_float4(bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1));
+            } else {
+              m4 = hq ? cur.mf1 : cur.mf0;
+            }
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {  // a pair of units per packed FFMA2
+              const int i0 = hq * 4 + pr * 2;
+              const float2 c2 = pr ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+              const float2 m2 = pr ? make_float2(m4.z, m4.w) : make_float2(m4.x, m4.y);
+              auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
+              float2 t = fadd2(make_float2(zi[i0], zi[i0 + 1]), sel(bI));
+              t = ffma2(sel(pIf), m2, t);
+              t = ffma2(sel(pIt), c2, t);
+              const float2 g = ffma2(tanh2(t), kHalf, kHalf);
+              const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
+              const float2 cf = ffma2(g, ffma2(m2, kNeg, tj), m2);   // (1-g)*mc + g*tj
+              const float2 ct = ffma2(g, ffma2(c2, kNeg, tj), c2);
+              float2 o = fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO));
+              o = ffma2(sel(pOf), cf, o);
+              o = ffma2(sel(pOt), ct, o);
+              const float2 qq = ffma2(tanh2(o), kHalf, kHalf);
+              const float2 f2 = fmul2(qq, tanh2(cf)), h2 = fmul2(qq, tanh2(ct));
+              fo[i0] = f2.x; fo[i0 + 1] = f2.y;
+              ho[i0] = h2.x; ho[i0 + 1] = h2.y;
+              co[i0] = ct.x; co[i0 + 1] = ct.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ho[i] = co[i] = fo[i] = 0.f;
         }
         if (rok || LAY == 2) {
           const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
@@ -365,9 +406,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         if (sub == 1) {
           tc_fence_before();
           mbar_arrive(ACC_EMPTY + 8 * b);
+          if (dbg) dbg[4 + 3 * p] = clock64();
           ++pc;
         }
       }
+      if (dbg) dbg[14] = clock64();
       // ---- head: combine the two column halves of each row
       if (a.params_out) {
         if (hsel == 1) {
@@ -412,7 +455,8 @@ __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* _
   const int n = g * TC_UN + ul;
   const int kc = k / TC_KC, kk = k - kc * TC_KC;
   const size_t off = (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES + sw128_off(n, kk);
-  *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(W[idx]);
+  // gates i (g == 0) and o (g == 2) go through sigmoid(z) = 0.5 tanh(z/2) + 0.5: fold the 1/2 (exact in bf16)
+  *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(g == 1 ? W[idx] : 0.5f * W[idx]);
 }
 
 static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
@@ -479,4 +523,22 @@ extern "C" int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* pa
   pack_gate_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_gate_weights_kernel");
+}
+
+// diagnostics: run the blocked bf16-state kernel once with per-tile phase timestamps (clock64 of worker 0)
+extern "C" int mmt_debug_cell_tc_timeline(const float* x, const void* hb, const float* c, const void* mhb,
+                                          const void* mcb, const uint8_t* valid, const mmt_cell_weights* w, int R,
+                                          void* hb_out, float* c_out, const float* cur_pos, float* params_out,
+                                          float* next_pos, long long* dbg, void* stream) {
+  using namespace mmt;
+  TcArgs a = {};
+  a.x = x; a.c = c; a.valid = valid;
+  a.hb = reinterpret_cast<const __nv_bfloat16*>(hb);
+  a.mhb = reinterpret_cast<const __nv_bfloat16*>(mhb);
+  a.mcb = reinterpret_cast<const __nv_bfloat16*>(mcb);
+  a.hb_out = reinterpret_cast<__nv_bfloat16*>(hb_out);
+  tc_fill_weights(a, w);
+  a.c_out = c_out; a.cur_pos = cur_pos; a.params_out = params_out; a.next_pos = next_pos;
+  a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = 5; a.dbg = dbg;
+  return tc_launch<2>(a, (cudaStream_t)stream);
 }
