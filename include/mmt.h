@@ -35,6 +35,8 @@ extern "C" {
 /* precision modes of the gate / aggregation contractions */
 #define MMT_PREC_F32 0   /* fp32 CUDA-core FMA, parity mode (1e-4 rel vs oracle)             */
 #define MMT_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
+#define MMT_PREC_BF16_STEPWISE 2 /* mmt_forecast_f32 only: bf16 as above but one kernel pair per step
+                                    (state in HBM) instead of the fused persistent rollout           */
 
 int mmt_version(void);
 const char* mmt_last_error(void);
@@ -220,6 +222,16 @@ int mmt_forecast_f32(const float* pos, const float* vis, const uint8_t* valid,
                      const float* eps, float* params, float* ade, float* fde, int32_t* best_k,
                      float* best_ade, float* best_fde, float* best_traj, void* work, size_t work_bytes,
                      void* stream);
+
+/* The recurrence alone in bf16 mode as ONE persistent kernel with the state on chip (what mmt_forecast_f32
+ * runs for g2k_lstm_mc when prec = MMT_PREC_BF16 and 128 % N == 0): per step pairwise kernel + adjacency +
+ * masked softmax -> aggregation (tcgen05) -> gate GEMM (tcgen05) -> gate update -> head -> next position.
+ * Replaces the per-frame loop of train.py:161-254 for a whole batch.  pos[S,N,T+P,2] (only the T observed
+ * frames are read), vis[S,N,T,2], valid[S,N] -> params[S,N,P,5].  N in {8,16,32,64,128}.
+ * timeline: NULL, or [64][32] int64 clock64() phase stamps of CTA 0 (diagnostics). */
+int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
+                     int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
+                     int64_t* timeline, void* stream);
 
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);

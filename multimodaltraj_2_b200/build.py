@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libmmt.so"
 SOURCES = ["capi.cu", "pairwise.cu", "aggregate.cu", "cell_f32.cu", "cell_tc.cu", "edge_mlp.cu",
-           "decode_score.cu", "track_a.cu", "scene_batch.cu", "forecast.cu", "scores.cu", "graph_agg.cu", "graph_mma.cu"]
+           "decode_score.cu", "track_a.cu", "scene_batch.cu", "forecast.cu", "scores.cu", "graph_agg.cu", "graph_mma.cu", "rollout_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -26,7 +26,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "mmt_common.cuh", PKG.parent / "include" / "mmt.h"]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "mmt_common.cuh", CSRC / "tc_common.cuh", PKG.parent / "include" / "mmt.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -25,6 +25,8 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
                         cudaStream_t stream);
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
                                float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
+                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, cudaStream_t stream);
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
                                    float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
 int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
@@ -84,7 +86,7 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
     off += align_up(bytes);
     return p;
   };
-  w.fast = cfg->prec == MMT_PREC_BF16 && !cfg->relational;
+  w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE) && !cfg->relational;
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
   w.blocked = w.fast && (128 % cfg->N == 0);
@@ -133,8 +135,9 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   MMT_REQUIRE(cw->U == 128 && cw->E == 64, "cell is built for U = 128, E = 64");
   MMT_REQUIRE(cw->W_h && cw->b_h, "head weights required");
   MMT_REQUIRE(!cfg->relational || (ew && ew->He > 0), "relational mode needs edge weights");
-  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16, "unknown precision mode");
-  MMT_REQUIRE(cfg->prec != MMT_PREC_BF16 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE,
+              "unknown precision mode");
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
   MMT_ALIGNED(pos);
   MMT_ALIGNED(vis);
   MMT_ALIGNED(work);
@@ -149,8 +152,15 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   const int S = cfg->S, N = cfg->N, T = cfg->T, P = cfg->P, F = T + P;
   const int R = S * N;
   float* par = params ? params : w.params;
+  int rc0;
 
-  if (w.fast) {
+  // bf16, non-relational, whole scenes per 128-row tile: the entire recurrence is one persistent kernel with the
+  // state on chip (rollout_tc.cu).  MMT_PREC_BF16_STEPWISE keeps the per-step kernels (A/B checks, other N).
+  const bool fused = w.fast && w.blocked && N >= 8 && cfg->prec == MMT_PREC_BF16;
+  if (fused) {
+    if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, stream)))
+      return rc0;
+  } else if (w.fast) {
     const size_t Rp = ((size_t)R + 127) / 128 * 128;
     cudaMemsetAsync(w.hb[0], 0, Rp * U * 2, stream);
     cudaMemsetAsync(w.cf[0], 0, Rp * U * 4, stream);
@@ -159,7 +169,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   }
   int ic = 0, ip = 1, in = 2, hb = 0;
   int rc;
-  for (int t = 0; t < T + P - 1; ++t) {
+  for (int t = 0; t < (fused ? 0 : T + P - 1); ++t) {
     prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
     count_launch();
     if ((rc = check_launch("prep_step_kernel"))) return rc;
@@ -233,4 +243,21 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   if ((rc = check_launch("gather_frames_kernel"))) return rc;
   return mmt_decode_score_f32(par, eps, cfg->seed, cfg->agent_offset, w.last_obs, w.gt, valid, S, N, P, cfg->K, ade,
                               fde, best_k, best_ade, best_fde, best_traj, stream);
+}
+
+extern "C" int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
+                                int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
+                                int64_t* timeline, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(pos && vis && valid && cw && params, "pos/vis/valid/weights/params required");
+  MMT_REQUIRE(S >= 0 && N >= 8 && N <= 128 && 128 % N == 0, "fused rollout needs N in {8,16,32,64,128}");
+  MMT_REQUIRE(T >= 1 && P >= 1, "need T >= 1, P >= 1");
+  MMT_REQUIRE(cw->U == 128 && cw->E == 64 && cw->W_h && cw->b_h && cw->W_packed_bf16,
+              "needs U = 128, E = 64, head weights and W_packed_bf16");
+  MMT_ALIGNED(pos);
+  MMT_ALIGNED(vis);
+  MMT_ALIGNED(params);
+  if (S == 0) return MMT_OK;
+  return launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, r2, inv_2sigma2, params,
+                           reinterpret_cast<long long*>(timeline), (cudaStream_t)stream);
 }

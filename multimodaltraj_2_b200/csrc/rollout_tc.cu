@@ -1,0 +1,530 @@
+// The whole obs T -> pred P recurrence of the bf16 path as ONE persistent kernel (sm_100a):
+// pairwise kernel + adjacency + masked softmax -> graph aggregation (tcgen05) -> gsk_lstm_cell gate GEMM
+// (tcgen05) -> gate update -> head -> next position, for all T+P-1 steps, with the recurrent state
+// ON CHIP.  ("tensor pipe only if the 20-step recurrence is fused with on-chip state".)
+//
+// One CTA per SM owns a 128-row tile (128/N whole scenes) for all its steps:
+//   shared memory  E | H | MH          bf16 [128 rows x 64 k] SWIZZLE_128B blocks = the K-major A operand
+//                                      [e | h | mh] of the gate GEMM (K = 320 = 5 blocks)
+//                  H, C                the same images are the MN-major B operand (agents along K, units
+//                                      along N) of the aggregation GEMMs  mh = att x h,  mc = att x c
+//                  ATT                 block-diagonal un-normalised attention, K-major A operand
+//                  W ring              gate weights streamed from L2 by cp.async.bulk, 12 KB stages
+//   tensor memory  2 gate accumulators (96 columns: i|j|o of 32 units) + mc (128) + mh (128)
+//   registers      fp32 cell state c: 64 values per worker thread (row x 16 units x 4 passes)
+// Only positions / vislets are read from HBM and only the 5 head parameters per predicted step are
+// written: ~0.5 KB per agent-trajectory instead of ~30 KB per agent for the per-step kernels.
+//
+// Warp roles: warps 0-7 workers (attention build, operand build, TMEM->smem conversion of mh, gate
+// epilogue, head); warps 8-10 stream weight stages; warp 11 issues every tcgen05.mma.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "mmt_common.cuh"
+#include "tc_common.cuh"
+
+namespace mmt {
+
+constexpr int RO_U = 128, RO_E = 64;
+constexpr int RO_UN = 32;                     // units per gate pass
+constexpr int RO_NP = RO_U / RO_UN;           // 4 passes
+constexpr int RO_N = 3 * RO_UN;               // 96 accumulator columns per pass
+constexpr int RO_NKC = 5;                     // k-chunks of 64: e | h0 h1 | mh0 mh1
+constexpr int RO_BLK = 128 * 128;             // one [128 rows x 128 B] block
+constexpr int RO_STAGE_BYTES = RO_N * 64 * 2; // 12288
+constexpr int RO_NSTAGE = 5;
+constexpr int RO_WORKERS = 256;
+constexpr int RO_NPROD = 3;                   // weight-stage producer warps (one issuing thread each)
+constexpr int RO_THREADS = RO_WORKERS + 32 * (RO_NPROD + 1);
+
+constexpr int RS_E = 0;
+constexpr int RS_H = RS_E + RO_BLK;           // 2 blocks
+constexpr int RS_MH = RS_H + 2 * RO_BLK;      // 2 blocks
+constexpr int RS_C = RS_MH + 2 * RO_BLK;      // 2 blocks
+constexpr int RS_ATT = RS_C + 2 * RO_BLK;     // 2 blocks
+constexpr int RS_W = RS_ATT + 2 * RO_BLK;
+constexpr int RS_BAR = RS_W + RO_NSTAGE * RO_STAGE_BYTES;
+constexpr int RS_TMEM = RS_BAR + 256;
+constexpr int RS_BIAS = RS_TMEM + 16;                  // b[384], w_If, w_It, w_Of, w_Ot [4][128]
+constexpr int RS_WE = RS_BIAS + (384 + 512) * 4;       // W_e[4][64], b_e[64]
+constexpr int RS_WH = RS_WE + (256 + 64) * 4;          // W_h[256][5], b_h[5] (+3 pad)
+constexpr int RS_HEAD = RS_WH + (256 * 5 + 8) * 4;     // head partials [128][5]
+constexpr int RS_CUR = RS_HEAD + 128 * 5 * 4;          // float2[128] current positions
+constexpr int RS_NEXT = RS_CUR + 1024;                 // float2[128] predicted next positions
+constexpr int RS_SUM = RS_NEXT + 1024;                 // float[2][128] attention row sums
+constexpr int RS_VAL = RS_SUM + 1024;                  // u8[128]
+constexpr int RS_TOTAL = RS_VAL + 128;
+static_assert(RS_TOTAL + 1024 <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t RT_ACC0 = 0, RT_ACC_STRIDE = 128, RT_MC = 256, RT_MH = 384;
+constexpr uint32_t kIdescGate = make_idesc_bf16(128, RO_N);
+constexpr uint32_t kIdescAggMN = make_idesc_bf16(128, 128) | (1u << 16);   // B operand MN-major
+
+struct RoArgs {
+  const float* pos;      // [R, F, 2]
+  const float* vis;      // [R, T, 2]
+  const uint8_t* valid;  // [R]
+  const float *W_e, *b_e, *b, *w_If, *w_It, *w_Of, *w_Ot, *W_h, *b_h;
+  const uint8_t* Wp;     // packed bf16 gate weights (mmt_pack_gate_weights_bf16)
+  float* params;         // [R, P, 5]
+  int R, N, T, P, F, num_tiles;
+  float r2, neg_inv_log2e;
+  int flags;  // TEMP diagnostics: 1 = no weight streaming / waits; 2 = workers skip the gate math
+  long long* dbg;        // optional [64 steps][32] clock64 stamps of CTA 0: [0,16) worker thread 0, [16,32) MMA thread
+};
+
+// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) contiguous, 8 k-rows of 128 B per atom;
+// LBO = byte distance between 64-element MN chunks, SBO = byte distance between 8-row k groups
+// (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + RS_BAR;
+  const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * RO_NSTAGE, ACC_FULL = bar0 + 16 * RO_NSTAGE,
+                 ACC_EMPTY = ACC_FULL + 16, ATT_READY = ACC_EMPTY + 16, E_READY = ATT_READY + 8,
+                 MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8;
+  float* s_bias = reinterpret_cast<float*>(smem + RS_BIAS);
+  float* s_we = reinterpret_cast<float*>(smem + RS_WE);
+  float* s_wh = reinterpret_cast<float*>(smem + RS_WH);
+  float* s_head = reinterpret_cast<float*>(smem + RS_HEAD);
+  float2* s_cur = reinterpret_cast<float2*>(smem + RS_CUR);
+  float2* s_next = reinterpret_cast<float2*>(smem + RS_NEXT);
+  float* s_sum = reinterpret_cast<float*>(smem + RS_SUM);
+  uint8_t* s_val = smem + RS_VAL;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + RS_TMEM);
+  const int nsteps = a.T + a.P - 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < RO_NSTAGE; ++s) {
+      mbar_init(W_FULL + 8 * s, 1);
+      mbar_init(W_EMPTY + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ACC_FULL + 8 * b, 1);
+      mbar_init(ACC_EMPTY + 8 * b, RO_WORKERS);
+    }
+    mbar_init(ATT_READY, RO_WORKERS);
+    mbar_init(E_READY, RO_WORKERS);
+    mbar_init(MH_READY, RO_WORKERS);
+    mbar_init(AGG_FULL, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(sbase + RS_TMEM, 512);
+  // sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 is folded into the packed i/o weight columns, biases and peepholes
+  for (int i = tid; i < 384; i += RO_THREADS) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
+  for (int i = tid; i < 128; i += RO_THREADS) {
+    s_bias[384 + i] = 0.5f * a.w_If[i];
+    s_bias[512 + i] = 0.5f * a.w_It[i];
+    s_bias[640 + i] = 0.5f * a.w_Of[i];
+    s_bias[768 + i] = 0.5f * a.w_Ot[i];
+  }
+  for (int i = tid; i < 256; i += RO_THREADS) s_we[i] = a.W_e[i];
+  for (int i = tid; i < 64; i += RO_THREADS) s_we[256 + i] = a.b_e[i];
+  for (int i = tid; i < 256 * 5; i += RO_THREADS) s_wh[i] = a.W_h[i];
+  if (tid < 5) s_wh[256 * 5 + tid] = a.b_h[tid];
+  // attention operand: entries outside a row's own scene stay zero for the whole kernel
+  for (int i = tid; i < 2 * RO_BLK / 16; i += RO_THREADS)
+    reinterpret_cast<uint4*>(smem + RS_ATT)[i] = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp >= 8 && warp < 8 + RO_NPROD) {
+    // =============================== weight-stage producers ===============================
+    // One thread managing the whole ring sustains only one cp.async.bulk per ~360-500 clk (issue + mbarrier
+    // round trip are serialised in that thread: scratch/bulk_bench2.cu), i.e. ~25-34 B/clk -- half of what the
+    // gate MMAs consume.  RO_NPROD threads in different warps take the stages round-robin instead.
+    if (lane == 0) {
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) ++my_tiles;
+      const uint32_t total = (a.flags & 1) ? 0u : (uint32_t)my_tiles * nsteps * (RO_NP * RO_NKC);
+      for (uint32_t it = warp - 8; it < total; it += RO_NPROD) {
+        const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, pk = it % (RO_NP * RO_NKC);
+        mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(W_FULL + 8 * s, RO_STAGE_BYTES);
+        bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)pk * RO_STAGE_BYTES, RO_STAGE_BYTES, W_FULL + 8 * s);
+      }
+    }
+  } else if (warp == 8 + RO_NPROD) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      uint32_t it = 0, pc = 0, sc = 0;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
+        for (int t = 0; t < nsteps; ++t, ++sc) {
+          const uint32_t par = sc & 1u;
+          long long* dbg = (a.dbg && blockIdx.x == 0 && sc < 64) ? a.dbg + sc * 32 + 16 : nullptr;
+          mbar_wait(ATT_READY, par);
+          tc_fence_after();
+          if (dbg) dbg[0] = clock64();
+          // ---- aggregation: mh = att x h (committed first: its conversion is on the critical path), mc = att x c
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t da = make_desc_sw128(sbase + RS_ATT + (ks >> 2) * RO_BLK) + (uint64_t)((ks & 3) * 2);
+              const uint64_t db = make_desc_sw128_mn(sbase + (which ? RS_C : RS_H) + ks * 2048, RO_BLK, 1024);
+              umma_bf16(tmem_base + (which ? RT_MC : RT_MH), da, db, kIdescAggMN, ks ? 1u : 0u);
+            }
+            if (which == 0) umma_commit(AGG_FULL);
+          }
+          if (dbg) dbg[1] = clock64();
+          mbar_wait(E_READY, par);
+          tc_fence_after();
+          if (dbg) dbg[2] = clock64();
+          // ---- gate GEMM: 4 passes x 5 k-chunks; the mh chunks of pass 0 wait for the conversion
+          for (int p = 0; p < RO_NP; ++p, ++pc) {
+            const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+            mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + RT_ACC0 + b * RT_ACC_STRIDE;
+            if (dbg) dbg[3 + 2 * p] = clock64();
+            for (int kc = 0; kc < RO_NKC; ++kc, ++it) {
+              if (p == 0 && kc == 3) {
+                mbar_wait(MH_READY, par);
+                tc_fence_after();
+                if (dbg) dbg[12] = clock64();
+              }
+              const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u;
+              if (!(a.flags & 1)) mbar_wait(W_FULL + 8 * s, ph);
+              tc_fence_after();
+              const uint64_t da = make_desc_sw128(sbase + RS_E + kc * RO_BLK);
+              const uint64_t db = make_desc_sw128(sbase + RS_W + s * RO_STAGE_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdescGate, (kc | ks) ? 1u : 0u);
+              if (!(a.flags & 1)) umma_commit(W_EMPTY + 8 * s);
+            }
+            umma_commit(ACC_FULL + 8 * b);
+            if (dbg) dbg[4 + 2 * p] = clock64();
+          }
+        }
+    }
+  } else {
+    // =============================== workers ===============================
+    const int q = warp & 3, hsel = warp >> 2;
+    const int r = q * 32 + lane;           // this thread's row: TMEM lane, attention row, epilogue row (== tid & 127)
+    const int rx = tid >> 1, khalf = tid & 1;  // operand-build mapping for e: row, 32 k's
+    const int N = a.N;
+    const int sb = (r / N) * N;            // first row of this row's scene inside the tile
+    const int jn = N >= 16 ? (N >> 1) : (hsel == 0 ? N : 0);
+    const int jbeg = N >= 16 ? hsel * jn : 0;
+    const float LOG2E = 1.4426950408889634f;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t pc = 0, sc = 0;
+
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int row0 = tile * 128;
+      const int gr = row0 + r, grx = row0 + rx;
+      worker_sync();   // every worker has stored the previous tile's last h' / read its s_val before the reset
+      const bool rok = gr < a.R;
+      const bool v = rok && a.valid[gr] != 0;
+      const bool xok = grx < a.R;
+      if (hsel == 0) s_val[r] = v ? 1 : 0;
+      // zero the recurrent state images (h, c)
+      {
+        uint4* hz = reinterpret_cast<uint4*>(smem + RS_H);
+        uint4* cz = reinterpret_cast<uint4*>(smem + RS_C);
+#pragma unroll
+        for (int k = 0; k < 2 * RO_BLK / 16 / RO_WORKERS; ++k) {
+          hz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
+          cz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      float c[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) c[i] = 0.f;
+      float2 pn = make_float2(0.f, 0.f), vn = make_float2(0.f, 0.f), prevp = make_float2(0.f, 0.f);
+      if (xok) {
+        pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)grx * a.F);
+        vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)grx * a.T);
+      }
+      float2 visv = vn;
+
+      for (int t = 0; t < nsteps; ++t, ++sc) {
+        const uint32_t par = sc & 1u;
+        const bool emit = t >= a.T - 1;
+        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && sc < 64) ? a.dbg + sc * 32 : nullptr;
+        if (dbg) dbg[0] = clock64();
+        // ---- (a) current position and the cell input x = [cur - prev | vislet]
+        float2 cur;
+        if (t < a.T) {
+          cur = pn;
+          visv = vn;
+        } else {
+          cur = s_next[rx];
+        }
+        float4 xv = make_float4(0.f, 0.f, visv.x, visv.y);
+        if (t > 0) {
+          xv.x = __fsub_rn(cur.x, prevp.x);
+          xv.y = __fsub_rn(cur.y, prevp.y);
+        }
+        prevp = cur;
+        if (khalf == 0) s_cur[rx] = cur;
+        if (t + 1 < a.T && xok) {   // prefetch the next observed frame
+          pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)grx * a.F + (t + 1));
+          vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)grx * a.T + (t + 1));
+        }
+        worker_sync();   // s_cur (and, on a tile's first step, s_val and the zeroed state) visible
+        // ---- (b) attention row r against columns [jbeg, jbeg + jn) of its scene (un-normalised)
+        {
+          const float2 pi = s_cur[r];
+          float sum = 0.f;
+          for (int j8 = jbeg; j8 < jbeg + jn; j8 += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int qq = 0; qq < 8; qq += 2) {
+              float e2[2];
+#pragma unroll
+              for (int z = 0; z < 2; ++z) {
+                const int j = sb + j8 + qq + z;
+                const float2 pj = s_cur[j];
+                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y);
+                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                const bool adj = v && s_val[j] != 0 && j != r && d2 < a.r2;
+                const float kern = ex2_fast(d2 * a.neg_inv_log2e);   // exp(-d2 / 2 sigma^2)
+                e2[z] = adj ? ex2_fast(kern * LOG2E) : 0.f;          // exp(kern): softmax numerator
+              }
+              pk[qq >> 1] = pack_bf16x2(e2[0], e2[1]);
+              sum += bf16_lo(pk[qq >> 1]) + bf16_hi(pk[qq >> 1]);    // normalise by what the MMA really sums
+            }
+            const int jt = sb + j8;
+            *reinterpret_cast<uint4*>(smem + RS_ATT + (jt >> 6) * RO_BLK + sw128_off(r, jt & 63)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          s_sum[hsel * 128 + r] = sum;
+        }
+        fence_proxy_async();   // generic-proxy smem writes (att; h', c' of the previous step) -> async proxy
+        tc_fence_before();
+        mbar_arrive(ATT_READY);
+        if (dbg) dbg[1] = clock64();
+        // ---- (c) e = relu(x W_e + b_e) -> block 0 (row rx, 32 k's); weights as 128-bit shared loads (4 k each)
+        {
+          const int k0 = khalf * 32;
+#pragma unroll
+          for (int kk = 0; kk < 32; kk += 8) {
+            float e8[8];
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const int k = k0 + kk + hq * 4;
+              const float4 w0 = *reinterpret_cast<const float4*>(s_we + k);
+              const float4 w1 = *reinterpret_cast<const float4*>(s_we + 64 + k);
+              const float4 w2 = *reinterpret_cast<const float4*>(s_we + 128 + k);
+              const float4 w3 = *reinterpret_cast<const float4*>(s_we + 192 + k);
+              const float4 bb = *reinterpret_cast<const float4*>(s_we + 256 + k);
+              e8[hq * 4 + 0] = fmaf(xv.w, w3.x, fmaf(xv.z, w2.x, fmaf(xv.y, w1.x, fmaf(xv.x, w0.x, bb.x))));
+              e8[hq * 4 + 1] = fmaf(xv.w, w3.y, fmaf(xv.z, w2.y, fmaf(xv.y, w1.y, fmaf(xv.x, w0.y, bb.y))));
+              e8[hq * 4 + 2] = fmaf(xv.w, w3.z, fmaf(xv.z, w2.z, fmaf(xv.y, w1.z, fmaf(xv.x, w0.z, bb.z))));
+              e8[hq * 4 + 3] = fmaf(xv.w, w3.w, fmaf(xv.z, w2.w, fmaf(xv.y, w1.w, fmaf(xv.x, w0.w, bb.w))));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e8[i] = xok ? fmaxf(e8[i], 0.f) : 0.f;
+            *reinterpret_cast<uint4*>(smem + RS_E + sw128_off(rx, k0 + kk)) =
+                make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]),
+                           pack_bf16x2(e8[6], e8[7]));
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(E_READY);
+        worker_sync();   // both halves of every attention row sum are written
+        const float ssum = s_sum[r] + s_sum[128 + r];
+        const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
+        if (dbg) dbg[2] = clock64();
+        // ---- (d) mh: TMEM -> normalise -> bf16 -> A-operand blocks 3,4 (this thread: row r, units 64 hsel ..)
+        mbar_wait(AGG_FULL, par);
+        tc_fence_after();
+        if (dbg) dbg[3] = clock64();
+#pragma unroll
+        for (int ch = 0; ch < 8; ch += 2) {
+          float v0[8], v1[8];
+          tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8, v0);
+          tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8 + 8, v1);
+          tmem_wait_ld();
+          uint8_t* dst = smem + RS_MH + hsel * RO_BLK + r * 128;
+          *reinterpret_cast<uint4*>(dst + ((ch ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(v0[0] * inv, v0[1] * inv), pack_bf16x2(v0[2] * inv, v0[3] * inv),
+                         pack_bf16x2(v0[4] * inv, v0[5] * inv), pack_bf16x2(v0[6] * inv, v0[7] * inv));
+          *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16x2(v1[0] * inv, v1[1] * inv), pack_bf16x2(v1[2] * inv, v1[3] * inv),
+                         pack_bf16x2(v1[4] * inv, v1[5] * inv), pack_bf16x2(v1[6] * inv, v1[7] * inv));
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(MH_READY);
+        if (dbg) dbg[4] = clock64();
+
+        // ---- (e) gate epilogue: 4 passes x 2 sub-chunks of 8 units
+        float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t hreg[RO_NP][8];   // h' of this step (bf16 pairs); stored once every gate MMA has read h
+#pragma unroll
+        for (int p = 0; p < RO_NP; ++p) {
+          const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+          mbar_wait(ACC_FULL + 8 * b, bph);
+          tc_fence_after();
+          if (dbg) dbg[5 + 2 * p] = clock64();
+          const uint32_t t_acc = t_row + RT_ACC0 + b * RT_ACC_STRIDE;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int ul = hsel * 16 + sub * 8;   // unit within pass
+            const int u = p * RO_UN + ul;         // global unit
+            float zi[8], zj[8], zo[8], zm[8];
+            tmem_ld8(t_acc + ul, zi);
+            tmem_ld8(t_acc + RO_UN + ul, zj);
+            tmem_ld8(t_acc + 2 * RO_UN + ul, zo);
+            tmem_ld8(t_row + RT_MC + u, zm);
+            tmem_wait_ld();
+            float ho[8], fo[8];
+            float* cc = &c[p * 16 + sub * 8];
+            if (v && !(a.flags & 2)) {
+              const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
+              const float2 inv2 = make_float2(inv, inv);
+#pragma unroll
+              for (int hq = 0; hq < 2; ++hq) {
+                const int uu = u + hq * 4;
+                const float4 bI = *reinterpret_cast<const float4*>(s_bias + uu);
+                const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + uu);
+                const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + uu);
+                const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + uu);
+                const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + uu);
+                const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + uu);
+                const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + uu);
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                  const int i0 = hq * 4 + pr * 2;
+                  auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
+                  const float2 c2 = make_float2(cc[i0], cc[i0 + 1]);
+                  const float2 m2 = fmul2(make_float2(zm[i0], zm[i0 + 1]), inv2);
+                  float2 tt = fadd2(make_float2(zi[i0], zi[i0 + 1]), sel(bI));
+                  tt = ffma2(sel(pIf), m2, tt);
+                  tt = ffma2(sel(pIt), c2, tt);
+                  const float2 g = ffma2(tanh2(tt), kHalf, kHalf);
+                  const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
+                  const float2 cf = ffma2(g, ffma2(m2, kNeg, tj), m2);   // (1-g) mc + g tanh j
+                  const float2 ct = ffma2(g, ffma2(c2, kNeg, tj), c2);   // (1-g) c  + g tanh j
+                  float2 o = fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO));
+                  o = ffma2(sel(pOf), cf, o);
+                  o = ffma2(sel(pOt), ct, o);
+                  const float2 qv = ffma2(tanh2(o), kHalf, kHalf);
+                  const float2 h2 = fmul2(qv, tanh2(ct));
+                  ho[i0] = h2.x; ho[i0 + 1] = h2.y;
+                  cc[i0] = ct.x; cc[i0 + 1] = ct.y;
+                  if (emit) {
+                    const float2 f2 = fmul2(qv, tanh2(cf));
+                    fo[i0] = f2.x; fo[i0 + 1] = f2.y;
+                  }
+                }
+              }
+              // c' (bf16) -> B operand of the next step's aggregation (its MMAs of this step are complete)
+              *reinterpret_cast<uint4*>(smem + RS_C + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(cc[0], cc[1]), pack_bf16x2(cc[2], cc[3]), pack_bf16x2(cc[4], cc[5]),
+                             pack_bf16x2(cc[6], cc[7]));
+#pragma unroll
+              for (int i = 0; i < 4; ++i) hreg[p][sub * 4 + i] = pack_bf16x2(ho[2 * i], ho[2 * i + 1]);
+              if (emit) {
+#pragma unroll
+                for (int hsrc = 0; hsrc < 2; ++hsrc) {
+                  const float4* wp = reinterpret_cast<const float4*>(s_wh + (size_t)(hsrc * RO_U + u) * 5);
+                  float wv[40];
+#pragma unroll
+                  for (int k4 = 0; k4 < 10; ++k4) {
+                    const float4 t4 = wp[k4];
+                    wv[4 * k4] = t4.x; wv[4 * k4 + 1] = t4.y; wv[4 * k4 + 2] = t4.z; wv[4 * k4 + 3] = t4.w;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int z = 0; z < 5; ++z) y[z] = fmaf(hsrc ? fo[i] : ho[i], wv[i * 5 + z], y[z]);
+                }
+              }
+            }
+          }
+          if (p == RO_NP - 1 && v) {
+            // every gate MMA of this step has completed (ACC_FULL of the last pass): h may be overwritten
+#pragma unroll
+            for (int pp = 0; pp < RO_NP; ++pp)
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                const int u = pp * RO_UN + hsel * 16 + sub * 8;
+                *reinterpret_cast<uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
+                    make_uint4(hreg[pp][sub * 4], hreg[pp][sub * 4 + 1], hreg[pp][sub * 4 + 2], hreg[pp][sub * 4 + 3]);
+              }
+          }
+          tc_fence_before();
+          mbar_arrive(ACC_EMPTY + 8 * b);
+          ++pc;
+        }
+        if (dbg) dbg[13] = clock64();
+        // ---- (f) head: combine the two column halves of each row, emit the 5 parameters and the next position
+        if (emit) {
+          if (hsel == 1) {
+#pragma unroll
+            for (int z = 0; z < 5; ++z) s_head[r * 5 + z] = y[z];
+          }
+          worker_sync();
+          if (hsel == 0) {
+            float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (v) {
+#pragma unroll
+              for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + s_wh[256 * 5 + z];
+              o[2] = __expf(o[2]);
+              o[3] = __expf(o[3]);
+              o[4] = tanh_fast(o[4]);
+            }
+            if (rok) {
+              float* po = a.params + ((size_t)gr * a.P + (t - (a.T - 1))) * 5;
+#pragma unroll
+              for (int z = 0; z < 5; ++z) po[z] = o[z];
+            }
+            const float2 cp = s_cur[r];
+            s_next[r] = make_float2(cp.x + o[0], cp.y + o[1]);
+          }
+          worker_sync();
+        }
+        if (dbg) dbg[14] = clock64();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+// pos[R,F,2], vis[R,T,2], valid[R] -> params[R,P,5].  Requires 128 % N == 0, N >= 8, U = 128, E = 64.
+int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
+                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, cudaStream_t stream) {
+  RoArgs a = {};
+  a.pos = pos; a.vis = vis; a.valid = valid;
+  a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
+  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
+  a.params = params;
+  a.R = S * N; a.N = N; a.T = T; a.P = P; a.F = T + P;
+  a.num_tiles = (a.R + 127) / 128;
+  a.r2 = r2; a.neg_inv_log2e = -inv_2sigma2 * 1.4426950408889634f;
+  a.dbg = dbg;
+  a.flags = getenv("MMT_RO_FLAGS") ? atoi(getenv("MMT_RO_FLAGS")) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  rollout_tc_kernel<<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  count_launch();
+  return check_launch("rollout_tc_kernel");
+}
+
+}  // namespace mmt

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-PREC_F32, PREC_BF16 = 0, 1
+PREC_F32, PREC_BF16, PREC_BF16_STEPWISE = 0, 1, 2
 
 
 def _p(t):
@@ -254,6 +254,22 @@ def scene_batch(frame_ids, frame_row_start, ped_id, xy, vis, win_start, N, F, fs
     return pos, vo, valid, slot
 
 
+def rollout_bf16(pos, vis, valid, params: CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, out=None, timeline=None):
+    """The T+P-1 step recurrence as one persistent tcgen05 kernel with the state on chip (mmt_rollout_bf16):
+    pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N] -> params[S,N,P,5].  N in {8,16,32,64,128}."""
+    lib = _lib.load()
+    _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis"); _chk(valid, torch.uint8, "valid")
+    S, N = valid.shape
+    if params.W_packed is None:
+        params.pack()
+    if out is None:
+        out = torch.empty((S, N, P, 5), dtype=torch.float32, device=pos.device)
+    cw = params.c_cell()
+    _lib.check(lib.mmt_rollout_bf16(_p(pos), _p(vis), _p(valid), C.byref(cw), S, N, T, P, r2, inv_2sigma2, _p(out),
+                                    _p(timeline), _stream()), "mmt_rollout_bf16")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 class Forecaster:
     """The whole hot path behind one call (mmt_forecast_f32): workspace and outputs are allocated
@@ -266,7 +282,7 @@ class Forecaster:
         self._graph = self._graph_key = None
         self._graph_n = 0
         self.p = params
-        if prec == PREC_BF16 and params.W_packed is None:
+        if prec != PREC_F32 and params.W_packed is None:
             params.pack()
         self.cfg = _lib.ForecastCfg(S, N, T, P, K, r2, inv_2sigma2, int(relational), prec, seed, agent_offset)
         He = params.W2.shape[0] if (relational and params.W2 is not None) else 0
