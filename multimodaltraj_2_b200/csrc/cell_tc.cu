@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           const uint32_t d_tmem = tmem_base + b * TC_ACC_STRIDE;
           for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
             const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
-            mbar_wait(W_FULL + 8 * s, ph);
-            tc_fence_after();
+            mbar_wait(W_FULL + 8 * s, ph);   // written by the async proxy: no tcgen05 fence needed
             const uint64_t da = make_desc_sw128(sbase + SM_A + kc * TC_A_BLOCK);
             const uint64_t db = make_desc_sw128(sbase + SM_W + s * TC_STAGE_BYTES);
 #pragma unroll

@@ -4,19 +4,23 @@
 // ON CHIP.  ("tensor pipe only if the 20-step recurrence is fused with on-chip state".)
 //
 // One CTA per SM owns a 128-row tile (128/N whole scenes) for all its steps:
-//   shared memory  E | H | MH          bf16 [128 rows x 64 k] SWIZZLE_128B blocks = the K-major A operand
-//                                      [e | h | mh] of the gate GEMM (K = 320 = 5 blocks)
-//                  H, C                the same images are the MN-major B operand (agents along K, units
-//                                      along N) of the aggregation GEMMs  mh = att x h,  mc = att x c
-//                  ATT                 block-diagonal un-normalised attention, K-major A operand
-//                  W ring              gate weights streamed from L2 by cp.async.bulk, 12 KB stages
-//   tensor memory  2 gate accumulators (96 columns: i|j|o of 32 units) + mc (128) + mh (128)
+//   tensor memory  A operand of the gate GEMM [e | h | mh] as bf16 pairs (160 columns; the MMAs take A
+//                  from TMEM, so only the weights cross shared memory), 2 gate accumulators (96 columns:
+//                  i|j|o of 32 units), mc accumulator (128), mh accumulator (128, aliases accumulator 1)
+//   shared memory  H, C   bf16 [agent][unit] SWIZZLE_128B images = MN-major B operand (agents along K) of
+//                         the aggregation GEMMs  mh = att x h,  mc = att x c
+//                  ATT    block-diagonal un-normalised attention, K-major A operand of the aggregation
+//                  W ring gate weights streamed from L2 by cp.async.bulk, 8 stages of 12 KB (one k-chunk)
 //   registers      fp32 cell state c: 64 values per worker thread (row x 16 units x 4 passes)
 // Only positions / vislets are read from HBM and only the 5 head parameters per predicted step are
 // written: ~0.5 KB per agent-trajectory instead of ~30 KB per agent for the per-step kernels.
 //
-// Warp roles: warps 0-7 workers (attention build, operand build, TMEM->smem conversion of mh, gate
-// epilogue, head); warps 8-10 stream weight stages; warp 11 issues every tcgen05.mma.
+// Warp roles: warps 0-7 workers (attention build, e / mh operand build, gate epilogue, head);
+// warps 8-9 stream weight stages; warps 10-11 issue the tcgen05.mma (gate passes alternate between them).
+// Measured design inputs (scratch/mma_bench.cu, bulk_bench2.cu, mufu_bench2.cu on B200): an SS-form
+// M128 x N96 MMA re-reads 4 KB of A from shared memory per 48-clk MMA and, together with the workers'
+// own shared-memory traffic, ran at 83-90 clk in situ; one thread managing a bulk-copy ring sustains one
+// copy per ~360 clk; MUFU.TANH / EX2 issue 16 lanes/clk/SM.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -25,23 +29,24 @@
 
 namespace mmt {
 
-constexpr int RO_U = 128, RO_E = 64;
-constexpr int RO_UN = 32;                     // units per gate pass
-constexpr int RO_NP = RO_U / RO_UN;           // 4 passes
-constexpr int RO_N = 3 * RO_UN;               // 96 accumulator columns per pass
-constexpr int RO_NKC = 5;                     // k-chunks of 64: e | h0 h1 | mh0 mh1
-constexpr int RO_BLK = 128 * 128;             // one [128 rows x 128 B] block
-constexpr int RO_STAGE_BYTES = RO_N * 64 * 2; // 12288
-constexpr int RO_NSTAGE = 5;
+constexpr int RO_U = 128;
+constexpr int RO_UN = 32;                       // units per gate pass
+constexpr int RO_NP = RO_U / RO_UN;             // 4 passes
+constexpr int RO_N = 3 * RO_UN;                 // 96 accumulator columns per pass
+constexpr int RO_NKC = 5;                       // k-chunks of 64: e | h0 h1 | mh0 mh1
+constexpr int RO_NCH = RO_NP * RO_NKC;          // 20 weight chunks per step
+constexpr int RO_BLK = 128 * 128;               // one [128 rows x 128 B] block
+constexpr int RO_CHUNK_BYTES = RO_N * 64 * 2;   // 12288: one (pass, k-chunk) of the packed weights
+constexpr int RO_STAGE_BYTES = RO_CHUNK_BYTES;
+constexpr int RO_NSTAGE = 8;
 constexpr int RO_WORKERS = 256;
-constexpr int RO_NPROD = 3;                   // weight-stage producer warps (one issuing thread each)
-constexpr int RO_THREADS = RO_WORKERS + 32 * (RO_NPROD + 1);
+constexpr int RO_NPROD = 2;                     // weight-stage producer warps (one issuing thread each)
+constexpr int RO_NISSUE = 2;                    // MMA-issuing warps: passes p % 2 == j (one thread tops out at ~68 clk/MMA)
+constexpr int RO_THREADS = RO_WORKERS + 32 * (RO_NPROD + RO_NISSUE);
 
-constexpr int RS_E = 0;
-constexpr int RS_H = RS_E + RO_BLK;           // 2 blocks
-constexpr int RS_MH = RS_H + 2 * RO_BLK;      // 2 blocks
-constexpr int RS_C = RS_MH + 2 * RO_BLK;      // 2 blocks
-constexpr int RS_ATT = RS_C + 2 * RO_BLK;     // 2 blocks
+constexpr int RS_H = 0;                         // 2 blocks (units 0-63 | 64-127)
+constexpr int RS_C = RS_H + 2 * RO_BLK;         // 2 blocks
+constexpr int RS_ATT = RS_C + 2 * RO_BLK;       // 2 blocks (agents 0-63 | 64-127 along K)
 constexpr int RS_W = RS_ATT + 2 * RO_BLK;
 constexpr int RS_BAR = RS_W + RO_NSTAGE * RO_STAGE_BYTES;
 constexpr int RS_TMEM = RS_BAR + 256;
@@ -49,14 +54,19 @@ constexpr int RS_BIAS = RS_TMEM + 16;                  // b[384], w_If, w_It, w_
 constexpr int RS_WE = RS_BIAS + (384 + 512) * 4;       // W_e[4][64], b_e[64]
 constexpr int RS_WH = RS_WE + (256 + 64) * 4;          // W_h[256][5], b_h[5] (+3 pad)
 constexpr int RS_HEAD = RS_WH + (256 * 5 + 8) * 4;     // head partials [128][5]
-constexpr int RS_CUR = RS_HEAD + 128 * 5 * 4;          // float2[128] current positions
-constexpr int RS_NEXT = RS_CUR + 1024;                 // float2[128] predicted next positions
+constexpr int RS_PX = RS_HEAD + 128 * 5 * 4;           // float[128] current x (invalid agents: far away)
+constexpr int RS_PY = RS_PX + 512;                     // float[128] current y
+constexpr int RS_NEXT = RS_PY + 512;                   // float2[128] predicted next positions
 constexpr int RS_SUM = RS_NEXT + 1024;                 // float[2][128] attention row sums
-constexpr int RS_VAL = RS_SUM + 1024;                  // u8[128]
-constexpr int RS_TOTAL = RS_VAL + 128;
+constexpr int RS_TOTAL = RS_SUM + 1024;
 static_assert(RS_TOTAL + 1024 <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t RT_ACC0 = 0, RT_ACC_STRIDE = 128, RT_MC = 256, RT_MH = 384;
+// tensor-memory columns
+constexpr uint32_t RT_A = 0;          // A operand: e (32 columns) | h (64) | mh (64), two bf16 per column
+constexpr uint32_t RT_A_H = 32, RT_A_MH = 96;
+constexpr uint32_t RT_ACC0 = 160, RT_ACC1 = 256;
+constexpr uint32_t RT_MH = 256;       // mh accumulator (fp32, 128 columns): aliases accumulator 1 + 32 spare columns
+constexpr uint32_t RT_MC = 384;       // mc accumulator (fp32, 128 columns)
 constexpr uint32_t kIdescGate = make_idesc_bf16(128, RO_N);
 constexpr uint32_t kIdescAggMN = make_idesc_bf16(128, 128) | (1u << 16);   // B operand MN-major
 
@@ -69,7 +79,7 @@ struct RoArgs {
   float* params;         // [R, P, 5]
   int R, N, T, P, F, num_tiles;
   float r2, neg_inv_log2e;
-  int flags;  // TEMP diagnostics: 1 = no weight streaming / waits; 2 = workers skip the gate math
+  int flags;  // TEMP diagnostics: 1 no weight streaming; 2 no gate math; 4 no epilogue TMEM loads; 8 no c'/h' smem stores
   long long* dbg;        // optional [64 steps][32] clock64 stamps of CTA 0: [0,16) worker thread 0, [16,32) MMA thread
 };
 
@@ -84,6 +94,12 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+// wait executed by a whole (convergent) warp: reconverge before the next elect.sync
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -101,10 +117,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   float* s_we = reinterpret_cast<float*>(smem + RS_WE);
   float* s_wh = reinterpret_cast<float*>(smem + RS_WH);
   float* s_head = reinterpret_cast<float*>(smem + RS_HEAD);
-  float2* s_cur = reinterpret_cast<float2*>(smem + RS_CUR);
+  float* s_px = reinterpret_cast<float*>(smem + RS_PX);
+  float* s_py = reinterpret_cast<float*>(smem + RS_PY);
   float2* s_next = reinterpret_cast<float2*>(smem + RS_NEXT);
   float* s_sum = reinterpret_cast<float*>(smem + RS_SUM);
-  uint8_t* s_val = smem + RS_VAL;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + RS_TMEM);
   const int nsteps = a.T + a.P - 1;
 
@@ -146,96 +162,121 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
 
   if (warp >= 8 && warp < 8 + RO_NPROD) {
     // =============================== weight-stage producers ===============================
-    // One thread managing the whole ring sustains only one cp.async.bulk per ~360-500 clk (issue + mbarrier
-    // round trip are serialised in that thread: scratch/bulk_bench2.cu), i.e. ~25-34 B/clk -- half of what the
-    // gate MMAs consume.  RO_NPROD threads in different warps take the stages round-robin instead.
+    // One thread managing a whole ring sustains only one cp.async.bulk per ~360 clk (issue + mbarrier round
+    // trip serialise in that thread: scratch/bulk_bench2.cu); RO_NPROD threads in different warps take the
+    // stages round-robin instead.
     if (lane == 0) {
       int my_tiles = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) ++my_tiles;
-      const uint32_t total = (a.flags & 1) ? 0u : (uint32_t)my_tiles * nsteps * (RO_NP * RO_NKC);
+      const uint32_t total = (a.flags & 1) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
       for (uint32_t it = warp - 8; it < total; it += RO_NPROD) {
-        const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, pk = it % (RO_NP * RO_NKC);
+        const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, pk = it % RO_NCH;
         mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(W_FULL + 8 * s, RO_STAGE_BYTES);
         bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)pk * RO_STAGE_BYTES, RO_STAGE_BYTES, W_FULL + 8 * s);
       }
     }
-  } else if (warp == 8 + RO_NPROD) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      uint32_t it = 0, pc = 0, sc = 0;
+  } else if (warp >= 8 + RO_NPROD) {
+    // =============================== MMA issuers ===============================
+    // Issuer 0: aggregation + gate passes 0, 2; issuer 1: gate passes 1, 3.  Two issuing threads reach the
+    // nominal 48 clk per M128 x N96 MMA where one tops out at ~68 (scratch/mma_bench3.cu); passes use different
+    // accumulators, so their MMAs may interleave freely in the tensor pipe.
+    {   // the whole warp runs this code convergently; one elected lane issues each tcgen05 instruction
+      const int me = warp - (8 + RO_NPROD);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t sc = 0;
+      const uint64_t d_att0 = make_desc_sw128(sbase + RS_ATT), d_att1 = make_desc_sw128(sbase + RS_ATT + RO_BLK);
+      const uint64_t d_h = make_desc_sw128_mn(sbase + RS_H, RO_BLK, 1024);
+      const uint64_t d_c = make_desc_sw128_mn(sbase + RS_C, RO_BLK, 1024);
+      const uint64_t d_w = make_desc_sw128(sbase + RS_W);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
         for (int t = 0; t < nsteps; ++t, ++sc) {
           const uint32_t par = sc & 1u;
-          long long* dbg = (a.dbg && blockIdx.x == 0 && sc < 64) ? a.dbg + sc * 32 + 16 : nullptr;
-          mbar_wait(ATT_READY, par);
-          tc_fence_after();
-          if (dbg) dbg[0] = clock64();
-          // ---- aggregation: mh = att x h (committed first: its conversion is on the critical path), mc = att x c
-#pragma unroll
-          for (int which = 0; which < 2; ++which) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t da = make_desc_sw128(sbase + RS_ATT + (ks >> 2) * RO_BLK) + (uint64_t)((ks & 3) * 2);
-              const uint64_t db = make_desc_sw128_mn(sbase + (which ? RS_C : RS_H) + ks * 2048, RO_BLK, 1024);
-              umma_bf16(tmem_base + (which ? RT_MC : RT_MH), da, db, kIdescAggMN, ks ? 1u : 0u);
-            }
-            if (which == 0) umma_commit(AGG_FULL);
-          }
-          if (dbg) dbg[1] = clock64();
-          mbar_wait(E_READY, par);
-          tc_fence_after();
-          if (dbg) dbg[2] = clock64();
-          // ---- gate GEMM: 4 passes x 5 k-chunks; the mh chunks of pass 0 wait for the conversion
-          for (int p = 0; p < RO_NP; ++p, ++pc) {
-            const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
-            mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u);
+          long long* dbg = (a.dbg && blockIdx.x == 0 && lane == 0 && sc < 64) ? a.dbg + sc * 32 + 16 : nullptr;
+          long long wwait = 0;
+          if (me == 0) {
+            mbar_wait_warp(ATT_READY, par);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + RT_ACC0 + b * RT_ACC_STRIDE;
+            if (dbg) dbg[0] = clock64();
+            // ---- aggregation: mh = att x h (committed first: its conversion is on the critical path), mc = att x c
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_elect(tmem_u + RT_MH, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_h + (uint64_t)(ks * 128),
+                        kIdescAggMN, ks ? 1u : 0u);
+            umma_commit_elect(AGG_FULL);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_bf16_elect(tmem_u + RT_MC, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_c + (uint64_t)(ks * 128),
+                        kIdescAggMN, ks ? 1u : 0u);
+            if (dbg) dbg[1] = clock64();
+          }
+          mbar_wait_warp(E_READY, par);
+          if (me == 1) mbar_wait_warp(MH_READY, par);   // accumulator 1 aliases the mh accumulator: wait for its conversion
+          tc_fence_after();
+          if (dbg && me == 0) dbg[2] = clock64();
+          // ---- gate GEMM: passes me, me + 2: 5 k-chunks each, A from tensor memory
+#pragma unroll 1
+          for (int p = me; p < RO_NP; p += RO_NISSUE) {
+            const uint32_t pc = sc * RO_NP + p;      // global pass counter: accumulator p & 1, use number pc >> 1
+            const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
+            mbar_wait_warp(ACC_EMPTY + 8 * b, bph ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + (b ? RT_ACC1 : RT_ACC0);
             if (dbg) dbg[3 + 2 * p] = clock64();
+            uint32_t it = sc * RO_NCH + p * RO_NKC;
+#pragma unroll
             for (int kc = 0; kc < RO_NKC; ++kc, ++it) {
-              if (p == 0 && kc == 3) {
-                mbar_wait(MH_READY, par);
+              if (p == 0 && kc == 3) {   // the mh chunks of pass 0 wait for the conversion
+                mbar_wait_warp(MH_READY, par);
                 tc_fence_after();
                 if (dbg) dbg[12] = clock64();
               }
-              const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u;
-              if (!(a.flags & 1)) mbar_wait(W_FULL + 8 * s, ph);
-              tc_fence_after();
-              const uint64_t da = make_desc_sw128(sbase + RS_E + kc * RO_BLK);
-              const uint64_t db = make_desc_sw128(sbase + RS_W + s * RO_STAGE_BYTES);
+              const uint32_t s = it % RO_NSTAGE;
+              if (!(a.flags & 1)) {
+                const long long w0 = (dbg && (a.flags & 16)) ? clock64() : 0;
+                // no tcgen05.fence here: the stage was written by the async proxy (bulk copy -> mbarrier), not by another
+                // thread's tcgen05 operation; a fence per chunk drained the MMA pipeline (pass 2650 -> see profiles/)
+                mbar_wait_warp(W_FULL + 8 * s, (it / RO_NSTAGE) & 1u);
+                if (dbg && (a.flags & 16)) wwait += clock64() - w0;
+              }
+              const uint64_t db = d_w + (uint64_t)((s * RO_STAGE_BYTES) >> 4);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdescGate, (kc | ks) ? 1u : 0u);
-              if (!(a.flags & 1)) umma_commit(W_EMPTY + 8 * s);
+                umma_bf16_ts_elect(d_tmem, tmem_u + RT_A + kc * 32 + ks * 8, db + (uint64_t)(ks * 2), kIdescGate,
+                             (kc | ks) ? 1u : 0u);
+              if (!(a.flags & 1)) umma_commit_elect(W_EMPTY + 8 * s);
             }
-            umma_commit(ACC_FULL + 8 * b);
+            umma_commit_elect(ACC_FULL + 8 * b);
             if (dbg) dbg[4 + 2 * p] = clock64();
           }
+          if (dbg) dbg[13 + me] = wwait;
         }
     }
   } else {
     // =============================== workers ===============================
     const int q = warp & 3, hsel = warp >> 2;
     const int r = q * 32 + lane;           // this thread's row: TMEM lane, attention row, epilogue row (== tid & 127)
-    const int rx = tid >> 1, khalf = tid & 1;  // operand-build mapping for e: row, 32 k's
     const int N = a.N;
     const int sb = (r / N) * N;            // first row of this row's scene inside the tile
     const int jn = N >= 16 ? (N >> 1) : (hsel == 0 ? N : 0);
     const int jbeg = N >= 16 ? hsel * jn : 0;
+    // the diagonal entry (j == r) of the attention row is masked out of the packed bf16 words of its 8-column chunk
+    const int jdiag8 = (r - sb) & ~7;
+    uint32_t dmask[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      dmask[w] = (((r - sb) & 7) >> 1) == w ? (((r - sb) & 1) ? 0x0000FFFFu : 0xFFFF0000u) : 0xFFFFFFFFu;
     const float LOG2E = 1.4426950408889634f;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t pc = 0, sc = 0;
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int row0 = tile * 128;
-      const int gr = row0 + r, grx = row0 + rx;
-      worker_sync();   // every worker has stored the previous tile's last h' / read its s_val before the reset
+      const int gr = row0 + r;
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
-      const bool xok = grx < a.R;
-      if (hsel == 0) s_val[r] = v ? 1 : 0;
-      // zero the recurrent state images (h, c)
+      worker_sync();   // every worker has stored the previous tile's last h' before the reset
+      // zero the recurrent state: h, c images in shared memory and the h columns of the TMEM A operand
       {
         uint4* hz = reinterpret_cast<uint4*>(smem + RS_H);
         uint4* cz = reinterpret_cast<uint4*>(smem + RS_C);
@@ -244,14 +285,17 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           hz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
           cz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
         }
+        const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_st8(t_row + RT_A_H + hsel * 32 + k * 8, z8);
       }
       float c[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) c[i] = 0.f;
       float2 pn = make_float2(0.f, 0.f), vn = make_float2(0.f, 0.f), prevp = make_float2(0.f, 0.f);
-      if (xok) {
-        pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)grx * a.F);
-        vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)grx * a.T);
+      if (rok) {
+        pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)gr * a.F);
+        vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)gr * a.T);
       }
       float2 visv = vn;
 
@@ -260,13 +304,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         const bool emit = t >= a.T - 1;
         long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && sc < 64) ? a.dbg + sc * 32 : nullptr;
         if (dbg) dbg[0] = clock64();
-        // ---- (a) current position and the cell input x = [cur - prev | vislet]
+        // ---- (a) current position and the cell input x = [cur - prev | vislet] of row r
         float2 cur;
         if (t < a.T) {
           cur = pn;
           visv = vn;
         } else {
-          cur = s_next[rx];
+          cur = s_next[r];
         }
         float4 xv = make_float4(0.f, 0.f, visv.x, visv.y);
         if (t > 0) {
@@ -274,34 +318,45 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           xv.y = __fsub_rn(cur.y, prevp.y);
         }
         prevp = cur;
-        if (khalf == 0) s_cur[rx] = cur;
-        if (t + 1 < a.T && xok) {   // prefetch the next observed frame
-          pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)grx * a.F + (t + 1));
-          vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)grx * a.T + (t + 1));
+        if (hsel == 0) {   // invalid agents sit far away: d2 = inf fails d2 < r2 for every partner
+          s_px[r] = v ? cur.x : 3.0e18f;
+          s_py[r] = v ? cur.y : 3.0e18f;
         }
-        worker_sync();   // s_cur (and, on a tile's first step, s_val and the zeroed state) visible
-        // ---- (b) attention row r against columns [jbeg, jbeg + jn) of its scene (un-normalised)
+        if (t + 1 < a.T && rok) {   // prefetch the next observed frame
+          pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)gr * a.F + (t + 1));
+          vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)gr * a.T + (t + 1));
+        }
+        worker_sync();   // positions (and, on a tile's first step, the zeroed state) visible
+        // ---- (b) attention row r against columns [jbeg, jbeg + jn) of its scene (un-normalised), packed fp32x2 math
         {
-          const float2 pi = s_cur[r];
+          const float2 nx = make_float2(-cur.x, -cur.x), ny = make_float2(-cur.y, -cur.y);
+          const float2 cexp = make_float2(a.neg_inv_log2e, a.neg_inv_log2e), l2e = make_float2(LOG2E, LOG2E);
           float sum = 0.f;
           for (int j8 = jbeg; j8 < jbeg + jn; j8 += 8) {
             uint32_t pk[4];
 #pragma unroll
-            for (int qq = 0; qq < 8; qq += 2) {
-              float e2[2];
+            for (int hq = 0; hq < 2; ++hq) {
+              const float4 xj = *reinterpret_cast<const float4*>(s_px + sb + j8 + hq * 4);
+              const float4 yj = *reinterpret_cast<const float4*>(s_py + sb + j8 + hq * 4);
 #pragma unroll
-              for (int z = 0; z < 2; ++z) {
-                const int j = sb + j8 + qq + z;
-                const float2 pj = s_cur[j];
-                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y);
-                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                const bool adj = v && s_val[j] != 0 && j != r && d2 < a.r2;
-                const float kern = ex2_fast(d2 * a.neg_inv_log2e);   // exp(-d2 / 2 sigma^2)
-                e2[z] = adj ? ex2_fast(kern * LOG2E) : 0.f;          // exp(kern): softmax numerator
+              for (int pr = 0; pr < 2; ++pr) {
+                const float2 dx = fadd2(pr ? make_float2(xj.z, xj.w) : make_float2(xj.x, xj.y), nx);
+                const float2 dy = fadd2(pr ? make_float2(yj.z, yj.w) : make_float2(yj.x, yj.y), ny);
+                const float2 d2 = fadd2(fmul2(dx, dx), fmul2(dy, dy));
+                const float2 ka = fmul2(d2, cexp);
+                const float2 kern = make_float2(ex2_fast(ka.x), ex2_fast(ka.y));   // exp(-d2 / 2 sigma^2)
+                const float2 ea = fmul2(kern, l2e);
+                const float e0 = (v && d2.x < a.r2) ? ex2_fast(ea.x) : 0.f;       // exp(kern): softmax numerator
+                const float e1 = (v && d2.y < a.r2) ? ex2_fast(ea.y) : 0.f;
+                pk[hq * 2 + pr] = pack_bf16x2(e0, e1);
               }
-              pk[qq >> 1] = pack_bf16x2(e2[0], e2[1]);
-              sum += bf16_lo(pk[qq >> 1]) + bf16_hi(pk[qq >> 1]);    // normalise by what the MMA really sums
             }
+            if (j8 == jdiag8) {
+#pragma unroll
+              for (int w = 0; w < 4; ++w) pk[w] &= dmask[w];
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) sum += bf16_lo(pk[w]) + bf16_hi(pk[w]);   // normalise by what the MMA really sums
             const int jt = sb + j8;
             *reinterpret_cast<uint4*>(smem + RS_ATT + (jt >> 6) * RO_BLK + sw128_off(r, jt & 63)) =
                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -309,42 +364,45 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           s_sum[hsel * 128 + r] = sum;
         }
         fence_proxy_async();   // generic-proxy smem writes (att; h', c' of the previous step) -> async proxy
-        tc_fence_before();
+        tc_fence_before();     // (and the h' tcgen05.st of the previous step, already waited for)
         mbar_arrive(ATT_READY);
         if (dbg) dbg[1] = clock64();
-        // ---- (c) e = relu(x W_e + b_e) -> block 0 (row rx, 32 k's); weights as 128-bit shared loads (4 k each)
+        // ---- (c) e = relu(x W_e + b_e): row r, k in [32 hsel, 32 hsel + 32) -> A-operand columns 16 hsel .. +15
         {
-          const int k0 = khalf * 32;
+          const int k0 = hsel * 32;
 #pragma unroll
-          for (int kk = 0; kk < 32; kk += 8) {
-            float e8[8];
+          for (int kk = 0; kk < 32; kk += 16) {
+            uint32_t pk[8];
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
+            for (int hq = 0; hq < 4; ++hq) {
               const int k = k0 + kk + hq * 4;
               const float4 w0 = *reinterpret_cast<const float4*>(s_we + k);
               const float4 w1 = *reinterpret_cast<const float4*>(s_we + 64 + k);
               const float4 w2 = *reinterpret_cast<const float4*>(s_we + 128 + k);
               const float4 w3 = *reinterpret_cast<const float4*>(s_we + 192 + k);
               const float4 bb = *reinterpret_cast<const float4*>(s_we + 256 + k);
-              e8[hq * 4 + 0] = fmaf(xv.w, w3.x, fmaf(xv.z, w2.x, fmaf(xv.y, w1.x, fmaf(xv.x, w0.x, bb.x))));
-              e8[hq * 4 + 1] = fmaf(xv.w, w3.y, fmaf(xv.z, w2.y, fmaf(xv.y, w1.y, fmaf(xv.x, w0.y, bb.y))));
-              e8[hq * 4 + 2] = fmaf(xv.w, w3.z, fmaf(xv.z, w2.z, fmaf(xv.y, w1.z, fmaf(xv.x, w0.z, bb.z))));
-              e8[hq * 4 + 3] = fmaf(xv.w, w3.w, fmaf(xv.z, w2.w, fmaf(xv.y, w1.w, fmaf(xv.x, w0.w, bb.w))));
+              float e0 = fmaf(xv.w, w3.x, fmaf(xv.z, w2.x, fmaf(xv.y, w1.x, fmaf(xv.x, w0.x, bb.x))));
+              float e1 = fmaf(xv.w, w3.y, fmaf(xv.z, w2.y, fmaf(xv.y, w1.y, fmaf(xv.x, w0.y, bb.y))));
+              float e2 = fmaf(xv.w, w3.z, fmaf(xv.z, w2.z, fmaf(xv.y, w1.z, fmaf(xv.x, w0.z, bb.z))));
+              float e3 = fmaf(xv.w, w3.w, fmaf(xv.z, w2.w, fmaf(xv.y, w1.w, fmaf(xv.x, w0.w, bb.w))));
+              e0 = rok ? fmaxf(e0, 0.f) : 0.f;
+              e1 = rok ? fmaxf(e1, 0.f) : 0.f;
+              e2 = rok ? fmaxf(e2, 0.f) : 0.f;
+              e3 = rok ? fmaxf(e3, 0.f) : 0.f;
+              pk[hq * 2] = pack_bf16x2(e0, e1);
+              pk[hq * 2 + 1] = pack_bf16x2(e2, e3);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e8[i] = xok ? fmaxf(e8[i], 0.f) : 0.f;
-            *reinterpret_cast<uint4*>(smem + RS_E + sw128_off(rx, k0 + kk)) =
-                make_uint4(pack_bf16x2(e8[0], e8[1]), pack_bf16x2(e8[2], e8[3]), pack_bf16x2(e8[4], e8[5]),
-                           pack_bf16x2(e8[6], e8[7]));
+            tmem_st8(t_row + RT_A + (k0 + kk) / 2, pk);
           }
+          tmem_wait_st();
         }
-        fence_proxy_async();
+        tc_fence_before();
         mbar_arrive(E_READY);
         worker_sync();   // both halves of every attention row sum are written
         const float ssum = s_sum[r] + s_sum[128 + r];
         const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
         if (dbg) dbg[2] = clock64();
-        // ---- (d) mh: TMEM -> normalise -> bf16 -> A-operand blocks 3,4 (this thread: row r, units 64 hsel ..)
+        // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 64 hsel .. +63)
         mbar_wait(AGG_FULL, par);
         tc_fence_after();
         if (dbg) dbg[3] = clock64();
@@ -354,39 +412,43 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8, v0);
           tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8 + 8, v1);
           tmem_wait_ld();
-          uint8_t* dst = smem + RS_MH + hsel * RO_BLK + r * 128;
-          *reinterpret_cast<uint4*>(dst + ((ch ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(v0[0] * inv, v0[1] * inv), pack_bf16x2(v0[2] * inv, v0[3] * inv),
-                         pack_bf16x2(v0[4] * inv, v0[5] * inv), pack_bf16x2(v0[6] * inv, v0[7] * inv));
-          *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2(v1[0] * inv, v1[1] * inv), pack_bf16x2(v1[2] * inv, v1[3] * inv),
-                         pack_bf16x2(v1[4] * inv, v1[5] * inv), pack_bf16x2(v1[6] * inv, v1[7] * inv));
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            pk[i] = pack_bf16x2(v0[2 * i] * inv, v0[2 * i + 1] * inv);
+            pk[4 + i] = pack_bf16x2(v1[2 * i] * inv, v1[2 * i + 1] * inv);
+          }
+          tmem_st8(t_row + RT_A_MH + hsel * 32 + ch * 4, pk);
         }
+        tmem_wait_st();
         tc_fence_before();
-        fence_proxy_async();
         mbar_arrive(MH_READY);
         if (dbg) dbg[4] = clock64();
 
         // ---- (e) gate epilogue: 4 passes x 2 sub-chunks of 8 units
         float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        uint32_t hreg[RO_NP][8];   // h' of this step (bf16 pairs); stored once every gate MMA has read h
 #pragma unroll
         for (int p = 0; p < RO_NP; ++p) {
           const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
           mbar_wait(ACC_FULL + 8 * b, bph);
           tc_fence_after();
           if (dbg) dbg[5 + 2 * p] = clock64();
-          const uint32_t t_acc = t_row + RT_ACC0 + b * RT_ACC_STRIDE;
+          const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const int ul = hsel * 16 + sub * 8;   // unit within pass
             const int u = p * RO_UN + ul;         // global unit
             float zi[8], zj[8], zo[8], zm[8];
-            tmem_ld8(t_acc + ul, zi);
-            tmem_ld8(t_acc + RO_UN + ul, zj);
-            tmem_ld8(t_acc + 2 * RO_UN + ul, zo);
-            tmem_ld8(t_row + RT_MC + u, zm);
-            tmem_wait_ld();
+            if (!(a.flags & 4)) {
+              tmem_ld8(t_acc + ul, zi);
+              tmem_ld8(t_acc + RO_UN + ul, zj);
+              tmem_ld8(t_acc + 2 * RO_UN + ul, zo);
+              tmem_ld8(t_row + RT_MC + u, zm);
+              tmem_wait_ld();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) zi[i] = zj[i] = zo[i] = zm[i] = 0.01f * i;
+            }
             float ho[8], fo[8];
             float* cc = &c[p * 16 + sub * 8];
             if (v && !(a.flags & 2)) {
@@ -406,24 +468,28 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                 for (int pr = 0; pr < 2; ++pr) {
                   const int i0 = hq * 4 + pr * 2;
                   auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
+                  // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes), arranged so that
+                  // only one packed FMA separates each MUFU result from its consumer:
+                  //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
+                  //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
                   const float2 c2 = make_float2(cc[i0], cc[i0 + 1]);
                   const float2 m2 = fmul2(make_float2(zm[i0], zm[i0 + 1]), inv2);
-                  float2 tt = fadd2(make_float2(zi[i0], zi[i0 + 1]), sel(bI));
-                  tt = ffma2(sel(pIf), m2, tt);
-                  tt = ffma2(sel(pIt), c2, tt);
-                  const float2 g = ffma2(tanh2(tt), kHalf, kHalf);
+                  const float2 t1 = ffma2(sel(pIf), m2, make_float2(zi[i0], zi[i0 + 1]));
+                  const float2 t2 = ffma2(sel(pIt), c2, sel(bI));
+                  const float2 th = tanh2(fadd2(t1, t2));
                   const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
-                  const float2 cf = ffma2(g, ffma2(m2, kNeg, tj), m2);   // (1-g) mc + g tanh j
-                  const float2 ct = ffma2(g, ffma2(c2, kNeg, tj), c2);   // (1-g) c  + g tanh j
-                  float2 o = fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO));
-                  o = ffma2(sel(pOf), cf, o);
-                  o = ffma2(sel(pOt), ct, o);
-                  const float2 qv = ffma2(tanh2(o), kHalf, kHalf);
-                  const float2 h2 = fmul2(qv, tanh2(ct));
+                  const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
+                  const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
+                  const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
+                  const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO)));
+                  const float2 to = tanh2(ffma2(sel(pOt), ct, o1));
+                  const float2 ha = fmul2(tanh2(ct), kHalf);
+                  const float2 h2 = ffma2(to, ha, ha);
                   ho[i0] = h2.x; ho[i0 + 1] = h2.y;
                   cc[i0] = ct.x; cc[i0 + 1] = ct.y;
                   if (emit) {
-                    const float2 f2 = fmul2(qv, tanh2(cf));
+                    const float2 fa = fmul2(tanh2(cf), kHalf);
+                    const float2 f2 = ffma2(to, fa, fa);
                     fo[i0] = f2.x; fo[i0 + 1] = f2.y;
                   }
                 }
@@ -432,8 +498,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               *reinterpret_cast<uint4*>(smem + RS_C + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
                   make_uint4(pack_bf16x2(cc[0], cc[1]), pack_bf16x2(cc[2], cc[3]), pack_bf16x2(cc[4], cc[5]),
                              pack_bf16x2(cc[6], cc[7]));
-#pragma unroll
-              for (int i = 0; i < 4; ++i) hreg[p][sub * 4 + i] = pack_bf16x2(ho[2 * i], ho[2 * i + 1]);
+              // h' (bf16) -> shared-memory B operand of the next aggregation right away (the gate MMAs read h from
+              // TMEM, the aggregation MMAs of this step are complete); the TMEM copy follows after the last pass
+              *reinterpret_cast<uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(ho[0], ho[1]), pack_bf16x2(ho[2], ho[3]), pack_bf16x2(ho[4], ho[5]),
+                             pack_bf16x2(ho[6], ho[7]));
               if (emit) {
 #pragma unroll
                 for (int hsrc = 0; hsrc < 2; ++hsrc) {
@@ -452,16 +521,23 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               }
             }
           }
-          if (p == RO_NP - 1 && v) {
-            // every gate MMA of this step has completed (ACC_FULL of the last pass): h may be overwritten
+          if (p == RO_NP - 1) {
+            // every gate MMA of this step has completed (ACC_FULL of the last pass): the h columns of the TMEM A
+            // operand may be overwritten.  Each thread re-reads the 4 x 16 units it stored above (its own writes;
+            // rows of invalid agents stay zero) and copies them: units u, u+1 -> column u/2.
 #pragma unroll
-            for (int pp = 0; pp < RO_NP; ++pp)
+            for (int pp = 0; pp < RO_NP; ++pp) {
+              uint32_t hw[8];
 #pragma unroll
               for (int sub = 0; sub < 2; ++sub) {
                 const int u = pp * RO_UN + hsel * 16 + sub * 8;
-                *reinterpret_cast<uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
-                    make_uint4(hreg[pp][sub * 4], hreg[pp][sub * 4 + 1], hreg[pp][sub * 4 + 2], hreg[pp][sub * 4 + 3]);
+                const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
+                                                                 ((((u & 63) >> 3) ^ (r & 7)) << 4));
+                hw[sub * 4] = t4.x; hw[sub * 4 + 1] = t4.y; hw[sub * 4 + 2] = t4.z; hw[sub * 4 + 3] = t4.w;
               }
+              tmem_st8(t_row + RT_A_H + pp * 16 + hsel * 8, hw);
+            }
+            tmem_wait_st();
           }
           tc_fence_before();
           mbar_arrive(ACC_EMPTY + 8 * b);
@@ -489,8 +565,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
 #pragma unroll
               for (int z = 0; z < 5; ++z) po[z] = o[z];
             }
-            const float2 cp = s_cur[r];
-            s_next[r] = make_float2(cp.x + o[0], cp.y + o[1]);
+            s_next[r] = make_float2(cur.x + o[0], cur.y + o[1]);
           }
           worker_sync();
         }

@@ -58,6 +58,36 @@ __global__ void __launch_bounds__(320, 1) k(int passes, int hammer, long long* o
       }
       done = 1;
     }
+  } else if (warp < 8 && hammer >= 3) {
+    // 3: tcgen05.ld loop; 4: MUFU.TANH loop; 5: FFMA2 loop; 6: ld + tanh + ffma2 mix (like the gate epilogue)
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384;
+    float acc[8] = {0.1f, 0.2f, 0.3f, 0.4f, 0.5f, 0.6f, 0.7f, 0.8f};
+    while (!done) {
+      if (hammer == 3 || hammer == 6) {
+        float v[8];
+        tmem_ld8(t_row + (warp >> 2) * 64, v);
+        tmem_ld8(t_row + (warp >> 2) * 64 + 8, acc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+      if (hammer == 4 || hammer == 6) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = tanh_fast(acc[i]);
+      }
+      if (hammer == 5 || hammer == 6) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float2 t = ffma2(make_float2(acc[i], acc[i + 1]), make_float2(0.99f, 0.98f), make_float2(0.01f, 0.02f));
+            acc[i] = t.x; acc[i + 1] = t.y;
+          }
+      }
+    }
+    if (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7] == 0.12345f) out[101] = 1;
   } else if (warp < 8 && hammer) {
     uint4 acc = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(smem + 144 * 1024);
@@ -82,7 +112,7 @@ template <int N, int MODE, int COMMIT> void run(long long* d) {
   auto kern = k<N, MODE, COMMIT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 162 * 1024);
   const int passes = 20;
-  for (int hammer : {0, 1, 2}) {
+  for (int hammer : {0, 2, 3, 4, 5, 6}) {
     kern<<<148, 320, 162 * 1024>>>(passes, hammer, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
@@ -93,9 +123,6 @@ template <int N, int MODE, int COMMIT> void run(long long* d) {
 }
 int main() {
   long long* d; cudaMalloc(&d, 1024);
-  run<32, 0, 0>(d); run<64, 0, 0>(d); run<96, 0, 0>(d); run<128, 0, 0>(d); run<192, 0, 0>(d); run<256, 0, 0>(d);
-  run<96, 0, 1>(d); run<192, 0, 1>(d);
-  run<32, 1, 0>(d); run<96, 1, 0>(d); run<128, 1, 0>(d); run<192, 1, 0>(d); run<256, 1, 0>(d);
-  run<96, 1, 1>(d);
+  run<96, 0, 1>(d); run<96, 1, 1>(d); run<128, 1, 1>(d); run<192, 1, 1>(d);
   return 0;
 }

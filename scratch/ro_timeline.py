@@ -25,7 +25,7 @@ for s in range(24):
     if r[0] == 0: break
     m = r[16:]
     order = [0, 1, 2, 3, 12, 4, 5, 6, 7, 8, 9, 10]
-    print(f'{s:4d} ' + ' '.join(f'{m[k] - r[0]:7d}' for k in order) + f' |   worker: att_arr {r[1]-r[0]} mh_arr {r[4]-r[0]} acc0 {r[5]-r[0]} acc1 {r[7]-r[0]} acc2 {r[9]-r[0]} acc3 {r[11]-r[0]} end {r[14]-r[0]}')
+    print(f'{s:4d} ' + ' '.join(f'{m[k] - r[0]:7d}' for k in order) + f' | Wwait {m[13]:5d} {m[14]:5d} |   worker: att_arr {r[1]-r[0]} mh_arr {r[4]-r[0]} acc0 {r[5]-r[0]} acc1 {r[7]-r[0]} acc2 {r[9]-r[0]} acc3 {r[11]-r[0]} end {r[14]-r[0]}')
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(3): ops.rollout_bf16(pos, vis, valid, p, out=out)
 torch.cuda.synchronize()
