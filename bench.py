@@ -135,7 +135,7 @@ def config(args, scenes_per_rank):
                         f"obs {T_OBS} / pred {P_PRED}, K={K_SAMPLES}, g2k_lstm_{args.variant} batched inference",
             "variant": f"g2k_lstm_{args.variant}", "precision_mode": args.prec, "scenes_per_gpu": scenes_per_rank,
             "agents_per_scene": args.agents, "noise": "in-kernel Philox4x32-10",
-            "l2": "per-step working set (~1 GB of state/workspace) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "inputs larger than L2: 4 device copies of the batch (59 MB each) are cycled and every step writes ~150 MB of outputs/workspace; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,13 +151,18 @@ def run_ours(args, rank, world, local_rank):
     from multimodaltraj_2_b200 import _lib, ops, synth
 
     S, N = args.scenes, args.agents
-    prec = ops.PREC_BF16 if args.prec == "bf16" else ops.PREC_F32
+    prec = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}[args.prec]
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
     fc = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(args.variant == "mcr"),
                         prec=prec, seed=0xB200, agent_offset=rank * S * N, device=dev, use_graph=not args.no_graph)
     pos_p, vis_p, valid_p = (torch.from_numpy(a).pin_memory() for a in (pos_h, vis_h, valid_h))
     pos, vis, valid = pos_p.to(dev), vis_p.to(dev), valid_p.to(dev)
+    # NSETS device copies of the inputs are cycled so that a step never finds its inputs in the 126 MB L2
+    # (one set = pos 42 MB + vis 17 MB; outputs and workspace add ~150 MB per step)
+    NSETS = 4
+    sets = [(pos, vis, valid)] + [(pos.clone(), vis.clone(), valid.clone()) for _ in range(NSETS - 1)]
+    step_no = [0]
 
     def barrier():
         if world > 1:
@@ -165,8 +170,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step():
-        return fc(pos, vis, valid)
+        p_, v_, m_ = sets[step_no[0] % NSETS]
+        step_no[0] += 1
+        return fc(p_, v_, m_)
 
+    for st in sets:                      # first call per input set: eager validation + CUDA-graph capture (untimed)
+        fc(*st)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -192,60 +201,125 @@ def run_ours(args, rank, world, local_rank):
     units = n_valid * world          # every rank holds the same number of valid agents (all valid)
     value = units / (ms_step * 1e-3)
 
-    # ---- e2e: host buffers in, scores out, copies inside the timed region
-    res_h = torch.empty((2,), dtype=torch.float32).pin_memory()
-    pos_d, vis_d, valid_d = torch.empty_like(pos), torch.empty_like(vis), torch.empty_like(valid)
+    # ---- e2e: host buffers in, scores out, copies inside the timed region.  A two-deep pipeline as a serving loop
+    # would run it: the H2D copy of step i+1 (copy stream, pinned host memory) overlaps the kernels of step i; every
+    # step still uploads its own inputs and reads back its own result.
+    res_h = [torch.empty((2,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    bufs = [(torch.empty_like(pos), torch.empty_like(vis), torch.empty_like(valid)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        pos_d.copy_(pos_p, non_blocking=True)
-        vis_d.copy_(vis_p, non_blocking=True)
-        valid_d.copy_(valid_p, non_blocking=True)
-        o = fc(pos_d, vis_d, valid_d)
-        res = torch.stack([o["best_ade"].sum(), o["best_fde"].sum()]) / n_valid
-        res_h.copy_(res, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return res_h
+    def e2e_run(n):
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(ev_free[b])          # the kernels of step i-2 have consumed this buffer
+                bufs[b][0].copy_(pos_p, non_blocking=True)
+                bufs[b][1].copy_(vis_p, non_blocking=True)
+                bufs[b][2].copy_(valid_p, non_blocking=True)
+                ev_copied[b].record(copy_stream)
+            main_stream.wait_event(ev_copied[b])
+            o = fc(*bufs[b])
+            ev_free[b].record(main_stream)
+            res = torch.stack([o["best_ade"].sum(), o["best_fde"].sum()]) / n_valid
+            res_h[b].copy_(res, non_blocking=True)
+            ev_done[b].record(main_stream)
+            if i >= 1:
+                ev_done[(i - 1) & 1].synchronize()              # the host consumes the previous step's result
+        ev_done[(n - 1) & 1].synchronize()
+        return res_h[(n - 1) & 1]
 
-    for _ in range(2):
-        e2e_step()
+    e2e_run(3)
     barrier()
-    n_e2e = max(3, min(args.steps, 10))
+    n_e2e = max(4, min(args.steps, 10))
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
+    last = e2e_run(n_e2e)
     barrier()
     te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = units / float(te.item())
     h2d = pos_p.numel() * 4 + vis_p.numel() * 4 + valid_p.numel()
-    ade, fde = float(res_h[0]), float(res_h[1])
+    ade, fde = float(last[0]), float(last[1])
 
-    # ---- roofline of the dominant kernel (gate update): same shapes, timed alone with CUDA events
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream
     R = S * N
-    x = torch.randn((R, 4), device=dev) * 0.3
-    h, c, mh, mc = (torch.randn((R, HIDDEN), device=dev) * 0.5 for _ in range(4))
-    vflat = valid.reshape(-1).contiguous()
-    cur = torch.randn((R, 2), device=dev)
-    for _ in range(3):
-        ops.gsk_cell(x, h, c, mh, mc, vflat, params, prec, cur_pos=cur, want_head=True)
-    torch.cuda.synchronize()
+    pk = peaks()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
+    nsteps = T_OBS + P_PRED - 1
+    fused = prec == ops.PREC_BF16 and args.variant == "mc" and 128 % N == 0 and N >= 8
+    prof = {}
+    pf = ROOT / "profiles" / "r01_traffic.json"
+    if pf.exists():
+        prof = json.loads(pf.read_text())
+    if fused:
+        # rollout_tc_kernel: the whole T+P-1 step recurrence (pairwise + softmax -> aggregation MMA -> gate MMA ->
+        # gate update -> head) in one launch.  Algorithmic FLOPs per agent-step: gate GEMM 2*320*384 + aggregation
+        # of h and c over the scene 2*N*2U.
+        par_out = torch.empty((S, N, P_PRED, 5), device=dev)
+        for _ in range(3):
+            ops.rollout_bf16(pos, vis, valid, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out)
+        torch.cuda.synchronize()
+        k0.record()
+        for i in range(reps):
+            p_, v_, m_ = sets[i % NSETS]
+            ops.rollout_bf16(p_, v_, m_, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out)
+        k1.record()
+        torch.cuda.synchronize()
+        ro_ms = k0.elapsed_time(k1) / reps
+        flops = float(R) * nsteps * (2.0 * (EMBED + 2 * HIDDEN) * 3 * HIDDEN + 2.0 * N * 2 * HIDDEN)
+        achieved = flops / (ro_ms * 1e-3) / 1e12
+        peak = pk["bf16"]
+        roof = {"kernel": "rollout_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": prof.get("rollout_tc_kernel_dram_bytes_per_launch"),
+                "peak_source": f"{pk['src']} (burst bf16 cuBLAS: kernel timed alone); sustained peak {pk['bf16_sustained']}",
+                "frac_of_sustained": achieved / pk["bf16_sustained"], "ms_per_launch": ro_ms,
+                "algorithmic_flops_per_launch": flops, "launches_per_step": 1,
+                "algorithmic_hbm_bytes_per_launch": float(R) * (T_OBS * 16 + P_PRED * 20 + 1)}
+    else:
+        x = torch.randn((R, 4), device=dev) * 0.3
+        h, c, mh, mc = (torch.randn((R, HIDDEN), device=dev) * 0.5 for _ in range(4))
+        vflat = valid.reshape(-1).contiguous()
+        cur = torch.randn((R, 2), device=dev)
+        cprec = ops.PREC_F32 if prec == ops.PREC_F32 else ops.PREC_BF16
+        for _ in range(3):
+            ops.gsk_cell(x, h, c, mh, mc, vflat, params, cprec, cur_pos=cur, want_head=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(reps):
+            ops.gsk_cell(x, h, c, mh, mc, vflat, params, cprec, cur_pos=cur, want_head=True)
+        k1.record()
+        torch.cuda.synchronize()
+        cell_ms = k0.elapsed_time(k1) / reps
+        flops = 2.0 * R * (EMBED + 2 * HIDDEN) * 3 * HIDDEN
+        achieved = flops / (cell_ms * 1e-3) / 1e12
+        peak = pk["bf16_sustained"]
+        roof = {"kernel": "gsk_cell_tc_kernel" if prec != ops.PREC_F32 else "gsk_cell_f32_kernel", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{pk['src']} (sustained bf16 cuBLAS)", "ms_per_launch": cell_ms,
+                "algorithmic_flops_per_launch": flops, "launches_per_step": nsteps}
+    # decode + ADE/FDE epilogue kernel alone (Philox mode): 500 algorithmic bytes per agent
+    o_dec = fc.out
+    lo = pos[:, :, T_OBS - 1].contiguous()
+    gt = pos[:, :, T_OBS:].contiguous()
+    for _ in range(2):
+        ops.decode_score(o_dec["params"], lo, gt, valid, K_SAMPLES, seed=1, want_all=False)
+    torch.cuda.synchronize()
     k0.record()
     for _ in range(reps):
-        ops.gsk_cell(x, h, c, mh, mc, vflat, params, prec, cur_pos=cur, want_head=True)
+        ops.decode_score(o_dec["params"], lo, gt, valid, K_SAMPLES, seed=1, want_all=False)
     k1.record()
     torch.cuda.synchronize()
-    cell_ms = k0.elapsed_time(k1) / reps
-    pk = peaks()
-    flops = 2.0 * R * (EMBED + 2 * HIDDEN) * 3 * HIDDEN
-    achieved = flops / (cell_ms * 1e-3) / 1e12
-    peak = pk["bf16_sustained"]
-    roof = {"kernel": "gsk_cell_tc_kernel" if prec == ops.PREC_BF16 else "gsk_cell_f32_kernel", "bound": "tensor",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": f"{pk['src']} (sustained bf16 cuBLAS)", "ms_per_launch": cell_ms,
-            "algorithmic_flops_per_launch": flops, "launches_per_step": T_OBS + P_PRED - 1}
+    dec_ms = k0.elapsed_time(k1) / reps
+    roof_dec = {"kernel": "decode_score_kernel", "bound": "hbm", "achieved": R * 500.0 / (dec_ms * 1e-3) / 1e9,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": R * 500.0 / (dec_ms * 1e-3) / 1e9 / pk["hbm"],
+                "traffic": prof.get("decode_score_kernel_dram_bytes_per_launch"), "ms_per_launch": dec_ms,
+                "note": "Philox + Box-Muller in-kernel: ALU-bound in practice (K*P = 240 normal pairs per agent)"}
     # pairwise kernel: HBM roofline (5N^2 + 9N bytes per scene-frame)
     # all T observed frames of the batch in one launch: S*T scene-frames (output 5 N^2 S T bytes >> L2)
     fc_pos = pos[:, :, :T_OBS].permute(0, 2, 1, 3).reshape(S * T_OBS, N, 2).contiguous()
@@ -281,11 +355,11 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": value, "unit": "agent-trajectories/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if prec == ops.PREC_BF16 else "f32", "data": "synthetic", "config": config(args, S),
+                "dtype": "f32" if prec == ops.PREC_F32 else "bf16", "data": "synthetic", "config": config(args, S),
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 8},
-                "gpu_launches": int(launches), "roofline": roof, "roofline_pairwise": roof_pw,
+                "gpu_launches": int(launches), "roofline": roof, "roofline_pairwise": roof_pw, "roofline_decode": roof_dec,
                 "cpu_baseline": {"value": n_cpu * N / t_cpu, "unit": "agent-trajectories/s", "cores": 1, "kind": "port",
                                  "sample": f"{n_cpu} scenes x {N} agents, numpy fp32 oracle of the whole path "
                                            f"(host has {cores} cores; TF 1.14 reference not installable offline)"},
@@ -302,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32", "bf16-stepwise"])
     ap.add_argument("--variant", default="mc", choices=["mc", "mcr"])
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)

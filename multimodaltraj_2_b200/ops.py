@@ -279,7 +279,7 @@ class Forecaster:
                  prec=PREC_F32, seed=0, agent_offset=0, device="cuda", want_all=False, use_graph=False):
         self.lib = _lib.load()
         self.use_graph = use_graph
-        self._graph = self._graph_key = None
+        self._graphs = {}      # input-pointer tuple -> (CUDAGraph, launches per replay); at most 8 entries
         self._graph_n = 0
         self.p = params
         if prec != PREC_F32 and params.W_packed is None:
@@ -305,17 +305,19 @@ class Forecaster:
             return self._launch(pos, vis, valid, eps)
         global _graph_launches
         key = (pos.data_ptr(), vis.data_ptr(), valid.data_ptr(), None if eps is None else eps.data_ptr())
-        if self._graph_key != key:
+        if key not in self._graphs:
             self._launch(pos, vis, valid, eps)          # eager warm-up: sets kernel attributes, validates arguments
             torch.cuda.synchronize()
             n0 = int(self.lib.mmt_launch_count())
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._launch(pos, vis, valid, eps)
-            self._graph_n = int(self.lib.mmt_launch_count()) - n0
-            self._graph, self._graph_key = g, key
-        self._graph.replay()
-        _graph_launches += self._graph_n
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = (g, int(self.lib.mmt_launch_count()) - n0)
+        g, n = self._graphs[key]
+        g.replay()
+        _graph_launches += n
         return self.out
 
     def _launch(self, pos, vis, valid, eps=None):
