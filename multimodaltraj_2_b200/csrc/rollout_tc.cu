@@ -11,12 +11,15 @@
 //                         the aggregation GEMMs  mh = att x h,  mc = att x c
 //                  ATT    block-diagonal un-normalised attention, K-major A operand of the aggregation
 //                  W ring gate weights streamed from L2 by cp.async.bulk, 8 stages of 12 KB (one k-chunk)
-//   registers      fp32 cell state c: 64 values per worker thread (row x 16 units x 4 passes)
+//                  CF     fp32 cell state c, [unit/4][row][4]: conflict-free 128-bit access by (row, unit quad);
+//                         keeping it out of the register file is what lets 16 worker warps fit (4 per scheduler:
+//                         with 8 the workers issued one instruction per ~7 clk, latency-bound: profiles/)
 // Only positions / vislets are read from HBM and only the 5 head parameters per predicted step are
 // written: ~0.5 KB per agent-trajectory instead of ~30 KB per agent for the per-step kernels.
 //
-// Warp roles: warps 0-7 workers (attention build, e / mh operand build, gate epilogue, head);
-// warps 8-9 stream weight stages; warps 10-11 issue the tcgen05.mma (gate passes alternate between them).
+// Warp roles: warps 0-15 workers (attention build, e / mh operand build, gate epilogue, head): warp w owns TMEM
+// lane quarter w % 4 (rows) and column slice w / 4 (8 of the 32 units of a pass); warps 16-17 stream weight
+// stages; warps 18-19 issue the tcgen05.mma (gate passes alternate between them).
 // Measured design inputs (scratch/mma_bench.cu, bulk_bench2.cu, mufu_bench2.cu on B200): an SS-form
 // M128 x N96 MMA re-reads 4 KB of A from shared memory per 48-clk MMA and, together with the workers'
 // own shared-memory traffic, ran at 83-90 clk in situ; one thread managing a bulk-copy ring sustains one
@@ -38,8 +41,9 @@ constexpr int RO_NCH = RO_NP * RO_NKC;          // 20 weight chunks per step
 constexpr int RO_BLK = 128 * 128;               // one [128 rows x 128 B] block
 constexpr int RO_CHUNK_BYTES = RO_N * 64 * 2;   // 12288: one (pass, k-chunk) of the packed weights
 constexpr int RO_STAGE_BYTES = RO_CHUNK_BYTES;
-constexpr int RO_NSTAGE = 8;
-constexpr int RO_WORKERS = 256;
+constexpr int RO_NSTAGE = 4;
+constexpr int RO_WORKERS = 512;
+constexpr int RO_WWARPS = RO_WORKERS / 32;      // 16: first helper warp
 constexpr int RO_NPROD = 2;                     // weight-stage producer warps (one issuing thread each)
 constexpr int RO_NISSUE = 2;                    // MMA-issuing warps: passes p % 2 == j (one thread tops out at ~68 clk/MMA)
 constexpr int RO_THREADS = RO_WORKERS + 32 * (RO_NPROD + RO_NISSUE);
@@ -47,18 +51,19 @@ constexpr int RO_THREADS = RO_WORKERS + 32 * (RO_NPROD + RO_NISSUE);
 constexpr int RS_H = 0;                         // 2 blocks (units 0-63 | 64-127)
 constexpr int RS_C = RS_H + 2 * RO_BLK;         // 2 blocks
 constexpr int RS_ATT = RS_C + 2 * RO_BLK;       // 2 blocks (agents 0-63 | 64-127 along K)
-constexpr int RS_W = RS_ATT + 2 * RO_BLK;
+constexpr int RS_CF = RS_ATT + 2 * RO_BLK;      // fp32 c: 64 KB
+constexpr int RS_W = RS_CF + 128 * 128 * 4;
 constexpr int RS_BAR = RS_W + RO_NSTAGE * RO_STAGE_BYTES;
 constexpr int RS_TMEM = RS_BAR + 256;
 constexpr int RS_BIAS = RS_TMEM + 16;                  // b[384], w_If, w_It, w_Of, w_Ot [4][128]
 constexpr int RS_WE = RS_BIAS + (384 + 512) * 4;       // W_e[4][64], b_e[64]
-constexpr int RS_WH = RS_WE + (256 + 64) * 4;          // W_h[256][5], b_h[5] (+3 pad)
-constexpr int RS_HEAD = RS_WH + (256 * 5 + 8) * 4;     // head partials [128][5]
-constexpr int RS_PX = RS_HEAD + 128 * 5 * 4;           // float[128] current x (invalid agents: far away)
+constexpr int RS_WHT = RS_WE + (256 + 64) * 4;         // head weights transposed: W_hT[5][2U] (unit pairs feed FFMA2)
+constexpr int RS_PX = RS_WHT + 5 * 256 * 4;            // float[128] current x (invalid agents: far away)
 constexpr int RS_PY = RS_PX + 512;                     // float[128] current y
 constexpr int RS_NEXT = RS_PY + 512;                   // float2[128] predicted next positions
-constexpr int RS_SUM = RS_NEXT + 1024;                 // float[2][128] attention row sums
-constexpr int RS_TOTAL = RS_SUM + 1024;
+constexpr int RS_SUM = RS_NEXT + 1024;                 // float[4][128] attention row sums
+constexpr int RS_OBS = RS_SUM + 2048;                  // float4[128]: next observed frame (pos.xy, vislet.xy), cp.async
+constexpr int RS_TOTAL = RS_OBS + 2048;
 static_assert(RS_TOTAL + 1024 <= 227 * 1024, "shared memory budget");
 
 // tensor-memory columns
@@ -67,6 +72,8 @@ constexpr uint32_t RT_A_H = 32, RT_A_MH = 96;
 constexpr uint32_t RT_ACC0 = 160, RT_ACC1 = 256;
 constexpr uint32_t RT_MH = 256;       // mh accumulator (fp32, 128 columns): aliases accumulator 1 + 32 spare columns
 constexpr uint32_t RT_MC = 384;       // mc accumulator (fp32, 128 columns)
+constexpr uint32_t RT_HEAD = 352;     // 4 column slices x 8: head partial sums of a row, exchanged through TMEM
+                                      // (the 32 columns of the mh accumulator beyond accumulator 1: free after the conversion)
 constexpr uint32_t kIdescGate = make_idesc_bf16(128, RO_N);
 constexpr uint32_t kIdescAggMN = make_idesc_bf16(128, 128) | (1u << 16);   // B operand MN-major
 
@@ -79,7 +86,7 @@ struct RoArgs {
   float* params;         // [R, P, 5]
   int R, N, T, P, F, num_tiles;
   float r2, neg_inv_log2e;
-  int flags;  // TEMP diagnostics: 1 no weight streaming; 2 no gate math; 4 no epilogue TMEM loads; 8 no c'/h' smem stores
+  int flags;  // diagnostics: 1 = no weight streaming (timing experiments only), 16 = time the W_FULL waits
   long long* dbg;        // optional [64 steps][32] clock64 stamps of CTA 0: [0,16) worker thread 0, [16,32) MMA thread
 };
 
@@ -102,7 +109,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   __syncwarp();
 }
 
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
@@ -115,12 +122,12 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                  MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8;
   float* s_bias = reinterpret_cast<float*>(smem + RS_BIAS);
   float* s_we = reinterpret_cast<float*>(smem + RS_WE);
-  float* s_wh = reinterpret_cast<float*>(smem + RS_WH);
-  float* s_head = reinterpret_cast<float*>(smem + RS_HEAD);
+  float* s_wht = reinterpret_cast<float*>(smem + RS_WHT);
   float* s_px = reinterpret_cast<float*>(smem + RS_PX);
   float* s_py = reinterpret_cast<float*>(smem + RS_PY);
   float2* s_next = reinterpret_cast<float2*>(smem + RS_NEXT);
   float* s_sum = reinterpret_cast<float*>(smem + RS_SUM);
+  float4* s_obs = reinterpret_cast<float4*>(smem + RS_OBS);
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + RS_TMEM);
   const int nsteps = a.T + a.P - 1;
 
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     mbar_init(AGG_FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(sbase + RS_TMEM, 512);
+  if (warp == RO_WWARPS) tmem_alloc(sbase + RS_TMEM, 512);
   // sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 is folded into the packed i/o weight columns, biases and peepholes
   for (int i = tid; i < 384; i += RO_THREADS) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
   for (int i = tid; i < 128; i += RO_THREADS) {
@@ -150,8 +157,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   }
   for (int i = tid; i < 256; i += RO_THREADS) s_we[i] = a.W_e[i];
   for (int i = tid; i < 64; i += RO_THREADS) s_we[256 + i] = a.b_e[i];
-  for (int i = tid; i < 256 * 5; i += RO_THREADS) s_wh[i] = a.W_h[i];
-  if (tid < 5) s_wh[256 * 5 + tid] = a.b_h[tid];
+  for (int i = tid; i < 256 * 5; i += RO_THREADS) s_wht[(i % 5) * 256 + i / 5] = a.W_h[i];
   // attention operand: entries outside a row's own scene stay zero for the whole kernel
   for (int i = tid; i < 2 * RO_BLK / 16; i += RO_THREADS)
     reinterpret_cast<uint4*>(smem + RS_ATT)[i] = make_uint4(0, 0, 0, 0);
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp >= 8 && warp < 8 + RO_NPROD) {
+  if (warp >= RO_WWARPS && warp < RO_WWARPS + RO_NPROD) {
     // =============================== weight-stage producers ===============================
     // One thread managing a whole ring sustains only one cp.async.bulk per ~360 clk (issue + mbarrier round
     // trip serialise in that thread: scratch/bulk_bench2.cu); RO_NPROD threads in different warps take the
@@ -169,20 +175,20 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       int my_tiles = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) ++my_tiles;
       const uint32_t total = (a.flags & 1) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
-      for (uint32_t it = warp - 8; it < total; it += RO_NPROD) {
+      for (uint32_t it = warp - RO_WWARPS; it < total; it += RO_NPROD) {
         const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, pk = it % RO_NCH;
         mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(W_FULL + 8 * s, RO_STAGE_BYTES);
         bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)pk * RO_STAGE_BYTES, RO_STAGE_BYTES, W_FULL + 8 * s);
       }
     }
-  } else if (warp >= 8 + RO_NPROD) {
+  } else if (warp >= RO_WWARPS + RO_NPROD) {
     // =============================== MMA issuers ===============================
     // Issuer 0: aggregation + gate passes 0, 2; issuer 1: gate passes 1, 3.  Two issuing threads reach the
     // nominal 48 clk per M128 x N96 MMA where one tops out at ~68 (scratch/mma_bench3.cu); passes use different
     // accumulators, so their MMAs may interleave freely in the tensor pipe.
     {   // the whole warp runs this code convergently; one elected lane issues each tcgen05 instruction
-      const int me = warp - (8 + RO_NPROD);
+      const int me = warp - (RO_WWARPS + RO_NPROD);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t sc = 0;
       const uint64_t d_att0 = make_desc_sw128(sbase + RS_ATT), d_att1 = make_desc_sw128(sbase + RS_ATT + RO_BLK);
@@ -254,50 +260,47 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     }
   } else {
     // =============================== workers ===============================
-    const int q = warp & 3, hsel = warp >> 2;
-    const int r = q * 32 + lane;           // this thread's row: TMEM lane, attention row, epilogue row (== tid & 127)
+    const int q = warp & 3, cs = warp >> 2;
+    const int r = q * 32 + lane;           // this thread's row: TMEM lane, attention row, epilogue row
     const int N = a.N;
     const int sb = (r / N) * N;            // first row of this row's scene inside the tile
-    const int jn = N >= 16 ? (N >> 1) : (hsel == 0 ? N : 0);
-    const int jbeg = N >= 16 ? hsel * jn : 0;
+    const int nch = N >> 3;                // 8-column attention chunks per row; this thread takes chunks cs, cs + 4, ...
     // the diagonal entry (j == r) of the attention row is masked out of the packed bf16 words of its 8-column chunk
     const int jdiag8 = (r - sb) & ~7;
-    uint32_t dmask[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-      dmask[w] = (((r - sb) & 7) >> 1) == w ? (((r - sb) & 1) ? 0x0000FFFFu : 0xFFFF0000u) : 0xFFFFFFFFu;
     const float LOG2E = 1.4426950408889634f;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t pc = 0, sc = 0;
+    uint8_t* const cf_row = smem + RS_CF + r * 16;     // + (u >> 2) * 2048: 4 fp32 c of units u .. u+3
+    uint32_t sc = 0;
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int row0 = tile * 128;
       const int gr = row0 + r;
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
-      worker_sync();   // every worker has stored the previous tile's last h' before the reset
-      // zero the recurrent state: h, c images in shared memory and the h columns of the TMEM A operand
+      worker_sync();   // every worker has finished the previous tile before the reset
+      // zero the recurrent state: h, c (bf16 images + fp32 c) in shared memory and the h columns of the TMEM A operand
       {
-        uint4* hz = reinterpret_cast<uint4*>(smem + RS_H);
-        uint4* cz = reinterpret_cast<uint4*>(smem + RS_C);
+        uint4* hz = reinterpret_cast<uint4*>(smem + RS_H);   // H | C contiguous: 64 KB
+        uint4* cz = reinterpret_cast<uint4*>(smem + RS_CF);  // 64 KB
 #pragma unroll
-        for (int k = 0; k < 2 * RO_BLK / 16 / RO_WORKERS; ++k) {
+        for (int k = 0; k < 4 * RO_BLK / 16 / RO_WORKERS; ++k) {
           hz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
           cz[tid + RO_WORKERS * k] = make_uint4(0, 0, 0, 0);
         }
         const uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tmem_st8(t_row + RT_A_H + hsel * 32 + k * 8, z8);
+        tmem_st8(t_row + RT_A_H + cs * 16, z8);
+        tmem_st8(t_row + RT_A_H + cs * 16 + 8, z8);
       }
-      float c[64];
-#pragma unroll
-      for (int i = 0; i < 64; ++i) c[i] = 0.f;
-      float2 pn = make_float2(0.f, 0.f), vn = make_float2(0.f, 0.f), prevp = make_float2(0.f, 0.f);
-      if (rok) {
-        pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)gr * a.F);
-        vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)gr * a.T);
+      // observed frames arrive through shared memory: (pos, vislet) of frame t+1 is fetched with cp.async during
+      // step t by the slice-0 / slice-1 thread of each row (no registers held across the step)
+      float2 prevp = make_float2(0.f, 0.f), visv = make_float2(0.f, 0.f);
+      if (cs < 2) {
+        float2 f0 = make_float2(0.f, 0.f);
+        if (rok) f0 = cs == 0 ? __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)gr * a.F)
+                              : __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)gr * a.T);
+        reinterpret_cast<float2*>(s_obs + r)[cs] = f0;
       }
-      float2 visv = vn;
+      worker_sync();
 
       for (int t = 0; t < nsteps; ++t, ++sc) {
         const uint32_t par = sc & 1u;
@@ -307,8 +310,9 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         // ---- (a) current position and the cell input x = [cur - prev | vislet] of row r
         float2 cur;
         if (t < a.T) {
-          cur = pn;
-          visv = vn;
+          const float4 ob = s_obs[r];
+          cur = make_float2(ob.x, ob.y);
+          visv = make_float2(ob.z, ob.w);
         } else {
           cur = s_next[r];
         }
@@ -318,21 +322,24 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           xv.y = __fsub_rn(cur.y, prevp.y);
         }
         prevp = cur;
-        if (hsel == 0) {   // invalid agents sit far away: d2 = inf fails d2 < r2 for every partner
+        if (cs == 0) {   // invalid agents sit far away: d2 = inf fails d2 < r2 for every partner
           s_px[r] = v ? cur.x : 3.0e18f;
           s_py[r] = v ? cur.y : 3.0e18f;
         }
-        if (t + 1 < a.T && rok) {   // prefetch the next observed frame
-          pn = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)gr * a.F + (t + 1));
-          vn = __ldg(reinterpret_cast<const float2*>(a.vis) + (size_t)gr * a.T + (t + 1));
+        worker_sync();   // positions (and, on a tile's first step, the zeroed state) visible; s_obs consumed
+        if (t + 1 < a.T && rok && cs < 2) {   // prefetch the next observed frame
+          const float* src = cs == 0 ? a.pos + ((size_t)gr * a.F + (t + 1)) * 2 : a.vis + ((size_t)gr * a.T + (t + 1)) * 2;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(reinterpret_cast<float2*>(s_obs + r) + cs)),
+                       "l"(src)
+                       : "memory");
         }
-        worker_sync();   // positions (and, on a tile's first step, the zeroed state) visible
-        // ---- (b) attention row r against columns [jbeg, jbeg + jn) of its scene (un-normalised), packed fp32x2 math
+        // ---- (b) attention row r against 8-column chunks cs, cs+4, .. of its scene (un-normalised), packed fp32x2 math
         {
           const float2 nx = make_float2(-cur.x, -cur.x), ny = make_float2(-cur.y, -cur.y);
           const float2 cexp = make_float2(a.neg_inv_log2e, a.neg_inv_log2e), l2e = make_float2(LOG2E, LOG2E);
           float sum = 0.f;
-          for (int j8 = jbeg; j8 < jbeg + jn; j8 += 8) {
+          for (int ch = cs; ch < nch; ch += 4) {
+            const int j8 = ch << 3;
             uint32_t pk[4];
 #pragma unroll
             for (int hq = 0; hq < 2; ++hq) {
@@ -352,8 +359,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               }
             }
             if (j8 == jdiag8) {
+              const int dw = ((r - sb) & 7) >> 1;
+              const uint32_t dm = ((r - sb) & 1) ? 0x0000FFFFu : 0xFFFF0000u;
 #pragma unroll
-              for (int w = 0; w < 4; ++w) pk[w] &= dmask[w];
+              for (int w = 0; w < 4; ++w) pk[w] &= (w == dw) ? dm : 0xFFFFFFFFu;
             }
 #pragma unroll
             for (int w = 0; w < 4; ++w) sum += bf16_lo(pk[w]) + bf16_hi(pk[w]);   // normalise by what the MMA really sums
@@ -361,56 +370,54 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             *reinterpret_cast<uint4*>(smem + RS_ATT + (jt >> 6) * RO_BLK + sw128_off(r, jt & 63)) =
                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          s_sum[hsel * 128 + r] = sum;
+          s_sum[cs * 128 + r] = sum;
         }
         fence_proxy_async();   // generic-proxy smem writes (att; h', c' of the previous step) -> async proxy
         tc_fence_before();     // (and the h' tcgen05.st of the previous step, already waited for)
         mbar_arrive(ATT_READY);
         if (dbg) dbg[1] = clock64();
-        // ---- (c) e = relu(x W_e + b_e): row r, k in [32 hsel, 32 hsel + 32) -> A-operand columns 16 hsel .. +15
+        // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Runs while
+        //      the aggregation MMAs execute (placing it before the attention build delayed them: measured +900 clk)
         {
-          const int k0 = hsel * 32;
+          uint32_t pk[8];
 #pragma unroll
-          for (int kk = 0; kk < 32; kk += 16) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int hq = 0; hq < 4; ++hq) {
-              const int k = k0 + kk + hq * 4;
-              const float4 w0 = *reinterpret_cast<const float4*>(s_we + k);
-              const float4 w1 = *reinterpret_cast<const float4*>(s_we + 64 + k);
-              const float4 w2 = *reinterpret_cast<const float4*>(s_we + 128 + k);
-              const float4 w3 = *reinterpret_cast<const float4*>(s_we + 192 + k);
-              const float4 bb = *reinterpret_cast<const float4*>(s_we + 256 + k);
-              float e0 = fmaf(xv.w, w3.x, fmaf(xv.z, w2.x, fmaf(xv.y, w1.x, fmaf(xv.x, w0.x, bb.x))));
-              float e1 = fmaf(xv.w, w3.y, fmaf(xv.z, w2.y, fmaf(xv.y, w1.y, fmaf(xv.x, w0.y, bb.y))));
-              float e2 = fmaf(xv.w, w3.z, fmaf(xv.z, w2.z, fmaf(xv.y, w1.z, fmaf(xv.x, w0.z, bb.z))));
-              float e3 = fmaf(xv.w, w3.w, fmaf(xv.z, w2.w, fmaf(xv.y, w1.w, fmaf(xv.x, w0.w, bb.w))));
-              e0 = rok ? fmaxf(e0, 0.f) : 0.f;
-              e1 = rok ? fmaxf(e1, 0.f) : 0.f;
-              e2 = rok ? fmaxf(e2, 0.f) : 0.f;
-              e3 = rok ? fmaxf(e3, 0.f) : 0.f;
-              pk[hq * 2] = pack_bf16x2(e0, e1);
-              pk[hq * 2 + 1] = pack_bf16x2(e2, e3);
-            }
-            tmem_st8(t_row + RT_A + (k0 + kk) / 2, pk);
+          for (int hq = 0; hq < 4; ++hq) {
+            const int k = cs * 16 + hq * 4;
+            const float4 w0 = *reinterpret_cast<const float4*>(s_we + k);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_we + 64 + k);
+            const float4 w2 = *reinterpret_cast<const float4*>(s_we + 128 + k);
+            const float4 w3 = *reinterpret_cast<const float4*>(s_we + 192 + k);
+            const float4 bb = *reinterpret_cast<const float4*>(s_we + 256 + k);
+            float e0 = fmaf(xv.w, w3.x, fmaf(xv.z, w2.x, fmaf(xv.y, w1.x, fmaf(xv.x, w0.x, bb.x))));
+            float e1 = fmaf(xv.w, w3.y, fmaf(xv.z, w2.y, fmaf(xv.y, w1.y, fmaf(xv.x, w0.y, bb.y))));
+            float e2 = fmaf(xv.w, w3.z, fmaf(xv.z, w2.z, fmaf(xv.y, w1.z, fmaf(xv.x, w0.z, bb.z))));
+            float e3 = fmaf(xv.w, w3.w, fmaf(xv.z, w2.w, fmaf(xv.y, w1.w, fmaf(xv.x, w0.w, bb.w))));
+            e0 = rok ? fmaxf(e0, 0.f) : 0.f;
+            e1 = rok ? fmaxf(e1, 0.f) : 0.f;
+            e2 = rok ? fmaxf(e2, 0.f) : 0.f;
+            e3 = rok ? fmaxf(e3, 0.f) : 0.f;
+            pk[hq * 2] = pack_bf16x2(e0, e1);
+            pk[hq * 2 + 1] = pack_bf16x2(e2, e3);
           }
+          tmem_st8(t_row + RT_A + cs * 8, pk);
           tmem_wait_st();
         }
         tc_fence_before();
         mbar_arrive(E_READY);
-        worker_sync();   // both halves of every attention row sum are written
-        const float ssum = s_sum[r] + s_sum[128 + r];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
+        const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
         const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
         if (dbg) dbg[2] = clock64();
-        // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 64 hsel .. +63)
+        // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 32 cs .. +31)
         mbar_wait(AGG_FULL, par);
         tc_fence_after();
         if (dbg) dbg[3] = clock64();
 #pragma unroll
-        for (int ch = 0; ch < 8; ch += 2) {
+        for (int ch = 0; ch < 4; ch += 2) {
           float v0[8], v1[8];
-          tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8, v0);
-          tmem_ld8(t_row + RT_MH + hsel * 64 + ch * 8 + 8, v1);
+          tmem_ld8(t_row + RT_MH + cs * 32 + ch * 8, v0);
+          tmem_ld8(t_row + RT_MH + cs * 32 + ch * 8 + 8, v1);
           tmem_wait_ld();
           uint32_t pk[8];
 #pragma unroll
@@ -418,144 +425,147 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             pk[i] = pack_bf16x2(v0[2 * i] * inv, v0[2 * i + 1] * inv);
             pk[4 + i] = pack_bf16x2(v1[2 * i] * inv, v1[2 * i + 1] * inv);
           }
-          tmem_st8(t_row + RT_A_MH + hsel * 32 + ch * 4, pk);
+          tmem_st8(t_row + RT_A_MH + cs * 16 + ch * 4, pk);
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(MH_READY);
         if (dbg) dbg[4] = clock64();
 
-        // ---- (e) gate epilogue: 4 passes x 2 sub-chunks of 8 units
-        float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        // ---- (e) gate epilogue: 4 passes; this thread: row r, units 32 p + 8 cs .. +7, four at a time
+        float2 y2[5];
 #pragma unroll
+        for (int z = 0; z < 5; ++z) y2[z] = make_float2(0.f, 0.f);
+        const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
+        const float2 inv2 = make_float2(inv, inv);
+#pragma unroll 1
         for (int p = 0; p < RO_NP; ++p) {
-          const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+          const uint32_t pc = sc * RO_NP + p;
+          const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
           mbar_wait(ACC_FULL + 8 * b, bph);
           tc_fence_after();
           if (dbg) dbg[5 + 2 * p] = clock64();
-          const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0);
+          const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
+          const int u0 = p * RO_UN + cs * 8;        // first of this thread's 8 units
+          uint32_t hw[4], cw[4];                    // h', c' as bf16 pairs
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int ul = hsel * 16 + sub * 8;   // unit within pass
-            const int u = p * RO_UN + ul;         // global unit
-            float zi[8], zj[8], zo[8], zm[8];
-            if (!(a.flags & 4)) {
-              tmem_ld8(t_acc + ul, zi);
-              tmem_ld8(t_acc + RO_UN + ul, zj);
-              tmem_ld8(t_acc + 2 * RO_UN + ul, zo);
-              tmem_ld8(t_row + RT_MC + u, zm);
-              tmem_wait_ld();
-            } else {
+          for (int hq = 0; hq < 2; ++hq) {
+            const int u = u0 + hq * 4;
+            float zi[4], zj[4], zo[4], zm[4];
+            tmem_ld4(t_acc + hq * 4, zi);
+            tmem_ld4(t_acc + RO_UN + hq * 4, zj);
+            tmem_ld4(t_acc + 2 * RO_UN + hq * 4, zo);
+            tmem_ld4(t_row + RT_MC + u, zm);
+            float4 c4 = *reinterpret_cast<const float4*>(cf_row + (u >> 2) * 2048);
+            tmem_wait_ld();
+            float ho[4] = {0.f, 0.f, 0.f, 0.f}, fo[4] = {0.f, 0.f, 0.f, 0.f};
+            if (v) {
+              const float4 bI = *reinterpret_cast<const float4*>(s_bias + u);
+              const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + u);
+              const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + u);
+              const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + u);
+              const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + u);
+              const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + u);
+              const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + u);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) zi[i] = zj[i] = zo[i] = zm[i] = 0.01f * i;
-            }
-            float ho[8], fo[8];
-            float* cc = &c[p * 16 + sub * 8];
-            if (v && !(a.flags & 2)) {
-              const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
-              const float2 inv2 = make_float2(inv, inv);
-#pragma unroll
-              for (int hq = 0; hq < 2; ++hq) {
-                const int uu = u + hq * 4;
-                const float4 bI = *reinterpret_cast<const float4*>(s_bias + uu);
-                const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + uu);
-                const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + uu);
-                const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + uu);
-                const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + uu);
-                const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + uu);
-                const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + uu);
-#pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                  const int i0 = hq * 4 + pr * 2;
-                  auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
-                  // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes), arranged so that
-                  // only one packed FMA separates each MUFU result from its consumer:
-                  //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
-                  //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
-                  const float2 c2 = make_float2(cc[i0], cc[i0 + 1]);
-                  const float2 m2 = fmul2(make_float2(zm[i0], zm[i0 + 1]), inv2);
-                  const float2 t1 = ffma2(sel(pIf), m2, make_float2(zi[i0], zi[i0 + 1]));
-                  const float2 t2 = ffma2(sel(pIt), c2, sel(bI));
-                  const float2 th = tanh2(fadd2(t1, t2));
-                  const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
-                  const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
-                  const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
-                  const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
-                  const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO)));
-                  const float2 to = tanh2(ffma2(sel(pOt), ct, o1));
-                  const float2 ha = fmul2(tanh2(ct), kHalf);
-                  const float2 h2 = ffma2(to, ha, ha);
-                  ho[i0] = h2.x; ho[i0 + 1] = h2.y;
-                  cc[i0] = ct.x; cc[i0 + 1] = ct.y;
-                  if (emit) {
-                    const float2 fa = fmul2(tanh2(cf), kHalf);
-                    const float2 f2 = ffma2(to, fa, fa);
-                    fo[i0] = f2.x; fo[i0 + 1] = f2.y;
-                  }
+              for (int pr = 0; pr < 2; ++pr) {
+                const int i0 = pr * 2;
+                auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
+                // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes), arranged so that
+                // only one packed FMA separates each MUFU result from its consumer:
+                //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
+                //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
+                const float2 c2 = sel(c4);
+                const float2 m2 = fmul2(make_float2(zm[i0], zm[i0 + 1]), inv2);
+                const float2 t1 = ffma2(sel(pIf), m2, make_float2(zi[i0], zi[i0 + 1]));
+                const float2 t2 = ffma2(sel(pIt), c2, sel(bI));
+                const float2 th = tanh2(fadd2(t1, t2));
+                const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
+                const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
+                const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
+                const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
+                const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO)));
+                const float2 to = tanh2(ffma2(sel(pOt), ct, o1));
+                const float2 ha = fmul2(tanh2(ct), kHalf);
+                const float2 h2 = ffma2(to, ha, ha);
+                ho[i0] = h2.x; ho[i0 + 1] = h2.y;
+                if (pr) { c4.z = ct.x; c4.w = ct.y; } else { c4.x = ct.x; c4.y = ct.y; }
+                if (emit) {
+                  const float2 fa = fmul2(tanh2(cf), kHalf);
+                  const float2 f2 = ffma2(to, fa, fa);
+                  fo[i0] = f2.x; fo[i0 + 1] = f2.y;
                 }
               }
-              // c' (bf16) -> B operand of the next step's aggregation (its MMAs of this step are complete)
-              *reinterpret_cast<uint4*>(smem + RS_C + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
-                  make_uint4(pack_bf16x2(cc[0], cc[1]), pack_bf16x2(cc[2], cc[3]), pack_bf16x2(cc[4], cc[5]),
-                             pack_bf16x2(cc[6], cc[7]));
-              // h' (bf16) -> shared-memory B operand of the next aggregation right away (the gate MMAs read h from
-              // TMEM, the aggregation MMAs of this step are complete); the TMEM copy follows after the last pass
-              *reinterpret_cast<uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 + ((((u & 63) >> 3) ^ (r & 7)) << 4)) =
-                  make_uint4(pack_bf16x2(ho[0], ho[1]), pack_bf16x2(ho[2], ho[3]), pack_bf16x2(ho[4], ho[5]),
-                             pack_bf16x2(ho[6], ho[7]));
+              *reinterpret_cast<float4*>(cf_row + (u >> 2) * 2048) = c4;
               if (emit) {
+                // head partial sums, two units per packed FMA: y2[z] += (v_u, v_u+1) * (W_hT[z][u], W_hT[z][u+1])
 #pragma unroll
                 for (int hsrc = 0; hsrc < 2; ++hsrc) {
-                  const float4* wp = reinterpret_cast<const float4*>(s_wh + (size_t)(hsrc * RO_U + u) * 5);
-                  float wv[40];
+                  const float2 va = hsrc ? make_float2(fo[0], fo[1]) : make_float2(ho[0], ho[1]);
+                  const float2 vb = hsrc ? make_float2(fo[2], fo[3]) : make_float2(ho[2], ho[3]);
 #pragma unroll
-                  for (int k4 = 0; k4 < 10; ++k4) {
-                    const float4 t4 = wp[k4];
-                    wv[4 * k4] = t4.x; wv[4 * k4 + 1] = t4.y; wv[4 * k4 + 2] = t4.z; wv[4 * k4 + 3] = t4.w;
+                  for (int z = 0; z < 5; ++z) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_wht + z * 256 + hsrc * RO_U + u);
+                    y2[z] = ffma2(va, make_float2(w4.x, w4.y), y2[z]);
+                    y2[z] = ffma2(vb, make_float2(w4.z, w4.w), y2[z]);
                   }
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int z = 0; z < 5; ++z) y[z] = fmaf(hsrc ? fo[i] : ho[i], wv[i * 5 + z], y[z]);
                 }
               }
             }
+            hw[hq * 2] = pack_bf16x2(ho[0], ho[1]);
+            hw[hq * 2 + 1] = pack_bf16x2(ho[2], ho[3]);
+            cw[hq * 2] = pack_bf16x2(c4.x, c4.y);
+            cw[hq * 2 + 1] = pack_bf16x2(c4.z, c4.w);
+          }
+          if (v) {
+            // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
+            // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass)
+            const uint32_t so = (u0 >> 6) * RO_BLK + r * 128 + ((((u0 & 63) >> 3) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(smem + RS_C + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            *reinterpret_cast<uint4*>(smem + RS_H + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           }
           if (p == RO_NP - 1) {
             // every gate MMA of this step has completed (ACC_FULL of the last pass): the h columns of the TMEM A
-            // operand may be overwritten.  Each thread re-reads the 4 x 16 units it stored above (its own writes;
-            // rows of invalid agents stay zero) and copies them: units u, u+1 -> column u/2.
+            // operand may be overwritten.  Each thread re-reads the 4 x 8 units it stored (its own writes; rows of
+            // invalid agents stay zero) and copies them: units u, u+1 -> column u/2.
 #pragma unroll
             for (int pp = 0; pp < RO_NP; ++pp) {
-              uint32_t hw[8];
-#pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
-                const int u = pp * RO_UN + hsel * 16 + sub * 8;
-                const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
-                                                                 ((((u & 63) >> 3) ^ (r & 7)) << 4));
-                hw[sub * 4] = t4.x; hw[sub * 4 + 1] = t4.y; hw[sub * 4 + 2] = t4.z; hw[sub * 4 + 3] = t4.w;
-              }
-              tmem_st8(t_row + RT_A_H + pp * 16 + hsel * 8, hw);
+              const int u = pp * RO_UN + cs * 8;
+              const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
+                                                               ((((u & 63) >> 3) ^ (r & 7)) << 4));
+              const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+              tmem_st4(t_row + RT_A_H + pp * 16 + cs * 4, w4);
             }
             tmem_wait_st();
           }
           tc_fence_before();
           mbar_arrive(ACC_EMPTY + 8 * b);
-          ++pc;
         }
         if (dbg) dbg[13] = clock64();
-        // ---- (f) head: combine the two column halves of each row, emit the 5 parameters and the next position
+        // ---- (f) head: combine the four column slices of each row, emit the 5 parameters and the next position
         if (emit) {
-          if (hsel == 1) {
+          {
+            uint32_t yw[8];
 #pragma unroll
-            for (int z = 0; z < 5; ++z) s_head[r * 5 + z] = y[z];
+            for (int z = 0; z < 5; ++z) yw[z] = __float_as_uint(y2[z].x + y2[z].y);
+            yw[5] = yw[6] = yw[7] = 0u;
+            tmem_st8(t_row + RT_HEAD + cs * 8, yw);
+            tmem_wait_st();
+            tc_fence_before();
           }
           worker_sync();
-          if (hsel == 0) {
+          if (cs == 0) {
+            tc_fence_after();
+            float p0[8], p1[8], p2[8], p3[8];
+            tmem_ld8(t_row + RT_HEAD, p0);
+            tmem_ld8(t_row + RT_HEAD + 8, p1);
+            tmem_ld8(t_row + RT_HEAD + 16, p2);
+            tmem_ld8(t_row + RT_HEAD + 24, p3);
+            tmem_wait_ld();
             float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             if (v) {
 #pragma unroll
-              for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + s_wh[256 * 5 + z];
+              for (int z = 0; z < 5; ++z) o[z] = (p0[z] + p1[z]) + (p2[z] + p3[z]) + __ldg(a.b_h + z);
               o[2] = __expf(o[2]);
               o[3] = __expf(o[3]);
               o[4] = tanh_fast(o[4]);
@@ -566,6 +576,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               for (int z = 0; z < 5; ++z) po[z] = o[z];
             }
             s_next[r] = make_float2(cur.x + o[0], cur.y + o[1]);
+            tc_fence_before();
           }
           worker_sync();
         }
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == RO_WWARPS) tmem_dealloc(tmem_base, 512);
 }
 
 // pos[R,F,2], vis[R,T,2], valid[R] -> params[R,P,5].  Requires 128 % N == 0, N >= 8, U = 128, E = 64.
