@@ -249,9 +249,10 @@ extern "C" int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_
                                 int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
                                 int64_t* timeline, void* stream) {
   using namespace mmt;
-  MMT_REQUIRE(pos && vis && valid && cw && params, "pos/vis/valid/weights/params required");
   MMT_REQUIRE(S >= 0 && N >= 8 && N <= 128 && 128 % N == 0, "fused rollout needs N in {8,16,32,64,128}");
   MMT_REQUIRE(T >= 1 && P >= 1, "need T >= 1, P >= 1");
+  if (S == 0) return MMT_OK;   // empty batch: nothing to read or write (the buffers may be NULL)
+  MMT_REQUIRE(pos && vis && valid && cw && params, "pos/vis/valid/weights/params required");
   MMT_REQUIRE(cw->U == 128 && cw->E == 64 && cw->W_h && cw->b_h && cw->W_packed_bf16,
               "needs U = 128, E = 64, head weights and W_packed_bf16");
   MMT_ALIGNED(pos);

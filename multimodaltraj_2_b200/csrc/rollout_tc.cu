@@ -109,6 +109,14 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   __syncwarp();
 }
 
+// One mbarrier arrival per warp: 512 per-thread arrivals on one barrier word serialise in the shared-memory
+// atomic unit (the issuer saw a barrier complete ~1000 clk after the typical worker had arrived).  Every lane has
+// issued its own fences; __syncwarp orders the lanes' writes before lane 0's releasing arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
@@ -138,11 +146,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACC_FULL + 8 * b, 1);
-      mbar_init(ACC_EMPTY + 8 * b, RO_WORKERS);
+      mbar_init(ACC_EMPTY + 8 * b, RO_WWARPS);
     }
-    mbar_init(ATT_READY, RO_WORKERS);
-    mbar_init(E_READY, RO_WORKERS);
-    mbar_init(MH_READY, RO_WORKERS);
+    mbar_init(ATT_READY, RO_WWARPS);
+    mbar_init(E_READY, RO_WWARPS);
+    mbar_init(MH_READY, RO_WWARPS);
     mbar_init(AGG_FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       for (int t = 0; t < nsteps; ++t, ++sc) {
         const uint32_t par = sc & 1u;
         const bool emit = t >= a.T - 1;
-        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == 0 && sc < 64) ? a.dbg + sc * 32 : nullptr;
+        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == ((a.flags >> 8) & 15) * 32 && sc < 64) ? a.dbg + sc * 32 : nullptr;
         if (dbg) dbg[0] = clock64();
         // ---- (a) current position and the cell input x = [cur - prev | vislet] of row r
         float2 cur;
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         }
         fence_proxy_async();   // generic-proxy smem writes (att; h', c' of the previous step) -> async proxy
         tc_fence_before();     // (and the h' tcgen05.st of the previous step, already waited for)
-        mbar_arrive(ATT_READY);
+        mbar_arrive_warp(ATT_READY);
         if (dbg) dbg[1] = clock64();
         // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Runs while
         //      the aggregation MMAs execute (placing it before the attention build delayed them: measured +900 clk)
@@ -399,12 +407,17 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             pk[hq * 2] = pack_bf16x2(e0, e1);
             pk[hq * 2 + 1] = pack_bf16x2(e2, e3);
           }
-          tmem_st8(t_row + RT_A + cs * 8, pk);
-          tmem_wait_st();
+          if (!(a.flags & 32)) {
+            tmem_st8(t_row + RT_A + cs * 8, pk);
+            tmem_wait_st();
+          }
         }
+        if (dbg) dbg[15] = clock64();
         tc_fence_before();
-        mbar_arrive(E_READY);
+        mbar_arrive_warp(E_READY);
+        if (dbg) dbg[12] = clock64();
         asm volatile("cp.async.wait_all;" ::: "memory");
+        if (dbg) dbg[10] = clock64();
         worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
         const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
         const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(MH_READY);
+        mbar_arrive_warp(MH_READY);
         if (dbg) dbg[4] = clock64();
 
         // ---- (e) gate epilogue: 4 passes; this thread: row r, units 32 p + 8 cs .. +7, four at a time
@@ -539,7 +552,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             tmem_wait_st();
           }
           tc_fence_before();
-          mbar_arrive(ACC_EMPTY + 8 * b);
+          mbar_arrive_warp(ACC_EMPTY + 8 * b);
         }
         if (dbg) dbg[13] = clock64();
         // ---- (f) head: combine the four column slices of each row, emit the 5 parameters and the next position

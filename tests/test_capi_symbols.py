@@ -42,6 +42,15 @@ def test_argument_validation_without_a_gpu():
     assert lib.mmt_pairwise_adj_f32(None, None, 0, 8, 1.0, 1.0, None, None, None, None) == 0       # empty batch
     assert lib.mmt_decode_score_f32(None, None, 0, 0, None, None, None, 1, 4, 40, 20, None, None, None, None, None,
                                     None, None) == -1                                              # P > 32
+    # fused rollout: pointer / shape checks come before any launch
+    assert lib.mmt_rollout_bf16(None, None, None, None, 1, 64, 8, 12, 4.0, 0.5, None, None, None) == -1
+    assert lib.mmt_rollout_bf16(None, None, None, None, 0, 64, 8, 12, 4.0, 0.5, None, None, None) == 0   # empty batch
+    cw = _lib.CellWeights()
+    cw.E, cw.U = 64, 128
+    import ctypes as C
+    one = C.c_void_p(16)          # non-NULL, 16-byte aligned placeholder: rejected by the shape check before any use
+    assert lib.mmt_rollout_bf16(one, one, one, C.byref(cw), 1, 12, 8, 12, 4.0, 0.5, one, None, None) == -1   # 128 % N != 0
+    assert b"N in {8,16,32,64,128}" in lib.mmt_last_error()
 
 
 def test_sass_contains_blackwell_tensor_and_bulk_copy_instructions():
@@ -50,6 +59,7 @@ def test_sass_contains_blackwell_tensor_and_bulk_copy_instructions():
     assert "UTCHMMA" in sass, "tcgen05.mma missing from SASS"
     assert "LDTM" in sass, "tcgen05.ld missing from SASS"
     assert "UBLKCP" in sass, "cp.async.bulk (TMA bulk copy) missing from SASS"
+    assert "STTM" in sass, "tcgen05.st (operands written to tensor memory) missing from SASS"
 
 
 def test_product_path_does_not_import_the_oracle():

@@ -343,3 +343,61 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
     assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
     assert np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max() < 5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# fused persistent rollout (mmt_rollout_bf16): the whole recurrence in one launch, state on chip
+@pytest.mark.parametrize("S,N", [(8, 64), (21, 16), (2, 128), (40, 8), (9, 32), (300, 64)])
+def test_rollout_bf16_matches_oracle_and_stepwise(cuda, S, N):
+    """bf16/tcgen05 mode, tolerance stated separately from fp32: the fused kernel's predicted mean trajectory is
+    within 5e-2 of the fp32 oracle and within 2.5e-2 of the per-step bf16 kernels (which keep c in fp32 HBM and
+    round mc to bf16; the fused kernel keeps c in fp32 on chip and mc in fp32).  S*N % 128 != 0 exercises the
+    tail tile; ragged validity masks exercise empty rows; S = 300 makes a CTA walk several tiles."""
+    T, P = 8, 12
+    pos, vis, valid = synth.make_crowd(S, N, seed=200 + N, half_extent=4.0, ragged=True)
+    p = synth.init_params(seed=5)
+    cp = ops.CellParams.from_numpy(p, cuda)
+    par = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), cp, T, P, 4.0, 0.5))
+    assert np.isfinite(par).all()
+    assert (par[valid == 0] == 0).all()                      # invalid agents: zero parameters
+    got_mean = np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T]
+    if S <= 40:                                              # the numpy oracle is slow: small cases only
+        eps = np.zeros((S, N, 1, P, 2), np.float32)
+        want = o_b.forecast(pos, vis, valid, p, eps, T, P)
+        m = valid.astype(bool)
+        assert np.abs(got_mean - want["pred_mean"])[m].max() < 5e-2
+        assert np.abs(par[..., 2:] - want["params"][..., 2:])[m].max() < 5e-2
+    fs = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)
+    step = npy(fs(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"])
+    step_mean = np.cumsum(step[..., :2], 2) + pos[:, :, T - 1:T]
+    assert np.abs(got_mean - step_mean).max() < 2.5e-2
+    # the forecaster's default bf16 mode runs the fused kernel: identical parameters
+    ff = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16, device=cuda)
+    assert np.array_equal(npy(ff(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"]), par)
+
+
+def test_rollout_bf16_is_deterministic_and_scene_local(cuda):
+    """Scenes are independent: a scene's result does not depend on which other scenes share its tile or batch
+    (the property the scene-sharded multi-GPU path relies on), and two runs are bit-identical."""
+    T, P, N = 8, 12, 32
+    pos, vis, valid = synth.make_crowd(12, N, seed=77, half_extent=4.0, ragged=True)
+    cp = ops.CellParams.from_numpy(synth.init_params(seed=1), cuda)
+    a = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), cp, T, P))
+    b = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), cp, T, P))
+    assert np.array_equal(a, b)
+    sel = [5, 2, 9]                                          # other order, other tile mates
+    c = npy(ops.rollout_bf16(dev(pos[sel], cuda), dev(vis[sel], cuda), dev(valid[sel], cuda), cp, T, P))
+    assert np.array_equal(c, a[sel])
+
+
+def test_rollout_bf16_empty_batch_and_other_horizons(cuda):
+    cp = ops.CellParams.from_numpy(synth.init_params(seed=1), cuda)
+    z = ops.rollout_bf16(torch.zeros((0, 16, 20, 2), device=cuda), torch.zeros((0, 16, 8, 2), device=cuda),
+                         torch.zeros((0, 16), dtype=torch.uint8, device=cuda), cp)
+    assert z.shape == (0, 16, 12, 5)
+    T, P, S, N = 5, 3, 4, 16                                 # a shorter horizon than the default obs 8 / pred 12
+    pos, vis, valid = synth.make_crowd(S, N, T=T, P=P, seed=3, half_extent=3.0)
+    p = synth.init_params(seed=2)
+    par = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), ops.CellParams.from_numpy(p, cuda), T, P))
+    want = o_b.forecast(pos, vis, valid, p, np.zeros((S, N, 1, P, 2), np.float32), T, P)
+    assert np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max() < 5e-2
