@@ -74,6 +74,17 @@ int mmt_edge_mlp_f32(const float* h, const uint8_t* adj, const float* W1, const 
                      int S, int N, int U, int He, float* score, float* work, size_t work_bytes,
                      void* stream);
 
+/* The same edge MLP on the tcgen05 tensor cores (bf16 operands, fp32 accumulation; U = He = 128): node projections
+ * [a | b] = h [W1a | W1b] as one GEMM, then per tile of 128 EDGES of the adjacency mask
+ * e1 = elu(a_i + b_j + b1) -> e2 = elu(e1 W2 + b2) (MMA) -> sigmoid(w_out . e2 + b_out).  `packed` comes from
+ * mmt_pack_edge_weights_bf16 (mmt_edge_weights_packed_bytes bytes).  work: >= 2*S*N*He floats.
+ * Replaces relational_inf_models/nri_learned.py:5-28 like mmt_edge_mlp_f32; tolerance 2e-2 vs the fp32 oracle. */
+size_t mmt_edge_weights_packed_bytes(int U, int He);
+int mmt_pack_edge_weights_bf16(const float* W1, const float* W2, int U, int He, void* packed, void* stream);
+int mmt_edge_mlp_bf16(const float* h, const uint8_t* adj, const void* packed, const float* b1, const float* b2,
+                      const float* w_out, const float* b_out, int S, int N, int U, int He, float* score,
+                      float* work, size_t work_bytes, void* stream);
+
 /* ---- gsk_lstm_cell: fused gate update ---------------------------------------------------------
  * Replaces models/gsk_lstm_cell.py:4-65 (dead Hadamard stub) with the GridLSTMCell gate
  * equations of helper.py:31-39 at U units over the graph neighbourhood:

@@ -46,6 +46,10 @@ SIGNATURES = {
     "mmt_aggregate_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "mmt_edge_mlp_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                    C.c_size_t, vp]),
+    "mmt_edge_weights_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mmt_pack_edge_weights_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "mmt_edge_mlp_bf16": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t,
+                                    vp]),
     "mmt_gsk_cell": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                C.c_int, vp, vp]),
     "mmt_gate_weights_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -1,0 +1,359 @@
+// Relational edge MLP of g2k_lstm_mcr on the 5th-generation tensor cores (bf16 operands, fp32 accumulation in
+// TMEM): SURVEY App. C.3 / section 8(f) rank 1; include/mmt.h mmt_edge_mlp_bf16.
+//
+//   [a | b] = h [W1a | W1b]                   node level:  node_proj_tc_kernel, one M128 x N256 x K128 GEMM per 128 rows
+//   e1_ij = elu(a_i + b_j + b1)               edge level:  edge_mlp_tc_kernel, per tile of 128 EDGES of the adjacency
+//   e2_ij = elu(e1_ij W2 + b2)                             mask: gather -> e1 tile (bf16, SWIZZLE_128B) -> 8 MMAs
+//   score_ij = sigmoid(w_out . e2_ij + b_out)              M128 x N128 x K16 -> epilogue from TMEM -> scatter
+// The crowd graphs are sparse (~3 neighbours per agent): only edges are evaluated, and an edge costs 2 x 512 B of
+// gathered node projections (L2-resident per scene) + 32 kFLOP on the tensor pipe; the fp32 CUDA-core version
+// (edge_mlp.cu, parity mode) spent 3.7 ms per step on C3, 77 % of the g2k_lstm_mcr step.
+#include <cuda_bf16.h>
+
+#include "mmt_common.cuh"
+#include "tc_common.cuh"
+
+namespace mmt {
+
+constexpr int EM_U = 128, EM_HE = 128;
+constexpr int EM_W1_BYTES = 2 * 256 * 128;     // [k-block 2][256 out rows][128 B]
+constexpr int EM_W2_BYTES = 2 * 128 * 128;     // [k-block 2][128 out rows][128 B]
+constexpr int EM_BLK = 128 * 128;              // A operand k-block: [128 rows][128 B]
+
+// ------------------------------------------------------------------------------------------------
+// packing: W1[2U,He], W2[He,He] fp32 row-major -> bf16 K-major SWIZZLE_128B operand images
+__global__ void pack_edge_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
+                                         uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 256 * 128) {
+    const int n = idx >> 7, k = idx & 127;   // output column n of [a | b], input unit k
+    const float w = n < 128 ? W1[(size_t)k * EM_HE + n] : W1[(size_t)(EM_U + k) * EM_HE + (n - 128)];
+    *reinterpret_cast<__nv_bfloat16*>(out + (k >> 6) * (256 * 128) + sw128_off(n, k & 63)) = __float2bfloat16_rn(w);
+  } else if (idx < 256 * 128 + 128 * 128) {
+    const int i2 = idx - 256 * 128;
+    const int n = i2 >> 7, k = i2 & 127;
+    *reinterpret_cast<__nv_bfloat16*>(out + EM_W1_BYTES + (k >> 6) * EM_BLK + sw128_off(n, k & 63)) =
+        __float2bfloat16_rn(W2[(size_t)k * EM_HE + n]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// node projections: out[R, 256] = h[R, 128 (ld)] x [W1a | W1b]   (fp32 in HBM, bf16 operands)
+constexpr int NP_SM_B = 0;                          // 64 KB
+constexpr int NP_SM_A = NP_SM_B + EM_W1_BYTES;      // 32 KB
+constexpr int NP_SM_BAR = NP_SM_A + 34 * 1024;      // A block (32 KB); the epilogue staging [8][32][33] floats needs 33 KB
+constexpr int NP_SM_TOTAL = NP_SM_BAR + 32;
+constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
+
+__global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
+                                                              const uint8_t* __restrict__ Wp, float* __restrict__ out,
+                                                              int num_tiles) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_w = sbase + NP_SM_BAR, bar_mma = bar_w + 8;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + NP_SM_BAR + 16);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(bar_w, EM_W1_BYTES);
+    bulk_g2s(sbase + NP_SM_B, Wp, EM_W1_BYTES, bar_w);
+  }
+  if (warp == 0) tmem_alloc(sbase + NP_SM_BAR + 16, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  mbar_wait(bar_w, 0);
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int row0 = tile * 128;
+    // A operand: one warp per row, lane -> 4 consecutive k (fp32 -> bf16), K-major SWIZZLE_128B
+    for (int rr = warp; rr < 128; rr += 8) {
+      const int g = row0 + rr;
+      float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < R) hv = __ldg(reinterpret_cast<const float4*>(h + (size_t)g * ld_h) + lane);
+      const int k = lane * 4;
+      *reinterpret_cast<uint2*>(smem + NP_SM_A + (k >> 6) * EM_BLK + sw128_off(rr, k & 63)) =
+          make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t da = make_desc_sw128(sbase + NP_SM_A + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
+        const uint64_t db = make_desc_sw128(sbase + NP_SM_B + (ks >> 2) * (256 * 128)) + (uint64_t)((ks & 3) * 2);
+        umma_bf16(tmem_base, da, db, kIdescNP, ks ? 1u : 0u);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, it & 1u);
+    tc_fence_after();
+    // epilogue: warp w -> rows 32 (w % 4) .., columns 128 (w / 4) ..  TMEM gives a lane one ROW; stored directly that
+    // is 32 rows x 16 B per instruction.  Each warp instead transposes 32 x 32 blocks through its 4 KB slice of the
+    // (now free) A block, so that every global store instruction writes 32 consecutive floats of one row.
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+      float* stg = reinterpret_cast<float*>(smem + NP_SM_A) + warp * (32 * 33);   // [32][33] padded
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_ld8(t_row + cb * 32 + j * 8, v[j]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stg[lane * 33 + j * 8 + i] = v[j][i];
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int g = row0 + q * 32 + rr;
+          if (g < R) out[(size_t)g * 256 + half * 128 + cb * 32 + lane] = stg[rr * 33 + lane];
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // TMEM drained and the A block free before the next tile
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge level
+constexpr int EE_LIST = 4096;                       // candidate pairs scanned per chunk (>= edges found)
+constexpr int EE_SM_W2 = 0;                         // 32 KB
+constexpr int EE_SM_A = EE_SM_W2 + EM_W2_BYTES;     // 32 KB
+constexpr int EE_SM_LIST = EE_SM_A + 2 * EM_BLK;    // u32[EE_LIST]: i << 16 | j (scene-local)
+constexpr int EE_SM_PAR = EE_SM_LIST + EE_LIST * 4; // b1[128] b2[128] w_out[128]
+constexpr int EE_SM_PART = EE_SM_PAR + 3 * 128 * 4; // float[128]: partial sums of the upper column half
+constexpr int EE_SM_BAR = EE_SM_PART + 512;
+constexpr int EE_SM_TOTAL = EE_SM_BAR + 48;
+constexpr uint32_t kIdescEE = make_idesc_bf16(128, 128);
+
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_fast(x * 1.4426950408889634f) - 1.0f; }
+
+__global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __restrict__ nab,   // [R, 256] = [a | b]
+                                                             const uint8_t* __restrict__ adj, const uint8_t* __restrict__ Wp,
+                                                             const float* __restrict__ b1, const float* __restrict__ b2,
+                                                             const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                                             int S, int N, float* __restrict__ score, int zero_fill) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_w = sbase + EE_SM_BAR, bar_mma = bar_w + 8;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + EE_SM_BAR + 16);
+  int* s_count = reinterpret_cast<int*>(smem + EE_SM_BAR + 24);
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + EE_SM_LIST);
+  float* s_b1 = reinterpret_cast<float*>(smem + EE_SM_PAR);
+  float* s_b2 = s_b1 + 128;
+  float* s_wo = s_b2 + 128;
+  float* s_part = reinterpret_cast<float*>(smem + EE_SM_PART);
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(bar_w, EM_W2_BYTES);
+    bulk_g2s(sbase + EE_SM_W2, Wp + EM_W1_BYTES, EM_W2_BYTES, bar_w);
+  }
+  if (warp == 0) tmem_alloc(sbase + EE_SM_BAR + 16, 128);
+  if (tid < 128) {
+    s_b1[tid] = b1[tid];
+    s_b2[tid] = b2[tid];
+    s_wo[tid] = w_out[tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const float bo = __ldg(b_out);
+  mbar_wait(bar_w, 0);
+  const int rows_per_chunk = EE_LIST / N > 0 ? EE_LIST / N : 1;
+  uint32_t it = 0;
+
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    float* sc = score + (size_t)s * N * N;
+    const uint8_t* ad = adj + (size_t)s * N * N;
+    const float* nab_s = nab + (size_t)s * N * 256;
+    if (zero_fill)
+      for (int i = tid; i < (N * N) >> 2; i += 256) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < N; r0 += rows_per_chunk) {
+      if (tid == 0) *s_count = 0;
+      __syncthreads();
+      // ---- compact the edges of rows [r0, r1) (ballot + one shared atomic per warp)
+      const int r1 = min(N, r0 + rows_per_chunk);
+      const int tot = (r1 - r0) * N;
+      for (int e0 = 0; e0 < tot; e0 += 256) {
+        const int e = e0 + tid;
+        const bool is = e < tot && ad[(size_t)r0 * N + e] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, is);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(s_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is) s_list[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)(r0 + e / N) << 16) | (uint32_t)(e % N);
+      }
+      __syncthreads();
+      const int ne = *s_count;
+      for (int t0 = 0; t0 < ne; t0 += 128, ++it) {
+        const int nt = min(128, ne - t0);
+        // ---- e1 tile: warp w builds edges 16 w .. 16 w + 15; lane -> 4 consecutive k, so every gather of a_i / b_j
+        //      is one coalesced 512-byte row (a thread-per-edge walk made each load instruction touch 32 sectors
+        //      and the tile took ~20 k clk); four edges in flight per warp
+        {
+          const int k = lane * 4;
+          const float4 c4 = *reinterpret_cast<const float4*>(s_b1 + k);
+          uint8_t* blk = smem + EE_SM_A + (k >> 6) * EM_BLK + ((k & 7) << 1);
+          const int chunk = (k & 63) >> 3;
+#pragma unroll
+          for (int e0 = 0; e0 < 16; e0 += 4) {
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = warp * 16 + e0 + u;
+              av[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e < nt) {
+                const uint32_t ij = s_list[t0 + e];
+                av[u] = __ldg(reinterpret_cast<const float4*>(nab_s + (size_t)(ij >> 16) * 256) + lane);
+                bv[u] = __ldg(reinterpret_cast<const float4*>(nab_s + (size_t)(ij & 0xffffu) * 256 + 128) + lane);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = warp * 16 + e0 + u;   // rows beyond nt get elu(b1): finite, never read back
+              *reinterpret_cast<uint2*>(blk + e * 128 + ((chunk ^ (e & 7)) << 4)) =
+                  make_uint2(pack_bf16x2(elu_fast(av[u].x + bv[u].x + c4.x), elu_fast(av[u].y + bv[u].y + c4.y)),
+                             pack_bf16x2(elu_fast(av[u].z + bv[u].z + c4.z), elu_fast(av[u].w + bv[u].w + c4.w)));
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t da = make_desc_sw128(sbase + EE_SM_A + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
+            const uint64_t db = make_desc_sw128(sbase + EE_SM_W2 + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
+            umma_bf16(tmem_base, da, db, kIdescEE, ks ? 1u : 0u);
+          }
+          umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, it & 1u);
+        tc_fence_after();
+        // ---- epilogue: thread -> (edge row, 64 columns): sum_c elu(acc + b2) * w_out
+        {
+          const int q = warp & 3, half = warp >> 2;
+          const int r = q * 32 + lane;
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + half * 64;
+          float part = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 8; ch += 2) {
+            float v0[8], v1[8];
+            tmem_ld8(t_row + ch * 8, v0);
+            tmem_ld8(t_row + ch * 8 + 8, v1);
+            tmem_wait_ld();
+            const int c = half * 64 + ch * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(s_b2 + c + i), ww = *reinterpret_cast<const float4*>(s_wo + c + i);
+              part = fmaf(elu_fast(v0[i] + bb.x), ww.x, part);
+              part = fmaf(elu_fast(v0[i + 1] + bb.y), ww.y, part);
+              part = fmaf(elu_fast(v0[i + 2] + bb.z), ww.z, part);
+              part = fmaf(elu_fast(v0[i + 3] + bb.w), ww.w, part);
+              const float4 bc = *reinterpret_cast<const float4*>(s_b2 + c + 8 + i), wc = *reinterpret_cast<const float4*>(s_wo + c + 8 + i);
+              part = fmaf(elu_fast(v1[i] + bc.x), wc.x, part);
+              part = fmaf(elu_fast(v1[i + 1] + bc.y), wc.y, part);
+              part = fmaf(elu_fast(v1[i + 2] + bc.z), wc.z, part);
+              part = fmaf(elu_fast(v1[i + 3] + bc.w), wc.w, part);
+            }
+          }
+          if (half == 1) s_part[r] = part;
+          tc_fence_before();
+          __syncthreads();   // partial sums visible; TMEM drained; A block free
+          if (half == 0 && r < nt) {
+            const uint32_t ij = s_list[t0 + r];
+            const float z = part + s_part[r] + bo;
+            sc[(size_t)(ij >> 16) * N + (ij & 0xffffu)] = 1.0f / (1.0f + __expf(-z));
+          }
+        }
+      }
+      __syncthreads();   // the list is rebuilt by the next chunk
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// h[R, U] (row stride ld_h) -> score[S,N,N] on the edges of adj; nab: >= R*256 floats of scratch.
+int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
+                       int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
+  const int R = S * N, tiles = (R + 127) / 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(node_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
+    cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EE_SM_TOTAL + 1024);
+    attr_set = true;
+  }
+  const uint8_t* Wp = reinterpret_cast<const uint8_t*>(packed);
+  int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  node_proj_tc_kernel<<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nab, tiles);
+  count_launch();
+  int rc = check_launch("node_proj_tc_kernel");
+  if (rc) return rc;
+  grid = S < 2 * kNumSMs ? S : 2 * kNumSMs;
+  edge_mlp_tc_kernel<<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nab, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
+                                                                zero_fill);
+  count_launch();
+  return check_launch("edge_mlp_tc_kernel");
+}
+
+int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream) {
+  const int n = 256 * 128 + 128 * 128;
+  pack_edge_weights_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W1, W2, reinterpret_cast<uint8_t*>(packed));
+  count_launch();
+  return check_launch("pack_edge_weights_kernel");
+}
+
+}  // namespace mmt
+
+extern "C" size_t mmt_edge_weights_packed_bytes(int U, int He) {
+  if (U != mmt::EM_U || He != mmt::EM_HE) return 0;
+  return (size_t)mmt::EM_W1_BYTES + mmt::EM_W2_BYTES;
+}
+
+extern "C" int mmt_pack_edge_weights_bf16(const float* W1, const float* W2, int U, int He, void* packed, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(W1 && W2 && packed, "W1/W2/packed must not be NULL");
+  MMT_REQUIRE(U == EM_U && He == EM_HE, "packing is built for U = 128, He = 128");
+  MMT_ALIGNED(packed);
+  return launch_pack_edge_weights(W1, W2, packed, (cudaStream_t)stream);
+}
+
+extern "C" int mmt_edge_mlp_bf16(const float* h, const uint8_t* adj, const void* packed, const float* b1, const float* b2,
+                                 const float* w_out, const float* b_out, int S, int N, int U, int He, float* score,
+                                 float* work, size_t work_bytes, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(S >= 0 && N > 0 && N % 4 == 0 && N <= 1024, "need 0 < N <= 1024, N % 4 == 0");
+  MMT_REQUIRE(U == EM_U && He == EM_HE, "tensor-core edge MLP is built for U = 128, He = 128");
+  if (S == 0) return MMT_OK;
+  MMT_REQUIRE(h && adj && packed && b1 && b2 && w_out && b_out && score && work, "all pointers required");
+  MMT_ALIGNED(h);
+  MMT_ALIGNED(packed);
+  MMT_ALIGNED(score);
+  MMT_ALIGNED(work);
+  if (work_bytes < sizeof(float) * 2 * (size_t)S * N * He) {
+    set_error("mmt_edge_mlp_bf16: workspace too small");
+    return MMT_EWORKSPACE;
+  }
+  mmt_edge_weights w{nullptr, b1, nullptr, b2, w_out, b_out, He};
+  return launch_edge_mlp_tc(h, U, adj, packed, &w, S, N, score, work, 1, (cudaStream_t)stream);
+}

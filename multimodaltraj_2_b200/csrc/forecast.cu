@@ -25,6 +25,9 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
                         cudaStream_t stream);
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
                                float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
+                       int N, float* score, float* nab, int zero_fill, cudaStream_t stream);
+int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream);
 int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
                       int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, cudaStream_t stream);
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const float* __restr
 
 struct Workspace {
   float *pbuf[3], *x, *hc[2], *mhc, *mf, *kern, *score, *ework, *params, *last_obs, *gt;
+  void* epacked;        // bf16 operand images of the edge-MLP weights (relational bf16 modes)
   uint8_t* adj;
   // bf16-state fast path (non-relational bf16 mode): h, mh, mc bf16 [R,U]; c fp32 [R,U]
   void *hb[2], *mhb, *mcb;
@@ -110,6 +114,7 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   }
   w.score = (float*)take(cfg->relational ? NN * 4 : 0);
   w.ework = (float*)take(cfg->relational ? 2 * R * He * 4 : 0);
+  w.epacked = take(cfg->relational && cfg->prec != MMT_PREC_F32 && U == 128 && He == 128 ? 96 * 1024 : 0);
   w.params = (float*)take(R * cfg->P * 5 * 4);
   w.last_obs = (float*)take(R * 2 * 4);
   w.gt = (float*)take(R * cfg->P * 2 * 4);
@@ -169,6 +174,9 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   }
   int ic = 0, ip = 1, in = 2, hb = 0;
   int rc;
+  // relational bf16 modes: the edge MLP runs on the tensor cores (edge_mlp_tc.cu); weights packed once per call
+  const bool edge_tc = cfg->relational && cfg->prec != MMT_PREC_F32 && U == 128 && He == 128;
+  if (edge_tc && (rc = launch_pack_edge_weights(ew->W1, ew->W2, w.epacked, stream))) return rc;
   for (int t = 0; t < (fused ? 0 : T + P - 1); ++t) {
     prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
     count_launch();
@@ -206,7 +214,10 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       return rc;
     const float* l2 = nullptr;
     if (cfg->relational) {
-      if ((rc = launch_edge_mlp_f32(w.hc[hb], 2 * U, w.adj, ew, S, N, U, w.score, w.ework, stream))) return rc;
+      // (the aggregation reads the scores only on the edges: no zero fill needed here)
+      if (edge_tc) rc = launch_edge_mlp_tc(w.hc[hb], 2 * U, w.adj, w.epacked, ew, S, N, w.score, w.ework, 0, stream);
+      else rc = launch_edge_mlp_f32(w.hc[hb], 2 * U, w.adj, ew, S, N, U, w.score, w.ework, stream);
+      if (rc) return rc;
       l2 = w.score;
     }
     if ((rc = launch_aggregate(w.kern, l2, w.adj, w.hc[hb], S, N, 2 * U, 2 * U, nullptr, w.mhc, 2 * U, stream)))

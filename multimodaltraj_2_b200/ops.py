@@ -78,7 +78,9 @@ def aggregate(logits, adj, feat, want_attn=True):
     return attn, out
 
 
-def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out):
+def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out, prec=PREC_F32):
+    """score[S,N,N] of the relational edge MLP on the edges of adj (0 elsewhere).  prec = PREC_BF16 runs the
+    tcgen05 version (U = He = 128)."""
     lib = _lib.load()
     for n, t in dict(h=h, W1=W1, b1=b1, W2=W2, b2=b2, w_out=w_out, b_out=b_out).items():
         _chk(t, torch.float32, n)
@@ -87,6 +89,15 @@ def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out):
     He = W2.shape[0]
     score = torch.empty((S, N, N), dtype=torch.float32, device=h.device)
     work = torch.empty((2 * S * N * He,), dtype=torch.float32, device=h.device)
+    if prec != PREC_F32:
+        nb = lib.mmt_edge_weights_packed_bytes(U, He)
+        if nb == 0:
+            raise ValueError("tensor-core edge MLP needs U = He = 128")
+        packed = torch.empty((nb,), dtype=torch.uint8, device=h.device)
+        _lib.check(lib.mmt_pack_edge_weights_bf16(_p(W1), _p(W2), U, He, _p(packed), _stream()), "mmt_pack_edge_weights_bf16")
+        _lib.check(lib.mmt_edge_mlp_bf16(_p(h), _p(adj), _p(packed), _p(b1), _p(b2), _p(w_out), _p(b_out), S, N, U, He,
+                                         _p(score), _p(work), work.numel() * 4, _stream()), "mmt_edge_mlp_bf16")
+        return score
     _lib.check(lib.mmt_edge_mlp_f32(_p(h), _p(adj), _p(W1), _p(b1), _p(W2), _p(b2), _p(w_out), _p(b_out), S, N, U, He,
                                     _p(score), _p(work), work.numel() * 4, _stream()), "mmt_edge_mlp_f32")
     return score

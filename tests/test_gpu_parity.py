@@ -108,6 +108,24 @@ def test_edge_mlp(cuda):
     np.testing.assert_allclose(npy(sc), osc, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("S,N", [(4, 32), (9, 64), (2, 256), (3, 12)])
+def test_edge_mlp_bf16_tensor_core(cuda, S, N):
+    """tcgen05 edge MLP (bf16 operands, fp32 accumulation, ex2-based elu): tolerance stated separately from fp32.
+    Edges exactly where the mask has them (bit-exact zero pattern), scores within 2e-2 of the fp32 oracle."""
+    U = 128
+    p = synth.init_params(seed=2)
+    rng = np.random.default_rng(6 + N)
+    pos, _, valid = synth.make_crowd(S, N, seed=23 + N, half_extent=4.0 if N < 100 else 8.0, ragged=(N == 12))
+    _, adj, _ = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
+    h = (rng.standard_normal((S, N, U)) * 0.5).astype(np.float32)
+    sc = npy(ops.edge_mlp(dev(h, cuda), dev(adj, cuda), dev(p["W1"], cuda), dev(p["b1"], cuda), dev(p["W2"], cuda),
+                          dev(p["b2"], cuda), dev(p["w_out"], cuda), dev(p["b_out"].reshape(1), cuda), prec=ops.PREC_BF16))
+    osc = o_b.edge_mlp(h, adj, p)
+    assert adj.sum() > 0
+    assert np.array_equal(sc != 0, adj != 0)
+    assert np.abs(sc - osc).max() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------
 def _cell_inputs(R, seed=0):
     rng = np.random.default_rng(seed)
@@ -343,6 +361,20 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
     assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
     assert np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max() < 5e-2
+
+
+def test_forecast_bf16_relational(cuda):
+    """g2k_lstm_mcr in bf16 mode (tcgen05 edge MLP + tcgen05 cell, per-step kernels): mean trajectory vs the fp32 oracle."""
+    S, N, T, P, K = 6, 64, 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0, ragged=True)
+    p = synth.init_params(seed=3)
+    eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
+    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=True, prec=ops.PREC_BF16, device=cuda)
+    o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+    torch.cuda.synchronize()
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=True)
+    got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
+    assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
 
 
 # ------------------------------------------------------------------------------------------------
