@@ -433,3 +433,22 @@ def test_rollout_bf16_empty_batch_and_other_horizons(cuda):
     par = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), ops.CellParams.from_numpy(p, cuda), T, P))
     want = o_b.forecast(pos, vis, valid, p, np.zeros((S, N, 1, P, 2), np.float32), T, P)
     assert np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max() < 5e-2
+
+
+def test_rollout_full_size_properties(cuda):
+    """BASELINE full size (C3: 4096 scenes x 64 agents), through size-independent properties: bit-identical repeats
+    (no races between the warp roles), scene sharding invariance (two half batches == the whole batch: what the
+    scene-sharded multi-GPU path relies on), agreement with the per-step bf16 kernels, zero rows for invalid agents."""
+    S, N, T, P = 4096, 64, 8, 12
+    pos, vis, valid = synth.make_crowd(S, N, seed=synth.SEED, ragged=True)
+    cp = ops.CellParams.from_numpy(synth.init_params(seed=0), cuda)
+    d = [dev(a, cuda) for a in (pos, vis, valid)]
+    ref = ops.rollout_bf16(*d, cp, T, P).clone()
+    for _ in range(3):
+        assert torch.equal(ops.rollout_bf16(*d, cp, T, P), ref)
+    lo = ops.rollout_bf16(*(x[:S // 2].contiguous() for x in d), cp, T, P)
+    hi = ops.rollout_bf16(*(x[S // 2:].contiguous() for x in d), cp, T, P)
+    assert torch.equal(torch.cat([lo, hi]), ref)
+    assert bool(torch.isfinite(ref).all()) and bool((ref[d[2] == 0] == 0).all())
+    step = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)(*d)["params"]
+    assert float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()) < 2.5e-2
