@@ -395,6 +395,65 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world, local_rank):
+    """--mode train: data-parallel training steps (teacher-forced NLL, BPTT through the fp32 kernels, ONE NCCL
+    all-reduce of the flat gradient bucket, RMSProp) on this rank's scene shard.  Extra mode: the headline metric of
+    BASELINE.json is the inference line printed by the default mode."""
+    import torch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from multimodaltraj_2_b200 import ops, synth
+    from multimodaltraj_2_b200.train import Trainer, flatten_bucket
+    S, N = args.scenes, args.agents
+    pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
+    pos, vis, valid = (torch.from_numpy(a).to(dev) for a in (pos_h, vis_h, valid_h))
+    params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = [float(tr.step(pos, vis, valid)) for _ in range(max(args.warmup, 1))]
+    barrier()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(pos, vis, valid)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    # all ranks hold identical weights after identical all-reduced updates
+    w = flatten_bucket({k: getattr(params, k) for k in ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h")})
+    spread = torch.stack([w.min(), -w.max()])
+    if world > 1:
+        lo = spread.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(spread, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, spread))
+    else:
+        in_sync = True
+    if rank == 0:
+        print(json.dumps({"mode": "train", "metric": "agent-trajectories/sec (training step: teacher-forced NLL + BPTT + gradient all-reduce + RMSProp)",
+                          "value": int(valid_h.sum()) * world / (ms_step * 1e-3), "unit": "agent-trajectories/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"{S} scenes x {N} agents per GPU, obs {T_OBS} / pred {P_PRED}, g2k_lstm_mc training step",
+                                     "gradient_bucket_bytes": int(w.numel() * 4), "collective": "one NCCL all-reduce (SUM) per step" if world > 1 else "none (1 GPU)"},
+                          "loss_first": losses[0], "loss_last": float(loss), "weights_identical_across_ranks": in_sync,
+                          "gpu_launches": int(ops.launch_count() - l0)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -406,6 +465,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly (no CUDA graph)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -414,6 +474,8 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.mode == "train":
+        run_train(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -244,6 +244,25 @@ int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, c
                      int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
                      int64_t* timeline, void* stream);
 
+/* ---- training step (SURVEY App. C.5 "Training loss (fills F2)", section 8e) ------------------------------------
+ * The reference has no loss / optimiser (train.py:23-366 logs raw errors); the loss defined for it is the teacher-
+ * forced mean bivariate-Gaussian NLL of the next displacement.  These two kernels are the element-wise work of one
+ * step of back-propagation through time; multimodaltraj_2_b200/train.py (Trainer) orchestrates them with the forward
+ * kernels above, library GEMMs for the weight / input gradients and one NCCL all-reduce of the flat gradient bucket.
+ *
+ * mmt_head_nll_f32: y = [m_t | m_f] W_h + b_h (raw head outputs), nll of target[R,2] under mu = y0:2,
+ * sigma = exp(y2:4), rho = tanh(y4); loss_sum[0] += scale * sum over valid rows; dy[R,5] = scale * d nll / d y
+ * (0 for invalid rows).
+ * mmt_gsk_cell_backward_f32: backward of mmt_gsk_cell given the pre-activations z[R,3U] = [e|h|mh] W + b, the
+ * previous cell state c, mc, and the upstream gradients d_mt (w.r.t. h' = m_t), d_mf, d_ct (either may be NULL = 0):
+ * dz[R,3U], dc[R,U] (w.r.t. the previous c), dmc[R,U]; dpeep[4,U] += gradients of (w_If, w_It, w_Of, w_Ot). */
+int mmt_head_nll_f32(const float* m_t, const float* m_f, const uint8_t* valid, const float* W_h, const float* b_h,
+                     const float* target, int R, int U, float scale, float* loss_sum, float* dy, void* stream);
+int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, const uint8_t* valid,
+                              const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot,
+                              const float* d_mt, const float* d_mf, const float* d_ct, int R, int U, float* dz,
+                              float* dc, float* dmc, float* dpeep, void* stream);
+
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);
 

@@ -73,6 +73,9 @@ SIGNATURES = {
     "mmt_forecast_workspace_bytes": (C.c_size_t, [C.POINTER(ForecastCfg), C.c_int, C.c_int]),
     "mmt_forecast_f32": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.POINTER(EdgeWeights),
                                    C.POINTER(ForecastCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
+    "mmt_head_nll_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
+    "mmt_gsk_cell_backward_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp,
+                                            vp]),
     "mmt_rollout_bf16": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_float, vp, vp, vp]),
 }

@@ -1,0 +1,141 @@
+// Training step of the Track-B path (SURVEY App. C.5 "Training loss (fills F2)"; section 8e: data-parallel training
+// with one gradient all-reduce): the two fused backward kernels.  The loss is the teacher-forced mean bivariate-
+// Gaussian NLL (oracle/train_b.py); back-propagation through time is orchestrated by multimodaltraj_2_b200/train.py
+// (Trainer): these kernels do the element-wise work of a step, the weight-gradient / input-gradient contractions
+// are plain library GEMMs.
+//
+//   mmt_head_nll_f32            y = [m_t | m_f] W_h + b_h ; nll(y, target) ; dy = d nll / d y          (warp per row)
+//   mmt_gsk_cell_backward_f32   gates re-evaluated from the saved pre-activations z, then d z, d c, d mc and the
+//                               peephole gradients (block-reduced, one atomicAdd per unit and block)
+#include "mmt_common.cuh"
+
+namespace mmt {
+
+__global__ void __launch_bounds__(256) head_nll_kernel(const float* __restrict__ m_t, const float* __restrict__ m_f,
+                                                       const uint8_t* __restrict__ valid, const float* __restrict__ W_h,
+                                                       const float* __restrict__ b_h, const float* __restrict__ target,
+                                                       int R, int U, float scale, float* __restrict__ loss_sum,
+                                                       float* __restrict__ dy) {
+  __shared__ float s_loss[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float wloss = 0.f;
+  for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+    float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < 2 * U; k += 32) {
+      const float v = k < U ? m_t[(size_t)r * U + k] : m_f[(size_t)r * U + (k - U)];
+#pragma unroll
+      for (int z = 0; z < 5; ++z) y[z] = fmaf(v, __ldg(W_h + (size_t)k * 5 + z), y[z]);
+    }
+#pragma unroll
+    for (int z = 0; z < 5; ++z) y[z] = warp_sum(y[z]) + __ldg(b_h + z);
+    if (lane == 0) {
+      float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid[r]) {
+        const float sx = expf(y[2]), sy = expf(y[3]), rho = tanhf(y[4]);
+        const float zx = (target[(size_t)r * 2] - y[0]) / sx, zy = (target[(size_t)r * 2 + 1] - y[1]) / sy;
+        const float om = 1.f - rho * rho, q = zx * zx - 2.f * rho * zx * zy + zy * zy;
+        wloss += (1.8378770664093453f + y[2] + y[3] + 0.5f * logf(om) + q / (2.f * om)) * scale;
+        g[0] = -(zx - rho * zy) / (om * sx) * scale;
+        g[1] = -(zy - rho * zx) / (om * sy) * scale;
+        g[2] = (1.f - (zx * zx - rho * zx * zy) / om) * scale;
+        g[3] = (1.f - (zy * zy - rho * zx * zy) / om) * scale;
+        g[4] = (-rho + (-zx * zy * om + rho * q) / om) * scale;
+      }
+#pragma unroll
+      for (int z = 0; z < 5; ++z) dy[(size_t)r * 5 + z] = g[z];
+    }
+  }
+  if (lane == 0) s_loss[warp] = wloss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_loss[w];
+    if (t != 0.f) atomicAdd(loss_sum, t);
+  }
+}
+
+// thread = unit u of a row; a block walks rows blockIdx.x, + gridDim.x, ... and keeps the four peephole partial
+// sums of its unit in registers
+__global__ void __launch_bounds__(128) gsk_cell_backward_kernel(
+    const float* __restrict__ z, const float* __restrict__ c, const float* __restrict__ mc, const uint8_t* __restrict__ valid,
+    const float* __restrict__ w_If, const float* __restrict__ w_It, const float* __restrict__ w_Of,
+    const float* __restrict__ w_Ot, const float* __restrict__ d_mt, const float* __restrict__ d_mf,
+    const float* __restrict__ d_ct, int R, int U, float* __restrict__ dz, float* __restrict__ dc,
+    float* __restrict__ dmc, float* __restrict__ dpeep) {
+  const int u = threadIdx.x;
+  if (u >= U) return;
+  const float pIf = w_If[u], pIt = w_It[u], pOf = w_Of[u], pOt = w_Ot[u];
+  float aIf = 0.f, aIt = 0.f, aOf = 0.f, aOt = 0.f;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const size_t o = (size_t)r * U + u, oz = (size_t)r * 3 * U + u;
+    float di = 0.f, dj = 0.f, dO = 0.f, dcp = 0.f, dm = 0.f;
+    if (valid[r]) {
+      const float cp = c[o], m = mc[o];
+      const float g = sigmoid_acc(z[oz] + pIf * m + pIt * cp);
+      const float tj = tanhf(z[oz + U]);
+      const float cf = (1.f - g) * m + g * tj, ct = (1.f - g) * cp + g * tj;
+      const float q = sigmoid_acc(z[oz + 2 * U] + pOf * cf + pOt * ct);
+      const float tcf = tanhf(cf), tct = tanhf(ct);
+      const float gmt = d_mt[o], gmf = d_mf ? d_mf[o] : 0.f, gct = d_ct ? d_ct[o] : 0.f;
+      const float dq = gmt * tct + gmf * tcf;
+      float dct = gmt * q * (1.f - tct * tct) + gct;
+      float dcf = gmf * q * (1.f - tcf * tcf);
+      const float dpo = dq * q * (1.f - q);
+      dcf += dpo * pOf;
+      dct += dpo * pOt;
+      aOf += dpo * cf;
+      aOt += dpo * ct;
+      const float dg = dcf * (tj - m) + dct * (tj - cp);
+      dm = dcf * (1.f - g);
+      dcp = dct * (1.f - g);
+      dj = (dcf + dct) * g * (1.f - tj * tj);
+      const float dpi = dg * g * (1.f - g);
+      dm += dpi * pIf;
+      dcp += dpi * pIt;
+      aIf += dpi * m;
+      aIt += dpi * cp;
+      di = dpi;
+      dO = dpo;
+    }
+    dz[oz] = di;
+    dz[oz + U] = dj;
+    dz[oz + 2 * U] = dO;
+    dc[o] = dcp;
+    dmc[o] = dm;
+  }
+  atomicAdd(dpeep + u, aIf);
+  atomicAdd(dpeep + U + u, aIt);
+  atomicAdd(dpeep + 2 * U + u, aOf);
+  atomicAdd(dpeep + 3 * U + u, aOt);
+}
+
+}  // namespace mmt
+
+extern "C" int mmt_head_nll_f32(const float* m_t, const float* m_f, const uint8_t* valid, const float* W_h,
+                                const float* b_h, const float* target, int R, int U, float scale, float* loss_sum,
+                                float* dy, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(R >= 0 && U > 0, "need R >= 0, U > 0");
+  if (R == 0) return MMT_OK;
+  MMT_REQUIRE(m_t && m_f && valid && W_h && b_h && target && loss_sum && dy, "all pointers required");
+  const int grid = (R + 7) / 8 < kNumSMs * 8 ? (R + 7) / 8 : kNumSMs * 8;
+  head_nll_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m_t, m_f, valid, W_h, b_h, target, R, U, scale, loss_sum, dy);
+  count_launch();
+  return check_launch("head_nll_kernel");
+}
+
+extern "C" int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, const uint8_t* valid,
+                                         const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot,
+                                         const float* d_mt, const float* d_mf, const float* d_ct, int R, int U,
+                                         float* dz, float* dc, float* dmc, float* dpeep, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(R >= 0 && U > 0 && U <= 128, "need R >= 0, 0 < U <= 128");
+  if (R == 0) return MMT_OK;
+  MMT_REQUIRE(z && c && mc && valid && w_If && w_It && w_Of && w_Ot && d_mt && dz && dc && dmc && dpeep,
+              "z/c/mc/valid/peepholes/d_mt/outputs required");
+  const int grid = R < kNumSMs * 16 ? R : kNumSMs * 16;
+  gsk_cell_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, c, mc, valid, w_If, w_It, w_Of, w_Ot, d_mt, d_mf,
+                                                                   d_ct, R, U, dz, dc, dmc, dpeep);
+  count_launch();
+  return check_launch("gsk_cell_backward_kernel");
+}

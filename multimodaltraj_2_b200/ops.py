@@ -181,6 +181,35 @@ def gsk_cell(x, h, c, mh, mc, valid, params: CellParams, prec=PREC_F32, cur_pos=
     return (h_out, c_out, mf, par, nxt) if want_head else (h_out, c_out, mf)
 
 
+def head_nll(m_t, m_f, valid, W_h, b_h, target, scale, loss_sum):
+    """Raw head + bivariate-Gaussian NLL of target[R,2]; accumulates scale * sum(nll) into loss_sum[1] and returns
+    dy[R,5] = scale * d nll / d y (mmt_head_nll_f32)."""
+    lib = _lib.load()
+    for n, t in dict(m_t=m_t, m_f=m_f, W_h=W_h, b_h=b_h, target=target, loss_sum=loss_sum).items():
+        _chk(t, torch.float32, n)
+    _chk(valid, torch.uint8, "valid")
+    R, U = m_t.shape
+    dy = torch.empty((R, 5), dtype=torch.float32, device=m_t.device)
+    _lib.check(lib.mmt_head_nll_f32(_p(m_t), _p(m_f), _p(valid), _p(W_h), _p(b_h), _p(target), R, U, float(scale),
+                                    _p(loss_sum), _p(dy), _stream()), "mmt_head_nll_f32")
+    return dy
+
+
+def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, dpeep):
+    """Backward of the gate update from the saved pre-activations (mmt_gsk_cell_backward_f32):
+    returns (dz[R,3U], dc[R,U], dmc[R,U]); dpeep[4,U] is accumulated in place."""
+    lib = _lib.load()
+    for n, t in dict(z=z, c=c, mc=mc, d_mt=d_mt, dpeep=dpeep).items():
+        _chk(t, torch.float32, n)
+    _chk(valid, torch.uint8, "valid")
+    R, U = c.shape
+    dz, dc, dmc = torch.empty_like(z), torch.empty_like(c), torch.empty_like(c)
+    _lib.check(lib.mmt_gsk_cell_backward_f32(_p(z), _p(c), _p(mc), _p(valid), _p(params.w_If), _p(params.w_It),
+                                             _p(params.w_Of), _p(params.w_Ot), _p(d_mt), _p(d_mf), _p(d_ct), R, U,
+                                             _p(dz), _p(dc), _p(dmc), _p(dpeep), _stream()), "mmt_gsk_cell_backward_f32")
+    return dz, dc, dmc
+
+
 def gridlstm_step(inputs, state, W_f, B_f, w_If, w_It, w_Of, w_Ot, U, F, peepholes=True):
     """GridLSTMCell as helper.py instantiates it.  inputs[B,>=4F], state[B,>=2UF] -> (m_out, state_out)."""
     lib = _lib.load()

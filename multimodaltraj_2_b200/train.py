@@ -62,6 +62,148 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
     return results
 
 
+# --------------------------------------------------------------------------------------------
+# training step (SURVEY App. C.5 "Training loss (fills F2)", section 8e): the reference has no loss or optimiser
+# (train.py:23-366 only logs raw errors); the step defined for it is
+#   teacher-forced rollout -> mean bivariate-Gaussian NLL of the next displacement + (lambda/2) ||W||^2
+#   -> back-propagation through time -> ONE all-reduce of the flat gradient bucket -> RMSProp (lr 0.005, decay 0.95,
+#   global-norm clip 10: the unused flags of argParser.py:40-47,72).
+TRAIN_KEYS = ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h")
+
+
+def flatten_bucket(grads: dict):
+    """One contiguous fp32 bucket (< 1 MB) in TRAIN_KEYS order."""
+    return torch.cat([grads[k].reshape(-1) for k in TRAIN_KEYS])
+
+
+def unflatten_bucket(flat, like: dict):
+    out, o = {}, 0
+    for k in TRAIN_KEYS:
+        n = like[k].numel()
+        out[k] = flat[o:o + n].view_as(like[k])
+        o += n
+    return out
+
+
+def allreduce_mean_(flat, counts=None):
+    """Sum-all-reduce of the gradient bucket over the data-parallel ranks (NCCL on GPUs, gloo in the CPU tests).
+    Every rank's gradient is the SUM over its own scenes of d nll; dividing by the global number of valid
+    agent-steps turns the reduced sum into the gradient of the global mean loss, whatever the sharding."""
+    dist = torch.distributed
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+        if counts is not None:
+            dist.all_reduce(counts)
+    return flat
+
+
+def rmsprop_update_(params: dict, grads: dict, ms: dict, lr=0.005, decay=0.95, eps=1e-10, clip=10.0):
+    """In-place RMSProp with global-norm clipping; returns the pre-clip gradient norm."""
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    s = torch.clamp(clip / torch.clamp(gn, min=1e-30), max=1.0)
+    for k, g in grads.items():
+        g = g * s
+        ms[k].mul_(decay).addcmul_(g, g, value=1 - decay)
+        params[k].addcdiv_(g, ms[k].sqrt() + eps, value=-lr)
+    return gn
+
+
+class Trainer:
+    """Data-parallel training of the g2k_lstm_mc cell on the B200 path (fp32 kernels of libmmt + library GEMMs).
+
+    forward  per step: mmt_pairwise_adj_f32 -> mmt_aggregate_f32 (attention kept) -> mmt_gsk_cell (fp32)
+    loss     emitting steps: mmt_head_nll_f32 (raw head, NLL, d nll / d y)
+    backward per step, reversed: head GEMMs -> mmt_gsk_cell_backward_f32 -> dW += A^T dz, dA = dz W^T (GEMMs)
+             -> relu / embedding -> att^T (d mh, d mc) back to the previous h, c
+    step()   flat bucket -> all-reduce (SUM) -> / global valid count -> + lambda W -> clip -> RMSProp.
+    """
+
+    def __init__(self, params: ops.CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, lr=0.005, decay=0.95,
+                 clip=10.0):
+        self.p, self.T, self.P, self.r2, self.inv = params, T, P, r2, inv_2sigma2
+        self.lam, self.lr, self.decay, self.clip = lam, lr, decay, clip
+        self.ms = {k: torch.zeros_like(getattr(params, k)) for k in TRAIN_KEYS}
+
+    def _tensors(self):
+        return {k: getattr(self.p, k) for k in TRAIN_KEYS}
+
+    def loss_and_grad_sums(self, pos, vis, valid):
+        """Teacher-forced forward + BPTT on this rank's scenes.  Returns (sum of nll over valid agent-steps [1],
+        number of valid agent-steps, {name: SUM-gradient}) -- sums, so that ranks combine by plain addition."""
+        p, T, P = self.p, self.T, self.P
+        S, N = valid.shape
+        R, U, E = S * N, p.U, p.E
+        dev = pos.device
+        vflat = valid.reshape(-1).contiguous()
+        h = torch.zeros((S, N, U), device=dev)
+        c = torch.zeros((S, N, U), device=dev)
+        saved = []
+        loss_sum = torch.zeros((1,), device=dev)
+        for t in range(T + P - 1):
+            cur = pos[:, :, t].contiguous()
+            disp = cur - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
+            x = torch.cat([disp, vis[:, :, min(t, T - 1)]], -1).reshape(R, 4).contiguous()
+            kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
+            att, mhc = ops.aggregate(kern, adj, torch.cat([h, c], -1).contiguous())
+            mh, mc = mhc[..., :U].reshape(R, U).contiguous(), mhc[..., U:].reshape(R, U).contiguous()
+            hn, cn, mf = ops.gsk_cell(x, h.reshape(R, U), c.reshape(R, U), mh, mc, vflat, p, ops.PREC_F32)
+            rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc, hn=hn, mf=mf)
+            if t >= T - 1:
+                rec["dy"] = ops.head_nll(hn, mf, vflat, p.W_h, p.b_h, (pos[:, :, t + 1] - cur).reshape(R, 2).contiguous(),
+                                         1.0, loss_sum)
+            saved.append(rec)
+            h, c = hn.view(S, N, U), cn.view(S, N, U)
+        # ---- back-propagation through time
+        g = {k: torch.zeros_like(getattr(p, k)) for k in TRAIN_KEYS}
+        dpeep = torch.zeros((4, U), device=dev)
+        Gh = torch.zeros((R, U), device=dev)
+        Gc = None
+        for t in reversed(range(T + P - 1)):
+            r = saved[t]
+            d_mf = None
+            if "dy" in r:
+                dy = r["dy"]
+                g["W_h"] += torch.cat([r["hn"], r["mf"]], -1).t() @ dy
+                g["b_h"] += dy.sum(0)
+                dhm = dy @ p.W_h.t()
+                Gh = Gh + dhm[:, :U]
+                d_mf = dhm[:, U:].contiguous()
+            e = torch.relu(r["x"] @ p.W_e + p.b_e)
+            A = torch.cat([e, r["h"], r["mh"]], -1)
+            z = torch.addmm(p.b, A, p.W)
+            dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep)
+            g["W"] += A.t() @ dz
+            g["b"] += dz.sum(0)
+            dA = dz @ p.W.t()
+            dpre = dA[:, :E] * (e > 0)
+            g["W_e"] += r["x"].t() @ dpre
+            g["b_e"] += dpre.sum(0)
+            attT = r["att"].transpose(1, 2)
+            Gh = dA[:, E:E + U] + torch.bmm(attT, dA[:, E + U:].reshape(S, N, U)).reshape(R, U)
+            Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
+        g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]
+        return loss_sum, valid.sum().float() * P, g
+
+    def loss_and_grads(self, pos, vis, valid):
+        """Single-process view: (mean loss incl. weight decay, {name: gradient of it})."""
+        loss_sum, n, g = self.loss_and_grad_sums(pos, vis, valid)
+        g = {k: v / n for k, v in g.items()}
+        g["W"] = g["W"] + self.lam * self.p.W
+        return loss_sum[0] / n + 0.5 * self.lam * (self.p.W * self.p.W).sum(), g
+
+    def step(self, pos, vis, valid):
+        """One data-parallel training step on this rank's scene shard; returns the global mean loss."""
+        loss_sum, n, g = self.loss_and_grad_sums(pos, vis, valid)
+        flat = flatten_bucket(g)
+        counts = torch.stack([loss_sum[0], n])
+        allreduce_mean_(flat, counts)                                  # ONE all-reduce of the < 1 MB bucket (+ 2 floats)
+        g = unflatten_bucket(flat / counts[1], g)
+        g["W"] = g["W"] + self.lam * self.p.W
+        rmsprop_update_(self._tensors(), g, self.ms, self.lr, self.decay, clip=self.clip)
+        self.p.W_packed = None                                         # the bf16 operand image is stale now
+        return counts[0] / counts[1] + 0.5 * self.lam * (self.p.W * self.p.W).sum()
+
+
 def save_checkpoint(path, params: ops.CellParams):
     """Flat {name: tensor} checkpoint (replaces tf.train.Saver, train.py:330-343)."""
     torch.save({k: getattr(params, k).cpu() for k in params.__dataclass_fields__

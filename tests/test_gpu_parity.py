@@ -452,3 +452,39 @@ def test_rollout_full_size_properties(cuda):
     assert bool(torch.isfinite(ref).all()) and bool((ref[d[2] == 0] == 0).all())
     step = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)(*d)["params"]
     assert float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()) < 2.5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# training step (teacher-forced NLL, BPTT, RMSProp): oracle = PyTorch autograd in fp64 on the CPU (oracle/train_b.py)
+def test_train_gradients_match_autograd_oracle(cuda):
+    import train_b as o_t
+    from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS
+    S, N = 3, 16
+    pos, vis, valid = synth.make_crowd(S, N, seed=5, half_extent=3.0, ragged=True)
+    p = synth.init_params(seed=1)
+    want_loss, want = o_t.loss_and_grads(pos, vis, valid, p)
+    tr = Trainer(ops.CellParams.from_numpy(p, cuda))
+    loss, g = tr.loss_and_grads(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
+    assert abs(float(loss) - want_loss) < 1e-4 * max(1.0, abs(want_loss))
+    for k in TRAIN_KEYS:                                   # fp32 kernels vs fp64 autograd: 2e-3 of the largest entry
+        assert rel_err(npy(g[k]).astype(np.float64), want[k]) < 2e-3, k
+
+
+def test_train_step_rmsprop_and_loss_decrease(cuda):
+    import train_b as o_t
+    from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS
+    S, N = 4, 16
+    pos, vis, valid = synth.make_crowd(S, N, seed=9, half_extent=3.0, ragged=True)
+    p = synth.init_params(seed=2)
+    cp = ops.CellParams.from_numpy(p, cuda)
+    tr = Trainer(cp)
+    d = [dev(a, cuda) for a in (pos, vis, valid)]
+    _, g0 = tr.loss_and_grads(*d)
+    want_p, _ = o_t.rmsprop_step({k: p[k].astype(np.float64) for k in TRAIN_KEYS},
+                                 {k: npy(g0[k]).astype(np.float64) for k in TRAIN_KEYS},
+                                 {k: np.zeros_like(p[k], np.float64) for k in TRAIN_KEYS})
+    l0 = float(tr.step(*d))
+    for k in TRAIN_KEYS:                                   # one RMSProp step from the same gradients
+        assert np.abs(npy(getattr(cp, k)) - want_p[k]).max() < 1e-5, k
+    losses = [l0] + [float(tr.step(*d)) for _ in range(6)]
+    assert losses[-1] < losses[0] - 0.05, losses

@@ -107,3 +107,60 @@ def test_scene_sharding_world_size_2_gloo():
         ret = m.dict()
         mp.spawn(_gloo_worker, args=(2, 29533, ret), nprocs=2, join=True)
         assert ret.get("ok") is True
+
+
+def _gloo_train_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import train_b as o_t
+    from multimodaltraj_2_b200 import synth
+    from multimodaltraj_2_b200.train import TRAIN_KEYS, allreduce_mean_, flatten_bucket, rmsprop_update_, unflatten_bucket
+    p = {k: torch.tensor(v) for k, v in synth.init_params(seed=4).items() if k in TRAIN_KEYS}
+    # every rank holds the SUM-gradient of its own scene shard and its own count of valid agent-steps
+    gen = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+    shard = [{k: torch.randn(p[k].shape, generator=gen[r]) for k in TRAIN_KEYS} for r in range(world)]
+    cnt = [torch.tensor([3.0 + r, 40.0 + 8 * r]) for r in range(world)]          # (loss sum, valid agent-steps)
+    flat, counts = flatten_bucket(shard[rank]), cnt[rank].clone()
+    allreduce_mean_(flat, counts)                                                # the ONE gradient all-reduce
+    g = unflatten_bucket(flat / counts[1], p)
+    ms = {k: torch.zeros_like(p[k]) for k in TRAIN_KEYS}
+    rmsprop_update_(p, g, ms)
+    if rank == 0:
+        n = sum(float(c[1]) for c in cnt)
+        want_g = {k: sum(s[k] for s in shard).numpy().astype(np.float64) / n for k in TRAIN_KEYS}
+        p0 = {k: v.astype(np.float64) for k, v in synth.init_params(seed=4).items() if k in TRAIN_KEYS}
+        want_p, _ = o_t.rmsprop_step(p0, want_g, {k: np.zeros_like(p0[k]) for k in TRAIN_KEYS})
+        ok = all(np.abs(g[k].numpy() - want_g[k]).max() < 1e-6 for k in TRAIN_KEYS)
+        ok = ok and all(np.abs(p[k].numpy() - want_p[k]).max() < 1e-5 for k in TRAIN_KEYS)
+        ret["ok"] = bool(ok and abs(float(counts[1]) - n) < 1e-6)
+    torch.distributed.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_and_rmsprop_world_size_2_gloo():
+    """Host logic of the data-parallel training step: flat bucket, one SUM all-reduce, division by the global count
+    of valid agent-steps, clipped RMSProp -- every rank ends with the update the oracle computes from the pooled data."""
+    import torch.multiprocessing as mp
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_gloo_train_worker, args=(2, 29541, ret), nprocs=2, join=True)
+        assert ret.get("ok") is True
+
+
+def test_train_oracle_gradient_matches_finite_differences():
+    """Pins the training oracle itself: autograd gradient of the teacher-forced NLL vs central differences."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import train_b as o_t
+    from multimodaltraj_2_b200 import synth
+    pos, vis, valid = synth.make_crowd(2, 8, seed=1, half_extent=2.0, ragged=True)
+    p = {k: np.asarray(v, np.float64) for k, v in synth.init_params(seed=3).items()}
+    _, g = o_t.loss_and_grads(pos, vis, valid, p)
+    rng = np.random.default_rng(0)
+    for k in ("W", "W_h", "w_It", "b_e"):
+        idx = tuple(rng.integers(0, s) for s in p[k].shape)
+        h = 1e-5
+        pp, pm = {**p, k: p[k].copy()}, {**p, k: p[k].copy()}
+        pp[k][idx] += h
+        pm[k][idx] -= h
+        fd = (o_t.loss_and_grads(pos, vis, valid, pp)[0] - o_t.loss_and_grads(pos, vis, valid, pm)[0]) / (2 * h)
+        assert abs(fd - g[k][idx]) < 1e-6 + 1e-4 * abs(fd), (k, fd, g[k][idx])
