@@ -75,7 +75,7 @@ struct Workspace {
   // bf16-state fast path (non-relational bf16 mode): h, mh, mc bf16 [R,U]; c fp32 [R,U]
   void *hb[2], *mhb, *mcb;
   float* cf[2];
-  bool fast, blocked;   // blocked: tile-blocked state layout (needs 128 % N == 0)
+  bool fast, blocked;   // blocked: tile-blocked state layout (128 % N == 0, or N % 128 == 0: a scene spans whole tiles)
   size_t bytes;
 };
 
@@ -93,7 +93,7 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE) && !cfg->relational;
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
-  w.blocked = w.fast && (128 % cfg->N == 0);
+  w.blocked = w.fast && (128 % cfg->N == 0 || (cfg->N % 128 == 0 && cfg->N <= 1024));
   if (w.fast) {
     const size_t Rp = (R + 127) / 128 * 128;   // state rows padded to whole 128-row tiles
     for (int i = 0; i < 2; ++i) {
@@ -161,7 +161,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
 
   // bf16, non-relational, whole scenes per 128-row tile: the entire recurrence is one persistent kernel with the
   // state on chip (rollout_tc.cu).  MMT_PREC_BF16_STEPWISE keeps the per-step kernels (A/B checks, other N).
-  const bool fused = w.fast && w.blocked && N >= 8 && cfg->prec == MMT_PREC_BF16;
+  const bool fused = w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16;
   if (fused) {
     if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, stream)))
       return rc0;

@@ -346,7 +346,7 @@ def test_forecast_fp32_matches_oracle(cuda, S, N, relational):
     assert np.array_equal(npy(o["best_k"]), best) and np.array_equal(npy(o["best_traj"]), bt)
 
 
-@pytest.mark.parametrize("S,N", [(8, 64), (5, 16), (3, 12), (2, 128), (1, 256), (40, 8), (9, 32)])
+@pytest.mark.parametrize("S,N", [(8, 64), (5, 16), (3, 12), (2, 128), (1, 256), (3, 256), (2, 384), (40, 8), (9, 32)])
 def test_forecast_bf16_tensor_core(cuda, S, N):
     """bf16/tcgen05 mode, stated separately: mean-trajectory error vs the fp32 oracle.  N | 128 takes the
     tile-blocked state layout, other N the row-major bf16 layout; S*N % 128 != 0 exercises the tail tile."""
