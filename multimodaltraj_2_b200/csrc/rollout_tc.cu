@@ -27,6 +27,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "mmt_common.cuh"
 #include "tc_common.cuh"
 
@@ -103,6 +105,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
+// k-chunk of the packed weights / A operand (0 = e, 1-2 = h, 3-4 = mh) consumed at position kcn of a pass
+__device__ __forceinline__ constexpr int ro_perm(int kcn) { return kcn == 0 ? 1 : kcn == 1 ? 2 : kcn == 2 ? 0 : kcn; }
+
 // wait executed by a whole (convergent) warp: reconverge before the next elect.sync
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   mbar_wait(bar, parity);
@@ -119,6 +124,9 @@ __device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
+// DIAG = true compiles the timeline stamps and the timing-experiment flags in (scratch/ro_timeline.py); the production
+// instantiation carries none of it: a few extra instructions per chunk in the MMA-issuing warps cost 2.5 % of the kernel.
+template <bool DIAG>
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   const uint32_t bar0 = sbase + RS_BAR;
   const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * RO_NSTAGE, ACC_FULL = bar0 + 16 * RO_NSTAGE,
                  ACC_EMPTY = ACC_FULL + 16, ATT_READY = ACC_EMPTY + 16, E_READY = ATT_READY + 8,
-                 MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8;
+                 MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8, P0_ISSUED = AGG_FULL + 8;
   float* s_bias = reinterpret_cast<float*>(smem + RS_BIAS);
   float* s_we = reinterpret_cast<float*>(smem + RS_WE);
   float* s_wht = reinterpret_cast<float*>(smem + RS_WHT);
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     mbar_init(E_READY, RO_WWARPS);
     mbar_init(MH_READY, RO_WWARPS);
     mbar_init(AGG_FULL, 1);
+    mbar_init(P0_ISSUED, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == RO_WWARPS) tmem_alloc(sbase + RS_TMEM, 512);
@@ -182,22 +191,26 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     if (lane == 0) {
       int my_tiles = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) ++my_tiles;
-      const uint32_t total = (a.flags & 1) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
+      const uint32_t total = (DIAG && (a.flags & 1)) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
       for (uint32_t it = warp - RO_WWARPS; it < total; it += RO_NPROD) {
-        const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, pk = it % RO_NCH;
-        mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
+        const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, j = it % RO_NCH;
+        if (DIAG && (a.flags & 64)) mbar_wait_spin(W_EMPTY + 8 * s, ph ^ 1u); else mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
         mbar_arrive_expect_tx(W_FULL + 8 * s, RO_STAGE_BYTES);
-        bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)pk * RO_STAGE_BYTES, RO_STAGE_BYTES, W_FULL + 8 * s);
+        bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)(j - j % RO_NKC + ro_perm(j % RO_NKC)) * RO_STAGE_BYTES,
+                 RO_STAGE_BYTES, W_FULL + 8 * s);
       }
     }
   } else if (warp >= RO_WWARPS + RO_NPROD) {
     // =============================== MMA issuers ===============================
     // Issuer 0: aggregation + gate passes 0, 2; issuer 1: gate passes 1, 3.  Two issuing threads reach the
-    // nominal 48 clk per M128 x N96 MMA where one tops out at ~68 (scratch/mma_bench3.cu); passes use different
-    // accumulators, so their MMAs may interleave freely in the tensor pipe.
-    {   // the whole warp runs this code convergently; one elected lane issues each tcgen05 instruction
-      const int me = warp - (RO_WWARPS + RO_NPROD);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // nominal 48 clk per M128 x N96 MMA where one tops out at ~68 (scratch/mma_bench3.cu).  The whole warp runs the
+    // code convergently; one elected lane issues each tcgen05 instruction.  Which issuer a warp is, the pass and the
+    // chunk are compile-time constants of two separate instantiations, so that every MMA operand (descriptors, tensor-
+    // memory addresses, barrier addresses) is warp-uniform to the compiler and lives in uniform registers: with the
+    // issuer index taken from threadIdx at run time each MMA cost ~10 extra instructions (R2UR.BROADCAST per operand).
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    auto issuer = [&](auto me_tag) {
+      constexpr int me = decltype(me_tag)::value;
       uint32_t sc = 0;
       const uint64_t d_att0 = make_desc_sw128(sbase + RS_ATT), d_att1 = make_desc_sw128(sbase + RS_ATT + RO_BLK);
       const uint64_t d_h = make_desc_sw128_mn(sbase + RS_H, RO_BLK, 1024);
@@ -206,12 +219,65 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
         for (int t = 0; t < nsteps; ++t, ++sc) {
           const uint32_t par = sc & 1u;
-          long long* dbg = (a.dbg && blockIdx.x == 0 && lane == 0 && sc < 64) ? a.dbg + sc * 32 + 16 : nullptr;
+          long long* dbg = (DIAG && a.dbg && blockIdx.x == 0 && lane == 0 && sc < 64) ? a.dbg + sc * 32 + 16 : nullptr;
+          const bool timed = DIAG && dbg && (a.flags & 16);
           long long wwait = 0;
-          if (me == 0) {
+          const uint32_t pc0 = sc * RO_NP;
+          // One (pass, k-chunk) of the gate GEMM: wait for its weight stage, 4 MMAs (A = 32 TMEM columns), release the
+          // stage.  j = 5 p + kcn is the chunk's position in the step; chunks are consumed in the order h0 h1 | e | mh0 mh1
+          // (ro_perm): the h part only needs the previous step.  20 chunks per step over 4 stages: the stage is j % 4
+          // and the parity of its use (5 sc + j / 4) & 1.
+          auto gate_chunk = [&](uint32_t d_tmem, auto j_tag) {
+            constexpr int j = decltype(j_tag)::value, kcn = j % RO_NKC;
+            constexpr uint32_t s = j % RO_NSTAGE;
+            static_assert(RO_NCH % RO_NSTAGE == 0, "stage of a chunk must not depend on the step");
+            if (!(DIAG && (a.flags & 1))) {
+              const long long w0 = timed ? clock64() : 0;
+              // no tcgen05.fence here: the stage was written by the async proxy (bulk copy -> mbarrier), not by another
+              // thread's tcgen05 operation; a fence per chunk drained the MMA pipeline (pass 2650 -> see profiles/)
+              if (!(DIAG && (a.flags & 128))) mbar_wait_warp(W_FULL + 8 * s, (sc + (j / RO_NSTAGE)) & 1u);   // 128: timing experiment
+              if (timed) wwait += clock64() - w0;
+            }
+            const uint64_t db = d_w + (uint64_t)((s * RO_STAGE_BYTES) >> 4);
+            const uint32_t acol = tmem_u + RT_A + (uint32_t)ro_perm(kcn) * 32u;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ts_elect(d_tmem, acol + ks * 8, db + (uint64_t)(ks * 2), kIdescGate, (kcn | ks) ? 1u : 0u);
+            if (!(DIAG && (a.flags & 1)) || (a.flags & 256)) umma_commit_elect(W_EMPTY + 8 * s);
+          };
+          auto gate_pass = [&](auto p_tag) {   // passes 1-3: all five chunks back to back
+            constexpr int p = decltype(p_tag)::value;
+            const uint32_t pc = pc0 + p;       // global pass counter: accumulator p & 1, use number pc >> 1
+            constexpr uint32_t b = p & 1u;
+            mbar_wait_warp(ACC_EMPTY + 8 * b, ((pc >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + (b ? RT_ACC1 : RT_ACC0);
+            if (DIAG && dbg) dbg[3 + 2 * p] = clock64();
+            gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 0>{});
+            gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 1>{});
+            gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 2>{});
+            gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 3>{});
+            gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 4>{});
+            umma_commit_elect(ACC_FULL + 8 * b);
+            if (DIAG && dbg) dbg[4 + 2 * p] = clock64();
+          };
+          if constexpr (me == 0) {
+            // ---- pass 0 (accumulator 0, free since the previous step's pass-2 epilogue).  Its h chunks go first, while
+            //      the workers still build the attention: h' of the previous step is in tensor memory once the workers
+            //      have released accumulator 1 after its last pass (on a tile's first step: once E_READY has published
+            //      the zeroed state).
+            const uint32_t d0 = tmem_u + RT_ACC0;
+            mbar_wait_warp(ACC_EMPTY, ((pc0 >> 1) & 1u) ^ 1u);
+            if (t > 0) {
+              mbar_wait_warp(ACC_EMPTY + 8, (((pc0 + 1) >> 1) & 1u) ^ 1u);
+              tc_fence_after();
+              if (DIAG && dbg) dbg[3] = clock64();
+              gate_chunk(d0, std::integral_constant<int, 0>{});
+              gate_chunk(d0, std::integral_constant<int, 1>{});
+            }
             mbar_wait_warp(ATT_READY, par);
             tc_fence_after();
-            if (dbg) dbg[0] = clock64();
+            if (DIAG && dbg) dbg[0] = clock64();
             // ---- aggregation: mh = att x h (committed first: its conversion is on the critical path), mc = att x c
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
@@ -222,50 +288,39 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16_elect(tmem_u + RT_MC, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_c + (uint64_t)(ks * 128),
                         kIdescAggMN, ks ? 1u : 0u);
-            if (dbg) dbg[1] = clock64();
-          }
-          mbar_wait_warp(E_READY, par);
-          if (me == 1) mbar_wait_warp(MH_READY, par);   // accumulator 1 aliases the mh accumulator: wait for its conversion
-          tc_fence_after();
-          if (dbg && me == 0) dbg[2] = clock64();
-          // ---- gate GEMM: passes me, me + 2: 5 k-chunks each, A from tensor memory
-#pragma unroll 1
-          for (int p = me; p < RO_NP; p += RO_NISSUE) {
-            const uint32_t pc = sc * RO_NP + p;      // global pass counter: accumulator p & 1, use number pc >> 1
-            const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
-            mbar_wait_warp(ACC_EMPTY + 8 * b, bph ^ 1u);
+            if (DIAG && dbg) dbg[1] = clock64();
+            mbar_wait_warp(E_READY, par);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_u + (b ? RT_ACC1 : RT_ACC0);
-            if (dbg) dbg[3 + 2 * p] = clock64();
-            uint32_t it = sc * RO_NCH + p * RO_NKC;
-#pragma unroll
-            for (int kc = 0; kc < RO_NKC; ++kc, ++it) {
-              if (p == 0 && kc == 3) {   // the mh chunks of pass 0 wait for the conversion
-                mbar_wait_warp(MH_READY, par);
-                tc_fence_after();
-                if (dbg) dbg[12] = clock64();
-              }
-              const uint32_t s = it % RO_NSTAGE;
-              if (!(a.flags & 1)) {
-                const long long w0 = (dbg && (a.flags & 16)) ? clock64() : 0;
-                // no tcgen05.fence here: the stage was written by the async proxy (bulk copy -> mbarrier), not by another
-                // thread's tcgen05 operation; a fence per chunk drained the MMA pipeline (pass 2650 -> see profiles/)
-                mbar_wait_warp(W_FULL + 8 * s, (it / RO_NSTAGE) & 1u);
-                if (dbg && (a.flags & 16)) wwait += clock64() - w0;
-              }
-              const uint64_t db = d_w + (uint64_t)((s * RO_STAGE_BYTES) >> 4);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_ts_elect(d_tmem, tmem_u + RT_A + kc * 32 + ks * 8, db + (uint64_t)(ks * 2), kIdescGate,
-                             (kc | ks) ? 1u : 0u);
-              if (!(a.flags & 1)) umma_commit_elect(W_EMPTY + 8 * s);
+            if (DIAG && dbg) dbg[2] = clock64();
+            if (t == 0) {
+              if (DIAG && dbg) dbg[3] = clock64();
+              gate_chunk(d0, std::integral_constant<int, 0>{});
+              gate_chunk(d0, std::integral_constant<int, 1>{});
             }
-            umma_commit_elect(ACC_FULL + 8 * b);
-            if (dbg) dbg[4 + 2 * p] = clock64();
+            gate_chunk(d0, std::integral_constant<int, 2>{});
+            mbar_wait_warp(MH_READY, par);   // the mh chunks wait for the conversion
+            tc_fence_after();
+            if (DIAG && dbg) dbg[12] = clock64();
+            gate_chunk(d0, std::integral_constant<int, 3>{});
+            gate_chunk(d0, std::integral_constant<int, 4>{});
+            umma_commit_elect(ACC_FULL);
+            if (DIAG && dbg) dbg[4] = clock64();
+            // pass 1 queues behind pass 0 in the tensor pipe: interleaved, both ran at half rate and accumulator 0,
+            // which the workers wait for first, completed ~1200 clk later
+            if (lane == 0) mbar_arrive(P0_ISSUED);
+            __syncwarp();
+            gate_pass(std::integral_constant<int, 2>{});
+          } else {
+            mbar_wait_warp(MH_READY, par);   // accumulator 1 aliases the mh accumulator: wait for its conversion
+            mbar_wait_warp(P0_ISSUED, par);
+            tc_fence_after();
+            gate_pass(std::integral_constant<int, 1>{});
+            gate_pass(std::integral_constant<int, 3>{});
           }
-          if (dbg) dbg[13 + me] = wwait;
+          if (DIAG && dbg) dbg[13 + me] = wwait;
         }
-    }
+    };
+    if (warp == RO_WWARPS + RO_NPROD) issuer(std::integral_constant<int, 0>{}); else issuer(std::integral_constant<int, 1>{});
   } else {
     // =============================== workers ===============================
     const int q = warp & 3, cs = warp >> 2;
@@ -312,8 +367,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       for (int t = 0; t < nsteps; ++t, ++sc) {
         const uint32_t par = sc & 1u;
         const bool emit = t >= a.T - 1;
-        long long* dbg = (a.dbg && blockIdx.x == 0 && tid == ((a.flags >> 8) & 15) * 32 && sc < 64) ? a.dbg + sc * 32 : nullptr;
-        if (dbg) dbg[0] = clock64();
+        long long* dbg = (DIAG && a.dbg && blockIdx.x == 0 && tid == ((a.flags >> 8) & 15) * 32 && sc < 64) ? a.dbg + sc * 32 : nullptr;
+        if (DIAG && dbg) dbg[0] = clock64();
         // ---- (a) current position and the cell input x = [cur - prev | vislet] of row r
         float2 cur;
         if (t < a.T) {
@@ -385,11 +440,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         fence_proxy_async();   // generic-proxy smem writes (att; h', c' of the previous step) -> async proxy
         tc_fence_before();     // (and the h' tcgen05.st of the previous step, already waited for)
         mbar_arrive_warp(ATT_READY);
-        if (dbg) dbg[1] = clock64();
-        // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Runs while
-        //      the aggregation MMAs execute (placing it before the attention build delayed them: measured +900 clk)
+        if (DIAG && dbg) dbg[1] = clock64();
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
+        const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
+        const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
+        // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Computed while
+        //      the aggregation MMAs execute; no worker barrier between here and MH_READY, so a warp that finishes early
+        //      starts its conversion early (placing e before the attention build delayed the aggregation: +900 clk)
+        uint32_t pe[8];
         {
-          uint32_t pk[8];
 #pragma unroll
           for (int hq = 0; hq < 4; ++hq) {
             const int k = cs * 16 + hq * 4;
@@ -406,28 +466,19 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             e1 = rok ? fmaxf(e1, 0.f) : 0.f;
             e2 = rok ? fmaxf(e2, 0.f) : 0.f;
             e3 = rok ? fmaxf(e3, 0.f) : 0.f;
-            pk[hq * 2] = pack_bf16x2(e0, e1);
-            pk[hq * 2 + 1] = pack_bf16x2(e2, e3);
-          }
-          if (!(a.flags & 32)) {
-            tmem_st8(t_row + RT_A + cs * 8, pk);
-            tmem_wait_st();
+            pe[hq * 2] = pack_bf16x2(e0, e1);
+            pe[hq * 2 + 1] = pack_bf16x2(e2, e3);
           }
         }
-        if (dbg) dbg[15] = clock64();
+        tmem_st8(t_row + RT_A + cs * 8, pe);
+        tmem_wait_st();
         tc_fence_before();
         mbar_arrive_warp(E_READY);
-        if (dbg) dbg[12] = clock64();
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        if (dbg) dbg[10] = clock64();
-        worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
-        const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
-        const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
-        if (dbg) dbg[2] = clock64();
+        if (DIAG && dbg) dbg[2] = clock64();
         // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 32 cs .. +31)
         mbar_wait(AGG_FULL, par);
         tc_fence_after();
-        if (dbg) dbg[3] = clock64();
+        if (DIAG && dbg) dbg[3] = clock64();
 #pragma unroll
         for (int ch = 0; ch < 4; ch += 2) {
           float v0[8], v1[8];
@@ -445,7 +496,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive_warp(MH_READY);
-        if (dbg) dbg[4] = clock64();
+        if (DIAG && dbg) dbg[4] = clock64();
 
         // ---- (e) gate epilogue: 4 passes; this thread: row r, units 32 p + 8 cs .. +7, four at a time
         float2 y2[5];
@@ -453,28 +504,35 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         for (int z = 0; z < 5; ++z) y2[z] = make_float2(0.f, 0.f);
         const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
         const float2 inv2 = make_float2(inv, inv);
+        // Branch-free body (rows of invalid agents compute on zeros and are masked by selects; emitting / observed steps
+        // are two instantiations): one basic block per pass, so the two unit quads of a thread interleave and the
+        // MUFU results of one hide behind the FMAs of the other.
+        auto gate_epilogue = [&](auto emit_tag) {
+          constexpr bool EMIT = decltype(emit_tag)::value;
 #pragma unroll 1
-        for (int p = 0; p < RO_NP; ++p) {
-          const uint32_t pc = sc * RO_NP + p;
-          const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
-          mbar_wait(ACC_FULL + 8 * b, bph);
-          tc_fence_after();
-          if (dbg) dbg[5 + 2 * p] = clock64();
-          const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
-          const int u0 = p * RO_UN + cs * 8;        // first of this thread's 8 units
-          uint32_t hw[4], cw[4];                    // h', c' as bf16 pairs
+          for (int p = 0; p < RO_NP; ++p) {
+            const uint32_t pc = sc * RO_NP + p;
+            const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
+            mbar_wait(ACC_FULL + 8 * b, bph);
+            tc_fence_after();
+            if (DIAG && dbg) dbg[5 + 2 * p] = clock64();
+            const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
+            const int u0 = p * RO_UN + cs * 8;        // first of this thread's 8 units
+            uint32_t hw[4], cw[4];                    // h', c' as bf16 pairs
+            float zi[2][4], zj[2][4], zo[2][4], zm[2][4];
 #pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            const int u = u0 + hq * 4;
-            float zi[4], zj[4], zo[4], zm[4];
-            tmem_ld4(t_acc + hq * 4, zi);
-            tmem_ld4(t_acc + RO_UN + hq * 4, zj);
-            tmem_ld4(t_acc + 2 * RO_UN + hq * 4, zo);
-            tmem_ld4(t_row + RT_MC + u, zm);
-            float4 c4 = *reinterpret_cast<const float4*>(cf_row + (u >> 2) * 2048);
+            for (int hq = 0; hq < 2; ++hq) {
+              tmem_ld4(t_acc + hq * 4, zi[hq]);
+              tmem_ld4(t_acc + RO_UN + hq * 4, zj[hq]);
+              tmem_ld4(t_acc + 2 * RO_UN + hq * 4, zo[hq]);
+              tmem_ld4(t_row + RT_MC + u0 + hq * 4, zm[hq]);
+            }
             tmem_wait_ld();
-            float ho[4] = {0.f, 0.f, 0.f, 0.f}, fo[4] = {0.f, 0.f, 0.f, 0.f};
-            if (v) {
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const int u = u0 + hq * 4;
+              float4 c4 = *reinterpret_cast<const float4*>(cf_row + (u >> 2) * 2048);
+              float ho[4], fo[4];
               const float4 bI = *reinterpret_cast<const float4*>(s_bias + u);
               const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + u);
               const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + u);
@@ -491,29 +549,31 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                 //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
                 //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
                 const float2 c2 = sel(c4);
-                const float2 m2 = fmul2(make_float2(zm[i0], zm[i0 + 1]), inv2);
-                const float2 t1 = ffma2(sel(pIf), m2, make_float2(zi[i0], zi[i0 + 1]));
+                const float2 m2 = fmul2(make_float2(zm[hq][i0], zm[hq][i0 + 1]), inv2);
+                const float2 t1 = ffma2(sel(pIf), m2, make_float2(zi[hq][i0], zi[hq][i0 + 1]));
                 const float2 t2 = ffma2(sel(pIt), c2, sel(bI));
                 const float2 th = tanh2(fadd2(t1, t2));
-                const float2 tj = tanh2(fadd2(make_float2(zj[i0], zj[i0 + 1]), sel(bJ)));
+                const float2 tj = tanh2(fadd2(make_float2(zj[hq][i0], zj[hq][i0 + 1]), sel(bJ)));
                 const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
                 const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
                 const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
-                const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[i0], zo[i0 + 1]), sel(bO)));
+                const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[hq][i0], zo[hq][i0 + 1]), sel(bO)));
                 const float2 to = tanh2(ffma2(sel(pOt), ct, o1));
                 const float2 ha = fmul2(tanh2(ct), kHalf);
                 const float2 h2 = ffma2(to, ha, ha);
-                ho[i0] = h2.x; ho[i0 + 1] = h2.y;
-                if (pr) { c4.z = ct.x; c4.w = ct.y; } else { c4.x = ct.x; c4.y = ct.y; }
-                if (emit) {
+                ho[i0] = v ? h2.x : 0.f; ho[i0 + 1] = v ? h2.y : 0.f;
+                const float2 cn = make_float2(v ? ct.x : 0.f, v ? ct.y : 0.f);
+                if (pr) { c4.z = cn.x; c4.w = cn.y; } else { c4.x = cn.x; c4.y = cn.y; }
+                if constexpr (EMIT) {
                   const float2 fa = fmul2(tanh2(cf), kHalf);
                   const float2 f2 = ffma2(to, fa, fa);
                   fo[i0] = f2.x; fo[i0 + 1] = f2.y;
                 }
               }
               *reinterpret_cast<float4*>(cf_row + (u >> 2) * 2048) = c4;
-              if (emit) {
+              if constexpr (EMIT) {
                 // head partial sums, two units per packed FMA: y2[z] += (v_u, v_u+1) * (W_hT[z][u], W_hT[z][u+1])
+                // (rows of invalid agents accumulate values nobody reads)
 #pragma unroll
                 for (int hsrc = 0; hsrc < 2; ++hsrc) {
                   const float2 va = hsrc ? make_float2(fo[0], fo[1]) : make_float2(ho[0], ho[1]);
@@ -526,37 +586,38 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                   }
                 }
               }
+              hw[hq * 2] = pack_bf16x2(ho[0], ho[1]);
+              hw[hq * 2 + 1] = pack_bf16x2(ho[2], ho[3]);
+              cw[hq * 2] = pack_bf16x2(c4.x, c4.y);
+              cw[hq * 2 + 1] = pack_bf16x2(c4.z, c4.w);
             }
-            hw[hq * 2] = pack_bf16x2(ho[0], ho[1]);
-            hw[hq * 2 + 1] = pack_bf16x2(ho[2], ho[3]);
-            cw[hq * 2] = pack_bf16x2(c4.x, c4.y);
-            cw[hq * 2 + 1] = pack_bf16x2(c4.z, c4.w);
-          }
-          if (v) {
-            // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
-            // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass)
-            const uint32_t so = (u0 >> 6) * RO_BLK + r * 128 + ((((u0 & 63) >> 3) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(smem + RS_C + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-            *reinterpret_cast<uint4*>(smem + RS_H + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          }
-          if (p == RO_NP - 1) {
-            // every gate MMA of this step has completed (ACC_FULL of the last pass): the h columns of the TMEM A
-            // operand may be overwritten.  Each thread re-reads the 4 x 8 units it stored (its own writes; rows of
-            // invalid agents stay zero) and copies them: units u, u+1 -> column u/2.
+            {
+              // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
+              // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass); zeros for invalid rows
+              const uint32_t so = (u0 >> 6) * RO_BLK + r * 128 + ((((u0 & 63) >> 3) ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(smem + RS_C + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+              *reinterpret_cast<uint4*>(smem + RS_H + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            }
+            if (p == RO_NP - 1) {
+              // every gate MMA of this step has completed (ACC_FULL of the last pass): the h columns of the TMEM A
+              // operand may be overwritten.  Each thread re-reads the 4 x 8 units it stored (its own writes) and
+              // copies them: units u, u+1 -> column u/2.
 #pragma unroll
-            for (int pp = 0; pp < RO_NP; ++pp) {
-              const int u = pp * RO_UN + cs * 8;
-              const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
-                                                               ((((u & 63) >> 3) ^ (r & 7)) << 4));
-              const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
-              tmem_st4(t_row + RT_A_H + pp * 16 + cs * 4, w4);
+              for (int pp = 0; pp < RO_NP; ++pp) {
+                const int u = pp * RO_UN + cs * 8;
+                const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
+                                                                 ((((u & 63) >> 3) ^ (r & 7)) << 4));
+                const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+                tmem_st4(t_row + RT_A_H + pp * 16 + cs * 4, w4);
+              }
+              tmem_wait_st();
             }
-            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive_warp(ACC_EMPTY + 8 * b);
           }
-          tc_fence_before();
-          mbar_arrive_warp(ACC_EMPTY + 8 * b);
-        }
-        if (dbg) dbg[13] = clock64();
+        };
+        if (emit) gate_epilogue(std::true_type{}); else gate_epilogue(std::false_type{});
+        if (DIAG && dbg) dbg[13] = clock64();
         // ---- (f) head: combine the four column slices of each row, emit the 5 parameters and the next position
         if (emit) {
           {
@@ -595,7 +656,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           }
           worker_sync();
         }
-        if (dbg) dbg[14] = clock64();
+        if (DIAG && dbg) dbg[14] = clock64();
       }
     }
   }
@@ -619,11 +680,16 @@ int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, 
   a.flags = getenv("MMT_RO_FLAGS") ? atoi(getenv("MMT_RO_FLAGS")) : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(rollout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
+    cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
+    cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
     attr_set = true;
   }
-  const int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  rollout_tc_kernel<<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
+  if (getenv("MMT_RO_GRID") && atoi(getenv("MMT_RO_GRID")) > 0 && atoi(getenv("MMT_RO_GRID")) < grid) grid = atoi(getenv("MMT_RO_GRID"));   // diagnostics
+  if (a.dbg || a.flags)
+    rollout_tc_kernel<true><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  else
+    rollout_tc_kernel<false><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
   count_launch();
   return check_launch("rollout_tc_kernel");
 }

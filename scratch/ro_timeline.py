@@ -26,10 +26,6 @@ for s in range(24):
     m = r[16:]
     order = [0, 1, 2, 3, 12, 4, 5, 6, 7, 8, 9, 10]
     print(f'{s:4d} ' + ' '.join(f'{m[k] - r[0]:7d}' for k in order) + f' | Wwait {m[13]:5d} {m[14]:5d} |   worker: att_arr {r[1]-r[0]} mh_arr {r[4]-r[0]} acc0 {r[5]-r[0]} acc1 {r[7]-r[0]} acc2 {r[9]-r[0]} acc3 {r[11]-r[0]} end {r[14]-r[0]}')
-print('E phase detail: e_build(+st wait)  arrive  cpasync_wait  sync+sum')
-for s_ in range(4, 12):
-    r = t[s_]
-    print(f'{s_:4d} {r[15]-r[1]:8d} {r[12]-r[15]:8d} {r[10]-r[12]:8d} {r[2]-r[10]:8d}')
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(3): ops.rollout_bf16(pos, vis, valid, p, out=out)
 torch.cuda.synchronize()
