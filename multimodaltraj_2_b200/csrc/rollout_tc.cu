@@ -128,8 +128,11 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" 
 // instantiation carries none of it: a few extra instructions per chunk in the MMA-issuing warps cost 2.5 % of the kernel.
 template <bool DIAG>
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  // 1024-byte alignment (SWIZZLE_128B atoms) requested from the toolchain instead of fixed up at run time: the base is
+  // then a link-time constant and every barrier address / UMMA descriptor derived from it is uniform
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* const smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + RS_BAR;
