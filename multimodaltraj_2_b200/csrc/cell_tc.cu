@@ -80,9 +80,11 @@ __host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  //
 template <int LAY>
 __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
   constexpr bool BF = LAY != 0;
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  // SWIZZLE_128B atoms need a 1024-byte aligned base; the launch adds 1 KB of slack for this
-  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  // SWIZZLE_128B atoms need a 1024-byte aligned base: requested from the toolchain, so that the base is a link-time
+  // constant and the barrier addresses / descriptors derived from it are uniform
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* const smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR;

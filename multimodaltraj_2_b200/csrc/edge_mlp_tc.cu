@@ -48,8 +48,9 @@ constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
 __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
                                                               const uint8_t* __restrict__ Wp, float* __restrict__ out,
                                                               int num_tiles) {
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
+  uint8_t* const smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_w = sbase + NP_SM_BAR, bar_mma = bar_w + 8;
@@ -145,8 +146,9 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __rest
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
                                                              const float* __restrict__ w_out, const float* __restrict__ b_out,
                                                              int S, int N, float* __restrict__ score, int zero_fill) {
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
+  uint8_t* const smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_w = sbase + EE_SM_BAR, bar_mma = bar_w + 8;

@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
     const float* __restrict__ c, int R, int N, float r2, float neg_inv_log2e, __nv_bfloat16* __restrict__ mhb,
     __nv_bfloat16* __restrict__ mcb, int num_tiles) {
-  extern __shared__ __align__(16) uint8_t smem_dyn[];
-  uint8_t* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
+  uint8_t* const smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float2* spos = reinterpret_cast<float2*>(smem + GM_SM_POS);
