@@ -411,7 +411,7 @@ def run_train(args, rank, world, local_rank):
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
     pos, vis, valid = (torch.from_numpy(a).to(dev) for a in (pos_h, vis_h, valid_h))
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
-    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2)
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm)   # lr 0.005 (argParser.py:40) diverges on this synthetic set
 
     def barrier():
         if world > 1:
@@ -445,8 +445,11 @@ def run_train(args, rank, world, local_rank):
         print(json.dumps({"mode": "train", "metric": "agent-trajectories/sec (training step: teacher-forced NLL + BPTT + gradient all-reduce + RMSProp)",
                           "value": int(valid_h.sum()) * world / (ms_step * 1e-3), "unit": "agent-trajectories/s", "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32" if args.train_gemm == "fp32" else "f32 kernels, tf32 tensor-core GEMMs in the backward (fp32 accumulation)",
+                          "data": "synthetic",
                           "config": {"workload": f"{S} scenes x {N} agents per GPU, obs {T_OBS} / pred {P_PRED}, g2k_lstm_mc training step",
+                                     "backward_gemm": args.train_gemm, "lr": 1e-3,
                                      "gradient_bucket_bytes": int(w.numel() * 4), "collective": "one NCCL all-reduce (SUM) per step" if world > 1 else "none (1 GPU)"},
                           "loss_first": losses[0], "loss_last": float(loss), "weights_identical_across_ranks": in_sync,
                           "gpu_launches": int(ops.launch_count() - l0)}), flush=True)
@@ -466,6 +469,7 @@ def main():
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly (no CUDA graph)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
+    ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32"], help="--mode train: arithmetic of the backward GEMMs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -119,7 +119,13 @@ class Trainer:
     """
 
     def __init__(self, params: ops.CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, lr=0.005, decay=0.95,
-                 clip=10.0):
+                 clip=10.0, gemm="fp32"):
+        # gemm: arithmetic of the library contractions of the backward pass (A^T dz, dz W^T, att^T d mh, head):
+        #   "fp32" CUDA-core SGEMM (parity mode: gradients within 2e-3 of the fp64 autograd oracle),
+        #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2).
+        if gemm not in ("fp32", "tf32"):
+            raise ValueError("gemm must be 'fp32' or 'tf32'")
+        self.gemm = gemm
         self.p, self.T, self.P, self.r2, self.inv = params, T, P, r2, inv_2sigma2
         self.lam, self.lr, self.decay, self.clip = lam, lr, decay, clip
         self.ms = {k: torch.zeros_like(getattr(params, k)) for k in TRAIN_KEYS}
@@ -154,6 +160,17 @@ class Trainer:
             saved.append(rec)
             h, c = hn.view(S, N, U), cn.view(S, N, U)
         # ---- back-propagation through time
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.gemm == "tf32"
+        try:
+            return self._backward(saved, loss_sum, valid, vflat, S, N)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32_was
+
+    def _backward(self, saved, loss_sum, valid, vflat, S, N):
+        p, T, P = self.p, self.T, self.P
+        R, U, E = S * N, p.U, p.E
+        dev = vflat.device
         g = {k: torch.zeros_like(getattr(p, k)) for k in TRAIN_KEYS}
         dpeep = torch.zeros((4, U), device=dev)
         Gh = torch.zeros((R, U), device=dev)
