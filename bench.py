@@ -24,6 +24,10 @@ from pathlib import Path
 
 import numpy as np
 
+# rank 0 prints ONE JSON line on stdout: NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version line there too
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
