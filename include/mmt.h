@@ -169,6 +169,24 @@ int mmt_mean_error_f32(const float* predicted, const float* truth, int n, int L,
 int mmt_train_val_scores_f32(const float* pred, const float* tgt, const int32_t* len, int n, int P,
                              int n_targets, float* euc, float* err, void* stream);
 
+/* ADE / FDE in metres (data/eth/univ/getPixelCoordinates.m:8-30): positions are pixel coordinates
+ * divided by (scale0, scale1) = (480, 640); world = Hm [pos0*scale0, pos1*scale1, 1]^T, divided by its third
+ * component.  pred/gt [n,P,2], valid[n] u8 or NULL, Hm[9] row-major (device).  ade[n], fde[n] (0 for invalid
+ * agents); sums[3] or NULL = (sum ade, sum fde, number of valid agents). */
+int mmt_ade_fde_world_f32(const float* pred, const float* gt, const uint8_t* valid, int n, int P, const float* Hm,
+                          float scale0, float scale1, float* ade, float* fde, float* sums, void* stream);
+
+/* ---- static-context branch ------------------------------------------------------------
+ * Replaces train.py:93-110 (scene image x one huge random filter -> _2dconv[D,D]) and train.py:154-158
+ * (stat_mask, _2dconv_in = _2dconv x stat_mask -> the ngh[D,T] input of g2k_lstm_mc(r)).
+ * img[H,W,C] f32; the image is zero-padded by one row on top and bottom and one column on the right
+ * (train.py:97-99); filt[FH,FW,C] with FH = H+2-D+1, FW = W+1-D+1 (the reference draws it unseeded, so it is an
+ * input); conv[D,D] = lam * VALID-correlation; ngh[D,T][i,t] = (sum_j conv[i,j]) * t/T.
+ * Workspace: mmt_static_context_workspace_bytes(H, D). */
+size_t mmt_static_context_workspace_bytes(int H, int D);
+int mmt_static_context_f32(const float* img, int H, int W, int C, const float* filt, int D, int T, float lam,
+                           float* conv, float* ngh, void* workspace, size_t workspace_bytes, void* stream);
+
 /* nri_learned.infer_rlns (sigmoid, nri_learned.py:16-21) and eval_rln_ngh (row softmax, :23-28) */
 int mmt_sigmoid_f32(const float* x, float* y, size_t n, void* stream);
 int mmt_rowsoftmax_f32(const float* x, float* y, int rows, int cols, void* stream);

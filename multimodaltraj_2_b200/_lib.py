@@ -62,6 +62,10 @@ SIGNATURES = {
                                       C.c_float, C.c_int, vp, vp, vp, vp]),
     "mmt_mean_error_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "mmt_train_val_scores_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "mmt_ade_fde_world_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]),
+    "mmt_static_context_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mmt_static_context_f32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp,
+                                         C.c_size_t, vp]),
     "mmt_sigmoid_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "mmt_rowsoftmax_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
     "mmt_decode_score_f32": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_int, C.c_int, C.c_int,

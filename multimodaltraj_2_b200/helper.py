@@ -85,3 +85,19 @@ class neighborhood_stat_enc():
             self.input.contiguous(), self.hidden_state.contiguous(), w["W_f"], w["B_f"], w["w_If"], w["w_It"],
             w["w_Of"], w["w_Ot"], self.U, self.F, False)
         return self.output, self.c_hidden_states
+
+
+def static_context(ctxt_img, dim, obs_len, lambda_param, filt=None, seed=0, device="cuda"):
+    """Static-context branch of train.py:93-110,154-158 on the device (``mmt_static_context_f32``): the scene image
+    (``imread('ctxt.png')``, [H,W,3]) correlated with one [H+3-dim, W+2-dim, 3] filter -> ``_2dconv[dim,dim]`` scaled by
+    ``lambda_param``, and ``_2dconv_in = _2dconv x stat_mask`` -> the ``ngh[dim, obs_len]`` fed to the model.
+    The reference draws the filter with an unseeded ``tf.random_normal``; here it is an argument, or drawn from numpy's
+    Philox generator with ``seed`` so that runs are reproducible.  Returns (_2dconv, _2dconv_in) as CUDA tensors."""
+    import numpy as np
+    img = torch.as_tensor(np.asarray(ctxt_img, np.float32)).to(device).contiguous()
+    H, W, C = img.shape
+    if filt is None:
+        g = np.random.Generator(np.random.Philox(seed))
+        filt = g.standard_normal((H + 3 - dim, W + 2 - dim, C)).astype(np.float32)
+    filt = torch.as_tensor(np.asarray(filt, np.float32)).to(device).contiguous()
+    return ops.static_context(img, filt, int(dim), int(obs_len), float(lambda_param))

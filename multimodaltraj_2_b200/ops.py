@@ -416,6 +416,40 @@ def train_val_scores(pred, tgt, lens, n_targets):
     return euc, err
 
 
+def ade_fde_world(pred, gt, H, valid=None, scale=(480.0, 640.0)):
+    """ADE / FDE in metres (mmt_ade_fde_world_f32; data/eth/univ/getPixelCoordinates.m:8-30): pred/gt [n,P,2] in the
+    data files' normalised pixel units, H[3,3] pixel -> world.  Returns (ade[n], fde[n], sums[3] = (sum ade, sum fde,
+    number of valid agents))."""
+    lib = _lib.load()
+    _chk(pred, torch.float32, "pred"); _chk(gt, torch.float32, "gt"); _chk(H, torch.float32, "H")
+    if valid is not None:
+        _chk(valid, torch.uint8, "valid")
+    n, P, _ = pred.shape
+    ade = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    fde = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    sums = torch.empty((3,), dtype=torch.float32, device=pred.device)
+    _lib.check(lib.mmt_ade_fde_world_f32(_p(pred), _p(gt), _p(valid), n, P, _p(H), float(scale[0]), float(scale[1]),
+                                         _p(ade), _p(fde), _p(sums), _stream()), "mmt_ade_fde_world_f32")
+    return ade, fde, sums
+
+
+def static_context(img, filt, D, T, lam):
+    """Static-context branch (mmt_static_context_f32; train.py:93-110,154-158): img[H,W,C], filt[H+3-D, W+2-D, C]
+    -> (_2dconv[D,D], _2dconv_in = ngh[D,T])."""
+    lib = _lib.load()
+    _chk(img, torch.float32, "img"); _chk(filt, torch.float32, "filt")
+    H, W, C = img.shape
+    if tuple(filt.shape) != (H + 3 - D, W + 2 - D, C):
+        raise ValueError(f"filt must be [{H + 3 - D}, {W + 2 - D}, {C}], got {tuple(filt.shape)}")
+    conv = torch.empty((D, D), dtype=torch.float32, device=img.device)
+    ngh = torch.empty((D, T), dtype=torch.float32, device=img.device)
+    nbytes = lib.mmt_static_context_workspace_bytes(H, D)
+    ws = torch.empty((max(nbytes, 16) // 4,), dtype=torch.float32, device=img.device)
+    _lib.check(lib.mmt_static_context_f32(_p(img), H, W, C, _p(filt), D, T, float(lam), _p(conv), _p(ngh), _p(ws),
+                                          ws.numel() * 4, _stream()), "mmt_static_context_f32")
+    return conv, ngh
+
+
 def sigmoid(x):
     lib = _lib.load()
     _chk(x, torch.float32, "x")

@@ -80,3 +80,21 @@ def standard_best_of_k(samples, gt, valid=None):
     fde = d[..., P - 1]
     best = np.argmin(ade, axis=-1).astype(np.int32)     # first minimum = lowest k
     return ade, fde, best
+
+
+def ade_fde_world(pred, gt, H, valid=None, scale=(480.0, 640.0)):
+    """ADE / FDE in metres: data/eth/univ/getPixelCoordinates.m:8-30 run backwards (the files hold
+    pinv(H) * world, rows divided by 480 and 640): world = H [p0*480, p1*640, 1]^T / third component.
+    pred/gt [n,P,2] -> (ade[n], fde[n]) in fp64; invalid agents score 0."""
+    pred, gt, H = np.asarray(pred, np.float64), np.asarray(gt, np.float64), np.asarray(H, np.float64)
+
+    def world(q):
+        p = np.stack([q[..., 0] * scale[0], q[..., 1] * scale[1], np.ones(q.shape[:-1])], -1)
+        w = p @ H.T
+        return w[..., :2] / w[..., 2:3]
+    d = np.linalg.norm(world(pred) - world(gt), axis=-1)
+    ade, fde = d.mean(-1), d[:, -1]
+    if valid is not None:
+        v = np.asarray(valid).astype(bool)
+        ade, fde = np.where(v, ade, 0.0), np.where(v, fde, 0.0)
+    return ade, fde

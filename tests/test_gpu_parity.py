@@ -505,3 +505,70 @@ def test_train_step_rmsprop_and_loss_decrease(cuda):
         assert np.abs(npy(getattr(cp, k)) - want_p[k]).max() < 1e-5, k
     losses = [l0] + [float(tr.step(*d)) for _ in range(6)]
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+# ------------------------------------------------------------------------------------------------
+# static-context branch (train.py:93-110,154-158)
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,D", [(40, 50, 16), (23, 31, 10), (16, 15, 16)])
+def test_static_context_matches_oracle(cuda, H, W, D):
+    import static_ctx as o_ctx
+    T, lam, C = 8, 0.0005, 3
+    rng = np.random.default_rng(H)
+    img = rng.integers(0, 256, (H, W, C)).astype(np.float32)
+    filt = o_ctx.seeded_filter(H, W, C, D, seed=1)
+    want_conv, want_ngh = o_ctx.static_context(img, filt, D, T, lam)
+    conv, ngh = ops.static_context(dev(img, cuda), dev(filt, cuda), D, T, lam)
+    assert rel_err(npy(conv).astype(np.float64), want_conv) < 1e-4       # fp32 FMA chains vs fp64, relative to max |conv|
+    assert rel_err(npy(ngh).astype(np.float64), want_ngh) < 1e-4
+    assert np.all(npy(ngh)[:, 0] == 0)
+
+
+@pytest.mark.gpu
+def test_static_context_full_size_impulse_and_mirror(cuda):
+    """At the reference's image size (576 x 720 x 3, D = 16: filter 563 x 706 x 3) the oracle is not run: the response
+    to unit impulses is the filter itself, tap for tap (bit-exact: every other product is an exact zero)."""
+    import static_ctx as o_ctx
+    from multimodaltraj_2_b200 import helper
+    H, W, C, D, T, lam = 576, 720, 3, 16, 8, 1.0
+    filt = o_ctx.seeded_filter(H, W, C, D, seed=0)
+    FH, FW = H + 3 - D, W + 2 - D
+    for (y, x, c) in [(0, 0, 0), (300, 411, 2), (H - 1, W - 1, 1)]:
+        img = np.zeros((H, W, C), np.float32)
+        img[y, x, c] = 1.0
+        conv, ngh = helper.static_context(img, D, T, lam, filt=filt)
+        want = np.zeros((D, D), np.float32)
+        for i in range(D):
+            for j in range(D):
+                a, b = y + 1 - i, x - j
+                if 0 <= a < FH and 0 <= b < FW:
+                    want[i, j] = filt[a, b, c]
+        assert np.array_equal(npy(conv), want)
+    # seeded mirror: same seed -> same result, and linear in the image
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (H, W, C)).astype(np.float32)
+    c1, _ = helper.static_context(a, D, T, 0.0005, seed=7)
+    c2, _ = helper.static_context(a, D, T, 0.0005, seed=7)
+    c3, _ = helper.static_context(2 * a, D, T, 0.0005, seed=7)
+    assert torch.equal(c1, c2)
+    assert rel_err(npy(c3).astype(np.float64), 2 * npy(c1).astype(np.float64)) < 1e-6
+
+
+# SURVEY 8f rank 4: ADE / FDE in metres through the homography (data/eth/univ/getPixelCoordinates.m:8-30)
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,P", [(1, 12), (257, 12), (64, 40)])
+def test_ade_fde_world_matches_oracle(cuda, n, P):
+    import scores as o_sc
+    rng = np.random.default_rng(n + P)
+    pred = rng.uniform(0, 1, (n, P, 2)).astype(np.float32)
+    gt = (pred + rng.normal(0, 0.02, (n, P, 2))).astype(np.float32)
+    valid = (rng.uniform(size=n) > 0.2).astype(np.uint8)
+    Hm = np.array([[0.028, 0.002, -3.1], [-0.001, 0.023, -2.2], [0.0003, -0.0001, 1.0]], np.float32)   # ETH-like scale
+    wa, wf = o_sc.ade_fde_world(pred, gt, Hm, valid)
+    ade, fde, sums = ops.ade_fde_world(dev(pred, cuda), dev(gt, cuda), dev(Hm, cuda), dev(valid, cuda))
+    np.testing.assert_allclose(npy(ade), wa, rtol=2e-4, atol=1e-5)     # metres; the bar is 1e-3 m
+    np.testing.assert_allclose(npy(fde), wf, rtol=2e-4, atol=1e-5)
+    s = npy(sums)
+    assert abs(s[0] - wa.sum()) < 1e-3 * max(1, n) and abs(s[1] - wf.sum()) < 1e-3 * max(1, n) and s[2] == valid.sum()
+    ade2, _, s2 = ops.ade_fde_world(dev(pred, cuda), dev(gt, cuda), dev(Hm, cuda))          # valid = NULL: every agent
+    assert s2[2].item() == n and np.all(npy(ade2)[valid == 0] > 0)

@@ -150,3 +150,51 @@ def test_track_b_invariants():
     lo = o_b.forecast_scene_loop(pos, vis, valid, p, eps, T=T, P=P, relational=True)
     assert np.array_equal(lo["best_k"], o["best_k"])
     np.testing.assert_allclose(lo["params"], o["params"], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# static-context branch and metric (world-coordinate) scores -- oracle identities
+def test_static_context_oracle_impulse_and_linearity():
+    import static_ctx as o_ctx
+    H, W, C, D, T, lam = 20, 26, 3, 10, 8, 0.0005
+    filt = o_ctx.seeded_filter(H, W, C, D, seed=3).astype(np.float64)
+    FH, FW = H + 3 - D, W + 2 - D
+    # a single 1 at image (y, x, c): conv[i, j] = lam * filt[y + 1 - i, x - j, c] wherever that tap exists (train.py:97-109:
+    # one zero row above the image, none on the left, VALID correlation)
+    for (y, x, c) in [(0, 0, 0), (7, 11, 2), (H - 1, W - 1, 1)]:
+        img = np.zeros((H, W, C))
+        img[y, x, c] = 1.0
+        conv, ngh = o_ctx.static_context(img, filt, D, T, lam)
+        want = np.zeros((D, D))
+        for i in range(D):
+            for j in range(D):
+                a, b = y + 1 - i, x - j
+                if 0 <= a < FH and 0 <= b < FW:
+                    want[i, j] = lam * filt[a, b, c]
+        np.testing.assert_allclose(conv, want, rtol=0, atol=1e-15)
+        # stat_mask rows are range(0, 1, 1/T) (train.py:154-155): column t of ngh is the row sum of conv times t/T
+        np.testing.assert_allclose(ngh, conv.sum(1, keepdims=True) * (np.arange(T) / T)[None], rtol=1e-12, atol=1e-15)
+        assert np.all(ngh[:, 0] == 0)
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(0, 255, (H, W, C)), rng.uniform(0, 255, (H, W, C))
+    ca, cb, cab = (o_ctx.static_context(m, filt, D, T, lam)[0] for m in (a, b, a + 2 * b))
+    np.testing.assert_allclose(cab, ca + 2 * cb, rtol=1e-10, atol=1e-9)
+
+
+def test_ade_fde_world_oracle_identities():
+    rng = np.random.default_rng(1)
+    n, P = 7, 12
+    pred, gt = rng.uniform(0, 1, (n, P, 2)), rng.uniform(0, 1, (n, P, 2))
+    # H = diag(1/480, 1/640, 1) undoes the scaling: metres == the file's normalised units
+    ade, fde = o_sc.ade_fde_world(pred, gt, np.diag([1 / 480.0, 1 / 640.0, 1.0]))
+    d = np.linalg.norm(pred - gt, axis=-1)
+    np.testing.assert_allclose(ade, d.mean(1), rtol=1e-12)
+    np.testing.assert_allclose(fde, d[:, -1], rtol=1e-12)
+    # a similarity transform scales every error by its factor; the projective row changes the depth division
+    s, th = 0.021, 0.3
+    Hs = np.array([[s * np.cos(th), -s * np.sin(th), 3.0], [s * np.sin(th), s * np.cos(th), -1.0], [0, 0, 1.0]])
+    ade2, _ = o_sc.ade_fde_world(pred / [480.0, 640.0], gt / [480.0, 640.0], Hs)
+    np.testing.assert_allclose(ade2, s * d.mean(1), rtol=1e-10)
+    valid = np.array([1, 0, 1, 1, 0, 1, 1], np.uint8)
+    ade3, fde3 = o_sc.ade_fde_world(pred, gt, Hs, valid)
+    assert np.all(ade3[valid == 0] == 0) and np.all(fde3[valid == 0] == 0)
