@@ -262,6 +262,13 @@ int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, c
                      int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
                      int64_t* timeline, void* stream);
 
+/* Forward gate update from pre-activations z[R,3U] = [e|h|mh] W + b (columns i | j | o) computed by a library GEMM:
+ * the gate equations of helper.py:31-39 -> h'[R,U], c'[R,U], m_f[R,U]; invalid rows give zeros.  Used by
+ * the training forward (Trainer), which keeps z for mmt_gsk_cell_backward_f32 instead of recomputing it. */
+int mmt_gsk_gates_f32(const float* z, const float* c, const float* mc, const uint8_t* valid, const float* w_If,
+                      const float* w_It, const float* w_Of, const float* w_Ot, int R, int U, float* h_out,
+                      float* c_out, float* mf_out, void* stream);
+
 /* ---- training step (SURVEY App. C.5 "Training loss (fills F2)", section 8e) ------------------------------------
  * The reference has no loss / optimiser (train.py:23-366 logs raw errors); the loss defined for it is the teacher-
  * forced mean bivariate-Gaussian NLL of the next displacement.  These two kernels are the element-wise work of one

@@ -78,6 +78,7 @@ SIGNATURES = {
     "mmt_forecast_f32": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.POINTER(EdgeWeights),
                                    C.POINTER(ForecastCfg), vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]),
     "mmt_head_nll_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
+    "mmt_gsk_gates_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "mmt_gsk_cell_backward_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp,
                                             vp]),
     "mmt_rollout_bf16": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -5,6 +5,8 @@
 // are plain library GEMMs.
 //
 //   mmt_head_nll_f32            y = [m_t | m_f] W_h + b_h ; nll(y, target) ; dy = d nll / d y          (warp per row)
+//   mmt_gsk_gates_f32           forward gate update from pre-activations z = [e|h|mh] W + b computed by a library GEMM:
+//                               h', c', m_f (the training forward keeps z for the backward instead of recomputing it)
 //   mmt_gsk_cell_backward_f32   gates re-evaluated from the saved pre-activations z, then d z, d c, d mc and the
 //                               peephole gradients (block-reduced, one atomicAdd per unit and block)
 #include "mmt_common.cuh"
@@ -53,6 +55,47 @@ __global__ void __launch_bounds__(256) head_nll_kernel(const float* __restrict__
     if (t != 0.f) atomicAdd(loss_sum, t);
   }
 }
+
+// forward gate update of helper.py:31-39 from the pre-activations: thread = 4 consecutive units of a row
+__global__ void __launch_bounds__(256) gsk_gates_kernel(const float* __restrict__ z, const float* __restrict__ c,
+                                                        const float* __restrict__ mc, const uint8_t* __restrict__ valid,
+                                                        const float* __restrict__ w_If, const float* __restrict__ w_It,
+                                                        const float* __restrict__ w_Of, const float* __restrict__ w_Ot,
+                                                        int R, int U, float* __restrict__ h_out, float* __restrict__ c_out,
+                                                        float* __restrict__ mf_out) {
+  const int U4 = U >> 2;
+  const long total = (long)R * U4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / U4), u = (int)(i - (long)r * U4) * 4;
+    const size_t o = (size_t)r * U + u, oz = (size_t)r * 3 * U + u;
+    float4 ho = make_float4(0.f, 0.f, 0.f, 0.f), co = ho, fo = ho;
+    if (valid[r]) {
+      const float4 zi = *reinterpret_cast<const float4*>(z + oz), zj = *reinterpret_cast<const float4*>(z + oz + U),
+                   zo = *reinterpret_cast<const float4*>(z + oz + 2 * U);
+      const float4 cp = *reinterpret_cast<const float4*>(c + o), m = *reinterpret_cast<const float4*>(mc + o);
+      const float4 pIf = *reinterpret_cast<const float4*>(w_If + u), pIt = *reinterpret_cast<const float4*>(w_It + u),
+                   pOf = *reinterpret_cast<const float4*>(w_Of + u), pOt = *reinterpret_cast<const float4*>(w_Ot + u);
+      auto one = [](float zi_, float zj_, float zo_, float cp_, float m_, float pIf_, float pIt_, float pOf_, float pOt_,
+                    float& h_, float& c_, float& f_) {
+        const float g = sigmoid_acc(zi_ + pIf_ * m_ + pIt_ * cp_);
+        const float tj = tanhf(zj_);
+        const float cf = (1.f - g) * m_ + g * tj, ct = (1.f - g) * cp_ + g * tj;
+        const float q = sigmoid_acc(zo_ + pOf_ * cf + pOt_ * ct);
+        h_ = q * tanhf(ct);
+        c_ = ct;
+        f_ = q * tanhf(cf);
+      };
+      one(zi.x, zj.x, zo.x, cp.x, m.x, pIf.x, pIt.x, pOf.x, pOt.x, ho.x, co.x, fo.x);
+      one(zi.y, zj.y, zo.y, cp.y, m.y, pIf.y, pIt.y, pOf.y, pOt.y, ho.y, co.y, fo.y);
+      one(zi.z, zj.z, zo.z, cp.z, m.z, pIf.z, pIt.z, pOf.z, pOt.z, ho.z, co.z, fo.z);
+      one(zi.w, zj.w, zo.w, cp.w, m.w, pIf.w, pIt.w, pOf.w, pOt.w, ho.w, co.w, fo.w);
+    }
+    *reinterpret_cast<float4*>(h_out + o) = ho;
+    *reinterpret_cast<float4*>(c_out + o) = co;
+    *reinterpret_cast<float4*>(mf_out + o) = fo;
+  }
+}
+
 
 // thread = unit u of a row; a block walks rows blockIdx.x, + gridDim.x, ... and keeps the four peephole partial
 // sums of its unit in registers
@@ -138,4 +181,20 @@ extern "C" int mmt_gsk_cell_backward_f32(const float* z, const float* c, const f
                                                                    d_ct, R, U, dz, dc, dmc, dpeep);
   count_launch();
   return check_launch("gsk_cell_backward_kernel");
+}
+
+extern "C" int mmt_gsk_gates_f32(const float* z, const float* c, const float* mc, const uint8_t* valid, const float* w_If,
+                                 const float* w_It, const float* w_Of, const float* w_Ot, int R, int U, float* h_out,
+                                 float* c_out, float* mf_out, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(R >= 0 && U > 0 && U % 4 == 0, "need R >= 0, U % 4 == 0");
+  if (R == 0) return MMT_OK;
+  MMT_REQUIRE(z && c && mc && valid && w_If && w_It && w_Of && w_Ot && h_out && c_out && mf_out, "all pointers required");
+  MMT_ALIGNED(z); MMT_ALIGNED(c); MMT_ALIGNED(mc); MMT_ALIGNED(h_out); MMT_ALIGNED(c_out); MMT_ALIGNED(mf_out);
+  MMT_ALIGNED(w_If); MMT_ALIGNED(w_It); MMT_ALIGNED(w_Of); MMT_ALIGNED(w_Ot);
+  const long blocks = ((long)R * (U / 4) + 255) / 256;
+  const int grid = blocks < (long)kNumSMs * 16 ? (int)blocks : kNumSMs * 16;
+  gsk_gates_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, c, mc, valid, w_If, w_It, w_Of, w_Ot, R, U, h_out, c_out, mf_out);
+  count_launch();
+  return check_launch("gsk_gates_kernel");
 }

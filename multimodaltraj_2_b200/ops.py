@@ -195,6 +195,19 @@ def head_nll(m_t, m_f, valid, W_h, b_h, target, scale, loss_sum):
     return dy
 
 
+def gsk_gates(z, c, mc, valid, params: "CellParams"):
+    """Forward gate update from pre-activations z[R,3U] (mmt_gsk_gates_f32) -> (h', c', m_f)."""
+    lib = _lib.load()
+    for n, t in dict(z=z, c=c, mc=mc).items():
+        _chk(t, torch.float32, n)
+    _chk(valid, torch.uint8, "valid")
+    R, U = c.shape
+    h_out, c_out, mf = torch.empty_like(c), torch.empty_like(c), torch.empty_like(c)
+    _lib.check(lib.mmt_gsk_gates_f32(_p(z), _p(c), _p(mc), _p(valid), _p(params.w_If), _p(params.w_It), _p(params.w_Of),
+                                     _p(params.w_Ot), R, U, _p(h_out), _p(c_out), _p(mf), _stream()), "mmt_gsk_gates_f32")
+    return h_out, c_out, mf
+
+
 def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, dpeep):
     """Backward of the gate update from the saved pre-activations (mmt_gsk_cell_backward_f32):
     returns (dz[R,3U], dc[R,U], dmc[R,U]); dpeep[4,U] is accumulated in place."""

@@ -122,7 +122,9 @@ class Trainer:
                  clip=10.0, gemm="fp32"):
         # gemm: arithmetic of the library contractions of the backward pass (A^T dz, dz W^T, att^T d mh, head):
         #   "fp32" CUDA-core SGEMM (parity mode: gradients within 2e-3 of the fp64 autograd oracle),
-        #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2).
+        #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2); the
+        #          forward gate GEMM then is a library tensor-core GEMM + mmt_gsk_gates_f32 as well (z kept, not recomputed)
+        #          instead of the fused fp32 CUDA-core cell kernel.
         if gemm not in ("fp32", "tf32"):
             raise ValueError("gemm must be 'fp32' or 'tf32'")
         self.gemm = gemm
@@ -136,6 +138,14 @@ class Trainer:
     def loss_and_grad_sums(self, pos, vis, valid):
         """Teacher-forced forward + BPTT on this rank's scenes.  Returns (sum of nll over valid agent-steps [1],
         number of valid agent-steps, {name: SUM-gradient}) -- sums, so that ranks combine by plain addition."""
+        tf32_was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.gemm == "tf32"
+        try:
+            return self._loss_and_grad_sums(pos, vis, valid)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32_was
+
+    def _loss_and_grad_sums(self, pos, vis, valid):
         p, T, P = self.p, self.T, self.P
         S, N = valid.shape
         R, U, E = S * N, p.U, p.E
@@ -152,20 +162,23 @@ class Trainer:
             kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
             att, mhc = ops.aggregate(kern, adj, torch.cat([h, c], -1).contiguous())
             mh, mc = mhc[..., :U].reshape(R, U).contiguous(), mhc[..., U:].reshape(R, U).contiguous()
-            hn, cn, mf = ops.gsk_cell(x, h.reshape(R, U), c.reshape(R, U), mh, mc, vflat, p, ops.PREC_F32)
-            rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc, hn=hn, mf=mf)
+            rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc)
+            if self.gemm == "tf32":
+                # gate GEMM on the tensor cores (library GEMM) + mmt_gsk_gates_f32; z and e are kept for the backward
+                e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
+                z = torch.addmm(p.b, torch.cat([e, rec["h"], mh], -1), p.W)
+                hn, cn, mf = ops.gsk_gates(z, rec["c"], mc, vflat, p)
+                rec["e"], rec["z"] = e, z
+            else:
+                hn, cn, mf = ops.gsk_cell(x, rec["h"], rec["c"], mh, mc, vflat, p, ops.PREC_F32)
+            rec["hn"], rec["mf"] = hn, mf
             if t >= T - 1:
                 rec["dy"] = ops.head_nll(hn, mf, vflat, p.W_h, p.b_h, (pos[:, :, t + 1] - cur).reshape(R, 2).contiguous(),
                                          1.0, loss_sum)
             saved.append(rec)
             h, c = hn.view(S, N, U), cn.view(S, N, U)
         # ---- back-propagation through time
-        tf32_was = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = self.gemm == "tf32"
-        try:
-            return self._backward(saved, loss_sum, valid, vflat, S, N)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = tf32_was
+        return self._backward(saved, loss_sum, valid, vflat, S, N)
 
     def _backward(self, saved, loss_sum, valid, vflat, S, N):
         p, T, P = self.p, self.T, self.P
@@ -185,9 +198,9 @@ class Trainer:
                 dhm = dy @ p.W_h.t()
                 Gh = Gh + dhm[:, :U]
                 d_mf = dhm[:, U:].contiguous()
-            e = torch.relu(r["x"] @ p.W_e + p.b_e)
+            e = r["e"] if "e" in r else torch.relu(r["x"] @ p.W_e + p.b_e)
             A = torch.cat([e, r["h"], r["mh"]], -1)
-            z = torch.addmm(p.b, A, p.W)
+            z = r.pop("z") if "z" in r else torch.addmm(p.b, A, p.W)
             dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep)
             g["W"] += A.t() @ dz
             g["b"] += dz.sum(0)

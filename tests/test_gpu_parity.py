@@ -572,3 +572,21 @@ def test_ade_fde_world_matches_oracle(cuda, n, P):
     assert abs(s[0] - wa.sum()) < 1e-3 * max(1, n) and abs(s[1] - wf.sum()) < 1e-3 * max(1, n) and s[2] == valid.sum()
     ade2, _, s2 = ops.ade_fde_world(dev(pred, cuda), dev(gt, cuda), dev(Hm, cuda))          # valid = NULL: every agent
     assert s2[2].item() == n and np.all(npy(ade2)[valid == 0] > 0)
+
+
+@pytest.mark.gpu
+def test_gsk_gates_from_preactivations_matches_oracle_and_fused_cell(cuda):
+    """mmt_gsk_gates_f32 (training forward in tf32 mode: library GEMM + gates) == the fused fp32 cell and the oracle."""
+    R = 300
+    p = synth.init_params(seed=1)
+    x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R + 2)
+    cp = ops.CellParams.from_numpy(p, cuda)
+    e = np.maximum(x @ p["W_e"] + p["b_e"], 0)
+    z = (np.concatenate([e, h, mh], -1) @ p["W"] + p["b"]).astype(np.float32)
+    hn, cn, mf = ops.gsk_gates(dev(z, cuda), dev(c, cuda), dev(mc, cuda), dev(valid, cuda), cp)
+    oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
+    for got, want in ((hn, oh[0]), (cn, oc[0]), (mf, of[0])):
+        assert np.abs(npy(got) - want).max() < 2e-5
+    h2, c2, f2 = ops.gsk_cell(dev(x, cuda), dev(h, cuda), dev(c, cuda), dev(mh, cuda), dev(mc, cuda), dev(valid, cuda), cp)
+    assert (hn - h2).abs().max().item() < 2e-5 and (cn - c2).abs().max().item() < 2e-5 and (mf - f2).abs().max().item() < 2e-5
+    assert np.all(npy(hn)[valid == 0] == 0) and np.all(npy(cn)[valid == 0] == 0)
