@@ -32,4 +32,6 @@ class ArgsParser():
     parser.add_argument('--precision', type=str, default='bf16', choices=['fp32', 'bf16'])
     parser.add_argument('--world_size', type=int, default=1)
     parser.add_argument('--data_root', type=str, default=None, help='directory holding eth/ and ucy/')
+    parser.add_argument('--save_dir', type=str, default=None,
+                        help='directory for TensorFlow-bundle checkpoints (train.py:330-343); resumed from if it holds one')
     parser.add_argument('--max_agents', type=int, default=64, help='padded agents per scene (N)')

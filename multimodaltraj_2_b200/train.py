@@ -4,7 +4,8 @@ The reference's "training" has no loss, optimiser or gradient step: 
 the model, runs the per-frame step and logs raw errors, then validates.  ``train(args)`` here does
 the same work on the batched B200 path: leave-one-out over the datasets, device-side scene
 batching, scene-sharded rollout + best-of-K scoring on every rank, ADE/FDE partial sums combined
-with one 3-float all-reduce, flat ``{name: tensor}`` checkpoints every ``save_every`` batches.
+with one 3-float all-reduce, TensorFlow-bundle checkpoints (``--save_dir``; ``tf_bundle.py``) the reference's
+``Saver`` can restore.
 """
 from __future__ import annotations
 
@@ -36,6 +37,9 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
     prec = ops.PREC_BF16 if getattr(args, "precision", "bf16") == "bf16" else ops.PREC_F32
     p = params if params is not None else ops.CellParams.from_numpy(
         synth.init_params(seed=0, E=args.embedding_size, U=args.rnn_size), device)
+    save_dir = getattr(args, "save_dir", None)
+    if params is None and save_dir and os.path.exists(os.path.join(save_dir, "checkpoint")):
+        p = load_checkpoint(save_dir, device)                        # train.py:383-402 (get_checkpoint_state + restore)
     N, T, P, K = args.max_agents, args.obs_len, args.pred_len, args.K
     results = {}
     for l in {args.leaveDataset}:                                   # train.py:28
@@ -59,6 +63,11 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
             if rank == 0:
                 print('dataset {0}: ADE = {1:.4f}  FDE = {2:.4f}  agents = {3}  ({4:.2f} s)'.format(
                     d, results[d]["ade"], results[d]["fde"], int(n), results[d]["seconds"]))
+                if save_dir:                                         # train.py:330-343 (same file naming)
+                    os.makedirs(save_dir, exist_ok=True)
+                    path = save_checkpoint(os.path.join(save_dir, 'g2k_MPC_model_kfold_train_{1}_{0}_{2}.ckpt'.format(0, d, 0)),
+                                           p, global_step=len(results) - 1)
+                    print("model saved to {}".format(path))
     return results
 
 
@@ -234,15 +243,50 @@ class Trainer:
         return counts[0] / counts[1] + 0.5 * self.lam * (self.p.W * self.p.W).sum()
 
 
-def save_checkpoint(path, params: ops.CellParams):
-    """Flat {name: tensor} checkpoint (replaces tf.train.Saver, train.py:330-343)."""
-    torch.save({k: getattr(params, k).cpu() for k in params.__dataclass_fields__
-                if isinstance(getattr(params, k), torch.Tensor) and k != "W_packed"}, path)
+def _param_names(params):
+    return [k for k in params.__dataclass_fields__ if isinstance(getattr(params, k), torch.Tensor) and k != "W_packed"]
 
 
-def load_checkpoint(path, device="cuda"):
-    d = torch.load(path, map_location=device)
-    return ops.CellParams(**d)
+def save_checkpoint(path, params: ops.CellParams, trainer: "Trainer" = None, global_step=None):
+    """``saver.save(sess, checkpoint_path, global_step=...)`` of train.py:330-343.
+
+    ``path`` ending in ``.pt``: flat torch ``{name: tensor}`` file.  Otherwise ``path`` is a checkpoint PREFIX and the
+    tensors are written as a TensorFlow bundle (``prefix[-step].index`` + ``.data-00000-of-00001`` + the ``checkpoint``
+    state file; multimodaltraj_2_b200/tf_bundle.py) that ``tf.train.Saver`` of the reference restores.  With ``trainer``
+    the RMSProp accumulators go in as ``<name>/RMSProp`` (TF's slot naming), which is what resuming needs."""
+    tensors = {k: getattr(params, k).detach().cpu() for k in _param_names(params)}
+    if trainer is not None:
+        tensors.update({f"{k}/RMSProp": v.detach().cpu() for k, v in trainer.ms.items()})
+    if str(path).endswith(".pt"):
+        torch.save(tensors, path)
+        return str(path)
+    from pathlib import Path
+    from . import tf_bundle
+    prefix = f"{path}-{int(global_step)}" if global_step is not None else str(path)
+    tf_bundle.write_checkpoint(prefix, {k: v.numpy() for k, v in tensors.items()})
+    tf_bundle.save_state(Path(prefix).parent, Path(prefix).name)
+    return prefix
+
+
+def load_checkpoint(path, device="cuda", trainer: "Trainer" = None):
+    """Restore what ``save_checkpoint`` wrote (``saver.restore``, train.py:383-402); ``path`` may also be a directory
+    holding a ``checkpoint`` state file (``tf.train.get_checkpoint_state``).  Fills ``trainer.ms`` when given."""
+    import os
+    if str(path).endswith(".pt"):
+        d = torch.load(path, map_location=device)
+    else:
+        from . import tf_bundle
+        prefix = tf_bundle.latest_checkpoint(path) if os.path.isdir(path) else str(path)
+        if prefix is None:
+            raise FileNotFoundError(f"no checkpoint state in {path}")
+        d = {k: torch.from_numpy(v.copy()).to(device) for k, v in tf_bundle.read_checkpoint(prefix).items()}
+    slots = {k[:-len("/RMSProp")]: v for k, v in d.items() if k.endswith("/RMSProp")}
+    params = ops.CellParams(**{k: v for k, v in d.items() if not k.endswith("/RMSProp")})
+    if trainer is not None:
+        trainer.p = params
+        for k, v in slots.items():
+            trainer.ms[k] = v.to(device)
+    return params
 
 
 if __name__ == '__main__':

@@ -12,7 +12,13 @@ Outputs (all under tests/golden/):
   zara01_slice.npz   first 2000 columns of data/ucy/zara/zara01/vis_body.csv plus what the reference's
                      own load_traj.DataLoader (imported from /root/reference, only its hard-coded
                      parent_dir patched) makes of them: the frame dictionary and three next_step() calls.
+  ref_ckpt/          two of the reference's own TF-1.14 checkpoints, copied verbatim (binary data files, 107 KB):
+                     save/g2k_mcr_model_val_0.ckpt-0 (17 tensors, one scalar) and
+                     save/g2k_mp_model_kfold_train_2_9_12.ckpt-210 (214 tensors, 14 restart groups) --
+                     golden files for the bundle writer (multimodaltraj_2_b200/tf_bundle.py must reproduce them
+                     byte for byte from their decoded tensors).
 """
+import shutil
 import sys
 import tempfile
 import types
@@ -25,6 +31,13 @@ ROOT = HERE.parent.parent
 REF = Path("/root/reference")
 sys.path.insert(0, str(ROOT / "oracle"))
 from tf_bundle import read_checkpoint  # noqa: E402
+
+
+def ref_ckpt():
+    (HERE / "ref_ckpt").mkdir(exist_ok=True)
+    for stem in ("g2k_mcr_model_val_0.ckpt-0", "g2k_mp_model_kfold_train_2_9_12.ckpt-210"):
+        for ext in (".index", ".data-00000-of-00001"):
+            shutil.copyfile(REF / "save" / (stem + ext), HERE / "ref_ckpt" / (stem + ext))
 
 
 def track_a():
@@ -100,3 +113,4 @@ def loader():
 if __name__ == "__main__":
     track_a()
     loader()
+    ref_ckpt()

@@ -7,6 +7,7 @@ import types
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -164,3 +165,69 @@ def test_train_oracle_gradient_matches_finite_differences():
         pm[k][idx] -= h
         fd = (o_t.loss_and_grads(pos, vis, valid, pp)[0] - o_t.loss_and_grads(pos, vis, valid, pm)[0]) / (2 * h)
         assert abs(fd - g[k][idx]) < 1e-6 + 1e-4 * abs(fd), (k, fd, g[k][idx])
+
+
+# ------------------------------------------------------------------------------------------------
+# TensorFlow-bundle checkpoints (train.py:330-343 save, :383-402 restore) without TensorFlow
+def _ref_ckpt_prefixes():
+    from pathlib import Path
+    gold = Path(__file__).resolve().parent / "golden" / "ref_ckpt"
+    out = sorted({str(f)[:-len(".index")] for f in gold.glob("*.index")})
+    ref = Path("/root/reference/save")           # in the build container: every checkpoint the reference ships
+    if ref.exists():
+        out += sorted({str(f)[:-len(".index")] for f in ref.glob("*.index")})
+    return out
+
+
+def test_tf_bundle_writer_reproduces_the_reference_checkpoints_byte_for_byte(tmp_path):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    import tf_bundle as o_tb                      # the oracle's independent reader
+    from multimodaltraj_2_b200 import tf_bundle
+    prefixes = _ref_ckpt_prefixes()
+    assert len(prefixes) >= 2
+    for n, pre in enumerate(prefixes):
+        got, want = tf_bundle.read_checkpoint(pre), o_tb.read_checkpoint(pre)
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+        out = tmp_path / f"c{n}"
+        tf_bundle.write_checkpoint(out, got)
+        for ext in (".index", ".data-00000-of-00001"):
+            assert Path(str(out) + ext).read_bytes() == Path(pre + ext).read_bytes(), (pre, ext)
+
+
+def test_tf_bundle_checksums_and_known_crc():
+    from multimodaltraj_2_b200 import tf_bundle
+    assert tf_bundle.crc32c(b"123456789") == 0xE3069283          # the CRC-32C check value
+    assert tf_bundle.crc32c(b"\x00" * 32) == 0x8A9136AA           # RFC 3720 B.4
+    assert tf_bundle.crc32c(bytes(range(32))) == 0x46DD794E
+
+
+def test_checkpoint_save_resume_round_trip(tmp_path):
+    import torch
+    from multimodaltraj_2_b200 import ops, synth, tf_bundle
+    from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS, save_checkpoint, load_checkpoint
+    p = ops.CellParams.from_numpy(synth.init_params(seed=4), "cpu")
+    tr = Trainer(p)
+    for k in TRAIN_KEYS:
+        tr.ms[k] = torch.rand_like(tr.ms[k])
+    prefix = save_checkpoint(tmp_path / "g2k_MPC_model_kfold_train_2_0_0.ckpt", p, trainer=tr, global_step=50)
+    assert prefix.endswith(".ckpt-50") and tf_bundle.latest_checkpoint(tmp_path) == prefix
+    tr2 = Trainer(ops.CellParams.from_numpy(synth.init_params(seed=5), "cpu"))
+    p2 = load_checkpoint(tmp_path, device="cpu", trainer=tr2)      # through the `checkpoint` state file
+    for k in TRAIN_KEYS:
+        assert torch.equal(getattr(p2, k), getattr(p, k)) and torch.equal(tr2.ms[k], tr.ms[k]), k
+    assert tr2.p is p2
+    # a flipped byte in the data file is caught by the per-tensor CRC-32C
+    f = tmp_path / "g2k_MPC_model_kfold_train_2_0_0.ckpt-50.data-00000-of-00001"
+    raw = bytearray(f.read_bytes())
+    raw[100] ^= 0x40
+    f.write_bytes(bytes(raw))
+    with pytest.raises(ValueError, match="checksum"):
+        tf_bundle.read_checkpoint(prefix)
+    # flat torch file
+    save_checkpoint(tmp_path / "w.pt", p)
+    p3 = load_checkpoint(tmp_path / "w.pt", device="cpu")
+    assert torch.equal(p3.W, p.W)
