@@ -415,7 +415,8 @@ def run_train(args, rank, world, local_rank):
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
     pos, vis, valid = (torch.from_numpy(a).to(dev) for a in (pos_h, vis_h, valid_h))
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
-    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm)   # lr 0.005 (argParser.py:40) diverges on this synthetic set
+    relational = getattr(args, "variant", "mc") == "mcr"
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational)   # lr 0.005 (argParser.py:40) diverges on this synthetic set
 
     def barrier():
         if world > 1:
@@ -436,7 +437,7 @@ def run_train(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     # all ranks hold identical weights after identical all-reduced updates
-    w = flatten_bucket({k: getattr(params, k) for k in ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h")})
+    w = flatten_bucket({k: getattr(params, k) for k in tr.keys})
     spread = torch.stack([w.min(), -w.max()])
     if world > 1:
         lo = spread.clone()
@@ -452,7 +453,7 @@ def run_train(args, rank, world, local_rank):
                           "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32" if args.train_gemm == "fp32" else "f32 kernels, tf32 tensor-core GEMMs in the backward (fp32 accumulation)",
                           "data": "synthetic",
-                          "config": {"workload": f"{S} scenes x {N} agents per GPU, obs {T_OBS} / pred {P_PRED}, g2k_lstm_mc training step",
+                          "config": {"workload": f"{S} scenes x {N} agents per GPU, obs {T_OBS} / pred {P_PRED}, g2k_lstm_{'mcr' if relational else 'mc'} training step",
                                      "backward_gemm": args.train_gemm, "lr": 1e-3,
                                      "gradient_bucket_bytes": int(w.numel() * 4), "collective": "one NCCL all-reduce (SUM) per step" if world > 1 else "none (1 GPU)"},
                           "loss_first": losses[0], "loss_last": float(loss), "weights_identical_across_ranks": in_sync,

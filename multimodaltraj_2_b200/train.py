@@ -78,16 +78,21 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
 #   -> back-propagation through time -> ONE all-reduce of the flat gradient bucket -> RMSProp (lr 0.005, decay 0.95,
 #   global-norm clip 10: the unused flags of argParser.py:40-47,72).
 TRAIN_KEYS = ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h")
+EDGE_KEYS = ("W1", "b1", "W2", "b2", "w_out", "b_out")     # + the relational edge MLP of g2k_lstm_mcr
+
+
+def _bucket_keys(d: dict):
+    return [k for k in TRAIN_KEYS + EDGE_KEYS if k in d]
 
 
 def flatten_bucket(grads: dict):
-    """One contiguous fp32 bucket (< 1 MB) in TRAIN_KEYS order."""
-    return torch.cat([grads[k].reshape(-1) for k in TRAIN_KEYS])
+    """One contiguous fp32 bucket (< 1 MB) in TRAIN_KEYS (+ EDGE_KEYS) order."""
+    return torch.cat([grads[k].reshape(-1) for k in _bucket_keys(grads)])
 
 
 def unflatten_bucket(flat, like: dict):
     out, o = {}, 0
-    for k in TRAIN_KEYS:
+    for k in _bucket_keys(like):
         n = like[k].numel()
         out[k] = flat[o:o + n].view_as(like[k])
         o += n
@@ -128,7 +133,7 @@ class Trainer:
     """
 
     def __init__(self, params: ops.CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, lr=0.005, decay=0.95,
-                 clip=10.0, gemm="fp32"):
+                 clip=10.0, gemm="fp32", relational=False):
         # gemm: arithmetic of the library contractions of the backward pass (A^T dz, dz W^T, att^T d mh, head):
         #   "fp32" CUDA-core SGEMM (parity mode: gradients within 2e-3 of the fp64 autograd oracle),
         #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2); the
@@ -137,12 +142,18 @@ class Trainer:
         if gemm not in ("fp32", "tf32"):
             raise ValueError("gemm must be 'fp32' or 'tf32'")
         self.gemm = gemm
+        # relational: g2k_lstm_mcr -- the attention logits are kern + the edge-MLP score (mmt_edge_mlp_f32); its backward
+        # (softmax -> per-edge two-layer ELU MLP -> node projections) runs on the compacted edge list with library ops
+        self.relational = bool(relational)
+        if self.relational and params.W1 is None:
+            raise ValueError("relational training needs the edge-MLP weights (W1 .. b_out)")
+        self.keys = TRAIN_KEYS + (EDGE_KEYS if self.relational else ())
         self.p, self.T, self.P, self.r2, self.inv = params, T, P, r2, inv_2sigma2
         self.lam, self.lr, self.decay, self.clip = lam, lr, decay, clip
-        self.ms = {k: torch.zeros_like(getattr(params, k)) for k in TRAIN_KEYS}
+        self.ms = {k: torch.zeros_like(getattr(params, k)) for k in self.keys}
 
     def _tensors(self):
-        return {k: getattr(self.p, k) for k in TRAIN_KEYS}
+        return {k: getattr(self.p, k) for k in self.keys}
 
     def loss_and_grad_sums(self, pos, vis, valid):
         """Teacher-forced forward + BPTT on this rank's scenes.  Returns (sum of nll over valid agent-steps [1],
@@ -169,9 +180,13 @@ class Trainer:
             disp = cur - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
             x = torch.cat([disp, vis[:, :, min(t, T - 1)]], -1).reshape(R, 4).contiguous()
             kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
+            if self.relational:
+                kern = kern + ops.edge_mlp(h.contiguous(), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out)
             att, mhc = ops.aggregate(kern, adj, torch.cat([h, c], -1).contiguous())
             mh, mc = mhc[..., :U].reshape(R, U).contiguous(), mhc[..., U:].reshape(R, U).contiguous()
             rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc)
+            if self.relational:
+                rec["adj"] = adj
             if self.gemm == "tf32":
                 # gate GEMM on the tensor cores (library GEMM) + mmt_gsk_gates_f32; z and e are kept for the backward
                 e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
@@ -193,7 +208,7 @@ class Trainer:
         p, T, P = self.p, self.T, self.P
         R, U, E = S * N, p.U, p.E
         dev = vflat.device
-        g = {k: torch.zeros_like(getattr(p, k)) for k in TRAIN_KEYS}
+        g = {k: torch.zeros_like(getattr(p, k)) for k in self.keys}
         dpeep = torch.zeros((4, U), device=dev)
         Gh = torch.zeros((R, U), device=dev)
         Gc = None
@@ -218,10 +233,48 @@ class Trainer:
             g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
             attT = r["att"].transpose(1, 2)
-            Gh = dA[:, E:E + U] + torch.bmm(attT, dA[:, E + U:].reshape(S, N, U)).reshape(R, U)
+            d_mh = dA[:, E + U:].reshape(S, N, U)
+            Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
             Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
+            if self.relational:
+                Gh = Gh + self._edge_backward(r, d_mh, dmc.view(S, N, U), g, S, N)
         g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]
         return loss_sum, valid.sum().float() * P, g
+
+    def _edge_backward(self, r, d_mh, d_mc, g, S, N):
+        """Back through the attention softmax and the relational edge MLP of one step (oracle: train_b.edge_scores):
+        accumulates the edge-weight gradients into ``g`` and returns d loss / d h[R,U] through the scores."""
+        p = self.p
+        U = p.U
+        h = r["h"]
+        att = r["att"]
+        # G_ij = d mh_i . h_j + d mc_i . c_j ; d logit = att * (G - sum_k att_ik G_ik)
+        G = torch.bmm(d_mh, h.view(S, N, U).transpose(1, 2)) + torch.bmm(d_mc, r["c"].view(S, N, U).transpose(1, 2))
+        dlog = att * (G - (att * G).sum(-1, keepdim=True))
+        s_, i_, j_ = r["adj"].nonzero(as_tuple=True)               # compacted edge list (host sync: first version)
+        if s_.numel() == 0:
+            return torch.zeros_like(h)
+        ri, rj = s_ * N + i_, s_ * N + j_
+        W1a, W1b = p.W1[:U], p.W1[U:]
+        a, b = h @ W1a, h @ W1b                                    # node projections [R, He]
+        pre1 = a[ri] + b[rj] + p.b1
+        e1 = torch.nn.functional.elu(pre1)
+        pre2 = torch.addmm(p.b2, e1, p.W2)
+        e2 = torch.nn.functional.elu(pre2)
+        sc = torch.sigmoid(e2 @ p.w_out + p.b_out)
+        du = dlog[s_, i_, j_] * sc * (1 - sc)
+        g["w_out"] += e2.t() @ du
+        g["b_out"] += du.sum()
+        dpre2 = du[:, None] * p.w_out[None, :] * torch.where(pre2 > 0, torch.ones_like(pre2), e2 + 1)
+        g["W2"] += e1.t() @ dpre2
+        g["b2"] += dpre2.sum(0)
+        dpre1 = (dpre2 @ p.W2.t()) * torch.where(pre1 > 0, torch.ones_like(pre1), e1 + 1)
+        g["b1"] += dpre1.sum(0)
+        da = torch.zeros_like(a).index_add_(0, ri, dpre1)
+        db = torch.zeros_like(b).index_add_(0, rj, dpre1)
+        g["W1"][:U] += h.t() @ da
+        g["W1"][U:] += h.t() @ db
+        return da @ W1a.t() + db @ W1b.t()
 
     def loss_and_grads(self, pos, vis, valid):
         """Single-process view: (mean loss incl. weight decay, {name: gradient of it})."""

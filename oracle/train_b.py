@@ -15,16 +15,28 @@ import numpy as np
 import torch
 
 PARAM_KEYS = ("W_e", "b_e", "W", "b", "w_If", "w_It", "w_Of", "w_Ot", "W_h", "b_h")
+EDGE_KEYS = ("W1", "b1", "W2", "b2", "w_out", "b_out")   # g2k_lstm_mcr: relational edge MLP (track_b.edge_mlp)
 
 
-def attention(cur, valid, r2, inv_2sigma2):
-    """cur[S,N,2], valid[S,N] bool -> att[S,N,N] (masked softmax of the kernel over the adjacency; rows without
-    neighbours are zero).  Same arithmetic as track_b.pairwise_adj + masked_softmax."""
+def edge_scores(h, p):
+    """track_b.edge_mlp in torch: sigmoid(w_out . elu(W2^T elu(W1a^T h_i + W1b^T h_j + b1) + b2) + b_out), all pairs."""
+    U = h.shape[-1]
+    a, b = h @ p["W1"][:U], h @ p["W1"][U:]
+    e1 = torch.nn.functional.elu(a[:, :, None, :] + b[:, None, :, :] + p["b1"])
+    e2 = torch.nn.functional.elu(e1 @ p["W2"] + p["b2"])
+    return torch.sigmoid(e2 @ p["w_out"] + p["b_out"])
+
+
+def attention(cur, valid, r2, inv_2sigma2, score=None):
+    """cur[S,N,2], valid[S,N] bool -> att[S,N,N] (masked softmax of the kernel [+ edge score] over the adjacency; rows
+    without neighbours are zero).  Same arithmetic as track_b.pairwise_adj + masked_softmax."""
     d = cur[:, :, None, :] - cur[:, None, :, :]
     d2 = (d * d).sum(-1)
     N = cur.shape[1]
     adj = (d2 < r2) & ~torch.eye(N, dtype=torch.bool)[None] & valid[:, :, None] & valid[:, None, :]
     kern = torch.exp(-d2 * inv_2sigma2)
+    if score is not None:
+        kern = kern + score
     lg = torch.where(adj, kern, torch.full_like(kern, -math.inf))
     mx = lg.max(-1, keepdim=True).values
     mx = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
@@ -56,8 +68,8 @@ def nll(y, d):
     return math.log(2 * math.pi) + y[..., 2] + y[..., 3] + 0.5 * torch.log(om) + (zx * zx - 2 * rho * zx * zy + zy * zy) / (2 * om)
 
 
-def loss_fn(pos, vis, valid, p, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005):
-    """Scalar training loss for torch tensors (any dtype)."""
+def loss_fn(pos, vis, valid, p, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, relational=False):
+    """Scalar training loss for torch tensors (any dtype).  relational: g2k_lstm_mcr (logits = kern + edge score)."""
     S, N = valid.shape
     U = p["w_If"].shape[0]
     h = torch.zeros((S, N, U), dtype=pos.dtype)
@@ -68,7 +80,7 @@ def loss_fn(pos, vis, valid, p, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005):
         cur = pos[:, :, t]
         disp = cur - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
         x = torch.cat([disp, vis[:, :, min(t, T - 1)]], -1)
-        att = attention(cur, vb, r2, inv_2sigma2)
+        att = attention(cur, vb, r2, inv_2sigma2, edge_scores(h, p) if relational else None)
         mh, mc = att @ h, att @ c
         h, c, m_f = cell(x, h, c, mh, mc, vb, p)
         if t >= T - 1:
@@ -78,13 +90,14 @@ def loss_fn(pos, vis, valid, p, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005):
     return total / n + 0.5 * lam * (p["W"] * p["W"]).sum()
 
 
-def loss_and_grads(pos, vis, valid, p_np, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005):
+def loss_and_grads(pos, vis, valid, p_np, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, relational=False):
     """numpy in, numpy out: (loss, {name: gradient}) in fp64."""
-    p = {k: torch.tensor(np.asarray(p_np[k], np.float64), requires_grad=True) for k in PARAM_KEYS}
+    keys = PARAM_KEYS + (EDGE_KEYS if relational else ())
+    p = {k: torch.tensor(np.asarray(p_np[k], np.float64), requires_grad=True) for k in keys}
     loss = loss_fn(torch.tensor(pos, dtype=torch.float64), torch.tensor(vis, dtype=torch.float64),
-                   torch.tensor(valid), p, T, P, r2, inv_2sigma2, lam)
+                   torch.tensor(valid), p, T, P, r2, inv_2sigma2, lam, relational)
     loss.backward()
-    return float(loss.detach()), {k: p[k].grad.numpy() for k in PARAM_KEYS}
+    return float(loss.detach()), {k: p[k].grad.numpy() for k in keys}
 
 
 def rmsprop_step(p, g, ms, lr=0.005, decay=0.95, eps=1e-10, clip=10.0):

@@ -590,3 +590,28 @@ def test_gsk_gates_from_preactivations_matches_oracle_and_fused_cell(cuda):
     h2, c2, f2 = ops.gsk_cell(dev(x, cuda), dev(h, cuda), dev(c, cuda), dev(mh, cuda), dev(mc, cuda), dev(valid, cuda), cp)
     assert (hn - h2).abs().max().item() < 2e-5 and (cn - c2).abs().max().item() < 2e-5 and (mf - f2).abs().max().item() < 2e-5
     assert np.all(npy(hn)[valid == 0] == 0) and np.all(npy(cn)[valid == 0] == 0)
+
+
+@pytest.mark.gpu
+def test_train_gradients_relational_match_autograd_oracle(cuda):
+    """g2k_lstm_mcr training step (BASELINE configs[1]): gradients through the attention softmax and the relational
+    edge MLP, fp32 kernels + library ops vs the fp64 autograd oracle."""
+    import train_b as o_t
+    from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS, EDGE_KEYS
+    S, N = 3, 16
+    pos, vis, valid = synth.make_crowd(S, N, seed=6, half_extent=1.5, ragged=False)    # dense: many neighbours per agent
+    p = synth.init_params(seed=1, He=64)
+    want_loss, want = o_t.loss_and_grads(pos, vis, valid, p, relational=True)
+    tr = Trainer(ops.CellParams.from_numpy(p, cuda), relational=True)
+    loss, g = tr.loss_and_grads(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
+    assert abs(float(loss) - want_loss) < 1e-4 * max(1.0, abs(want_loss))
+    for k in TRAIN_KEYS:
+        assert rel_err(npy(g[k]).astype(np.float64), want[k]) < 2e-3, k
+    scale = max(np.abs(want[k]).max() for k in EDGE_KEYS)
+    assert scale > 1e-6                                     # the scores matter in this crowd
+    for k in EDGE_KEYS:                                     # relative to the largest edge-weight gradient entry
+        assert np.abs(npy(g[k]).astype(np.float64) - want[k]).max() < 5e-3 * scale, k
+    # one data-parallel step runs and moves the edge weights
+    w0 = tr.p.W2.clone()
+    tr.step(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
+    assert not torch.equal(tr.p.W2, w0)
