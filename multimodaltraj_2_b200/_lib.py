@@ -89,7 +89,9 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _build.LIB
+    import os
+    alt = os.environ.get("MMT_LIB")     # another build of the same library (kernel experiments under scratch/)
+    return Path(alt) if alt else _build.LIB
 
 
 def load(build_if_missing: bool = True):

@@ -32,6 +32,10 @@
 #include "mmt_common.cuh"
 #include "tc_common.cuh"
 
+#ifndef RO_EXP
+#define RO_EXP 0   // timing experiments only (scratch/): 1 = one head-weight load per source, 2 = two gate-constant loads per quad
+#endif
+
 namespace mmt {
 
 constexpr int RO_U = 128;
@@ -504,7 +508,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         // ---- (e) gate epilogue: 4 passes; this thread: row r, units 32 p + 8 cs .. +7, four at a time
         float2 y2[5];
 #pragma unroll
-        for (int z = 0; z < 5; ++z) y2[z] = make_float2(0.f, 0.f);
+        for (int z = 0; z < 5; ++z) y2[z] = (RO_EXP & 1) ? make_float2((float)z, (float)z) : make_float2(0.f, 0.f);
         const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
         const float2 inv2 = make_float2(inv, inv);
         // Branch-free body (rows of invalid agents compute on zeros and are masked by selects; emitting / observed steps
@@ -537,12 +541,17 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               float4 c4 = *reinterpret_cast<const float4*>(cf_row + (u >> 2) * 2048);
               float ho[4], fo[4];
               const float4 bI = *reinterpret_cast<const float4*>(s_bias + u);
+#if RO_EXP & 2
+              const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + u);
+              const float4 bJ = bI, bO = bI, pIt = pIf, pOf = pIf, pOt = pIf;
+#else
               const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + u);
               const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + u);
               const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + u);
               const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + u);
               const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + u);
               const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + u);
+#endif
 #pragma unroll
               for (int pr = 0; pr < 2; ++pr) {
                 const int i0 = pr * 2;
@@ -581,9 +590,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                 for (int hsrc = 0; hsrc < 2; ++hsrc) {
                   const float2 va = hsrc ? make_float2(fo[0], fo[1]) : make_float2(ho[0], ho[1]);
                   const float2 vb = hsrc ? make_float2(fo[2], fo[3]) : make_float2(ho[2], ho[3]);
+#if RO_EXP & 1
+                  const float4 w4 = *reinterpret_cast<const float4*>(s_wht + hsrc * RO_U + u);
+#endif
 #pragma unroll
                   for (int z = 0; z < 5; ++z) {
+#if !(RO_EXP & 1)
                     const float4 w4 = *reinterpret_cast<const float4*>(s_wht + z * 256 + hsrc * RO_U + u);
+#endif
                     y2[z] = ffma2(va, make_float2(w4.x, w4.y), y2[z]);
                     y2[z] = ffma2(vb, make_float2(w4.z, w4.w), y2[z]);
                   }
