@@ -148,6 +148,24 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, float v[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 lanes x 256 bit: thread t of the warp holds (lane t/4, columns 2(t%4), 2(t%4)+1) in v[0..1] and (lane t/4 + 8, same
+// columns) in v[2..3] (cute SM100_TMEM_LOAD_16dp256b1x); the lane field of the address selects lanes 0-15 or 16-31 of
+// the warp's quarter.  One thread then owns 4 rows x 2 columns instead of 1 row x 8 columns: per-column constants
+// cost a quarter of the shared-memory load instructions.
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t addr, float v[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_16x256b(uint32_t addr, const uint32_t r[4]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

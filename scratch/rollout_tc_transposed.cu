@@ -33,7 +33,10 @@
 #include "tc_common.cuh"
 
 #ifndef RO_AGG256
-#define RO_AGG256 1   // 0: two N = 128 aggregation MMAs per k-step (mh, then mc) as in the first fused version
+#define RO_AGG256 0
+#endif
+#ifndef RO_SETMAXNREG
+#define RO_SETMAXNREG 0   // 1: helpers 64 / workers 112 registers (measured: ptxas then spills in both regions; kept for experiments)
 #endif
 
 namespace mmt {
@@ -61,9 +64,9 @@ constexpr int RS_CF = RS_ATT + 2 * RO_BLK;      // fp32 c: 64 KB
 constexpr int RS_W = RS_CF + 128 * 128 * 4;
 constexpr int RS_BAR = RS_W + RO_NSTAGE * RO_STAGE_BYTES;
 constexpr int RS_TMEM = RS_BAR + 256;
-constexpr int RS_BIAS = RS_TMEM + 16;                  // b[384], w_If, w_It, w_Of, w_Ot [4][128]
-constexpr int RS_WE = RS_BIAS + (384 + 512) * 4;       // W_e[4][64], b_e[64]
-constexpr int RS_WHT = RS_WE + (256 + 64) * 4;         // head weights transposed: W_hT[5][2U] (unit pairs feed FFMA2)
+constexpr int RS_GC = RS_TMEM + 16;                    // gate constants per unit pair (bias, peepholes): ro_gc_index()
+constexpr int RS_WE = RS_GC + 64 * 16 * 4;             // W_e[4][64], b_e[64]
+constexpr int RS_WHT = RS_WE + (256 + 64) * 4;         // head weights [z][unit pair][W_h(m_t) u, u+1 | W_h(m_f) u, u+1]
 constexpr int RS_PX = RS_WHT + 5 * 256 * 4;            // float[128] current x (invalid agents: far away)
 constexpr int RS_PY = RS_PX + 512;                     // float[128] current y
 constexpr int RS_NEXT = RS_PY + 512;                   // float2[128] predicted next positions
@@ -82,7 +85,7 @@ constexpr uint32_t RT_HEAD = 352;     // 4 column slices x 8: head partial sums 
                                       // (the 32 columns of the mh accumulator beyond accumulator 1: free after the conversion)
 constexpr uint32_t kIdescGate = make_idesc_bf16(128, RO_N);
 constexpr uint32_t kIdescAggMN = make_idesc_bf16(128, 128) | (1u << 16);   // B operand MN-major
-constexpr uint32_t kIdescAgg256 = make_idesc_bf16(128, 256) | (1u << 16);  // [h | c] in one MMA
+constexpr uint32_t kIdescAgg256 = make_idesc_bf16(128, 256) | (1u << 16);
 
 struct RoArgs {
   const float* pos;      // [R, F, 2]
@@ -109,6 +112,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
   d |= (uint64_t)2 << 61;
   return d;
 }
+
+// Gate constants of unit pair `pair` (units 2 pair, 2 pair + 1), vector c of 4:
+//   c = 0: b_i b_i' b_j b_j'   1: b_o b_o' w_If w_If'   2: w_It w_It' w_Of w_Of'   3: w_Ot w_Ot' - -
+// The four lanes of an epilogue row group (t % 4 = pair % 4) read the same vector of four adjacent pairs: 64 contiguous bytes.
+__host__ __device__ constexpr int ro_gc_index(int pair, int c) { return (((pair >> 2) * 4 + c) * 4 + (pair & 3)) * 4; }
 
 // k-chunk of the packed weights / A operand (0 = e, 1-2 = h, 3-4 = mh) consumed at position kcn of a pass
 __device__ __forceinline__ constexpr int ro_perm(int kcn) { return kcn == 0 ? 1 : kcn == 1 ? 2 : kcn == 2 ? 0 : kcn; }
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * RO_NSTAGE, ACC_FULL = bar0 + 16 * RO_NSTAGE,
                  ACC_EMPTY = ACC_FULL + 16, ATT_READY = ACC_EMPTY + 16, E_READY = ATT_READY + 8,
                  MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8, P0_ISSUED = AGG_FULL + 8;
-  float* s_bias = reinterpret_cast<float*>(smem + RS_BIAS);
+  float* s_gc = reinterpret_cast<float*>(smem + RS_GC);
   float* s_we = reinterpret_cast<float*>(smem + RS_WE);
   float* s_wht = reinterpret_cast<float*>(smem + RS_WHT);
   float* s_px = reinterpret_cast<float*>(smem + RS_PX);
@@ -155,6 +163,9 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + RS_TMEM);
   const int nsteps = a.T + a.P - 1;
 
+  // Set-up shared by all roles; instantiated inside each role branch so that nothing but kernel parameters is live
+  // across the setmaxnreg instructions (ptxas otherwise spills the common prologue against the smaller budget).
+  auto prologue = [&]() -> uint32_t {
   if (tid == 0) {
     for (int s = 0; s < RO_NSTAGE; ++s) {
       mbar_init(W_FULL + 8 * s, 1);
@@ -173,25 +184,42 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   }
   if (warp == RO_WWARPS) tmem_alloc(sbase + RS_TMEM, 512);
   // sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 is folded into the packed i/o weight columns, biases and peepholes
-  for (int i = tid; i < 384; i += RO_THREADS) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
-  for (int i = tid; i < 128; i += RO_THREADS) {
-    s_bias[384 + i] = 0.5f * a.w_If[i];
-    s_bias[512 + i] = 0.5f * a.w_It[i];
-    s_bias[640 + i] = 0.5f * a.w_Of[i];
-    s_bias[768 + i] = 0.5f * a.w_Ot[i];
+  for (int i = tid; i < 64 * 16; i += RO_THREADS) {
+    const int pair = i >> 4, c = (i >> 2) & 3, e = i & 3, u = 2 * pair + (e & 1);
+    float val = 0.f;
+    switch (c * 2 + (e >> 1)) {
+      case 0: val = 0.5f * a.b[u]; break;
+      case 1: val = a.b[128 + u]; break;
+      case 2: val = 0.5f * a.b[256 + u]; break;
+      case 3: val = 0.5f * a.w_If[u]; break;
+      case 4: val = 0.5f * a.w_It[u]; break;
+      case 5: val = 0.5f * a.w_Of[u]; break;
+      case 6: val = 0.5f * a.w_Ot[u]; break;
+      default: break;
+    }
+    s_gc[ro_gc_index(pair, c) + e] = val;
   }
   for (int i = tid; i < 256; i += RO_THREADS) s_we[i] = a.W_e[i];
   for (int i = tid; i < 64; i += RO_THREADS) s_we[256 + i] = a.b_e[i];
-  for (int i = tid; i < 256 * 5; i += RO_THREADS) s_wht[(i % 5) * 256 + i / 5] = a.W_h[i];
+  for (int i = tid; i < 256 * 5; i += RO_THREADS) {   // W_h[2U][5]: rows 0..U-1 multiply m_t, U..2U-1 multiply m_f
+    const int z = i % 5, row = i / 5, src = row >> 7, u = row & 127;
+    s_wht[(z * 64 + (u >> 1)) * 4 + src * 2 + (u & 1)] = a.W_h[i];
+  }
   // attention operand: entries outside a row's own scene stay zero for the whole kernel
   for (int i = tid; i < 2 * RO_BLK / 16; i += RO_THREADS)
     reinterpret_cast<uint4*>(smem + RS_ATT)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
-  __syncthreads();
+    asm volatile("bar.sync 0;" ::: "memory");   // all 640 threads, from either role branch
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-
-  if (warp >= RO_WWARPS && warp < RO_WWARPS + RO_NPROD) {
+    return *s_tmem;
+  };
+  uint32_t tmem_base;
+  // Register rebalancing between the warpgroups: the helper warpgroup (producers + issuers: uniform-register code) gives
+  // up registers, the four worker warpgroups take them (640 x 96 at launch; 128 x 56 + 512 x 112 = 64512 <= 65536).
+  if (warp >= RO_WWARPS) {
+  if (RO_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  tmem_base = prologue();
+  if (warp < RO_WWARPS + RO_NPROD) {
     // =============================== weight-stage producers ===============================
     // One thread managing a whole ring sustains only one cp.async.bulk per ~360 clk (issue + mbarrier round
     // trip serialise in that thread: scratch/bulk_bench2.cu); RO_NPROD threads in different warps take the
@@ -208,7 +236,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                  RO_STAGE_BYTES, W_FULL + 8 * s);
       }
     }
-  } else if (warp >= RO_WWARPS + RO_NPROD) {
+  } else {
     // =============================== MMA issuers ===============================
     // Issuer 0: aggregation + gate passes 0, 2; issuer 1: gate passes 1, 3.  Two issuing threads reach the
     // nominal 48 clk per M128 x N96 MMA where one tops out at ~68 (scratch/mma_bench3.cu).  The whole warp runs the
@@ -222,7 +250,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       uint32_t sc = 0;
       const uint64_t d_att0 = make_desc_sw128(sbase + RS_ATT), d_att1 = make_desc_sw128(sbase + RS_ATT + RO_BLK);
       const uint64_t d_h = make_desc_sw128_mn(sbase + RS_H, RO_BLK, 1024);
-      [[maybe_unused]] const uint64_t d_c = make_desc_sw128_mn(sbase + RS_C, RO_BLK, 1024);
+      const uint64_t d_c = make_desc_sw128_mn(sbase + RS_C, RO_BLK, 1024);
       const uint64_t d_w = make_desc_sw128(sbase + RS_W);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
         for (int t = 0; t < nsteps; ++t, ++sc) {
@@ -340,8 +368,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         }
     };
     if (warp == RO_WWARPS + RO_NPROD) issuer(std::integral_constant<int, 0>{}); else issuer(std::integral_constant<int, 1>{});
+  }
   } else {
     // =============================== workers ===============================
+    if (RO_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    tmem_base = prologue();
     const int q = warp & 3, cs = warp >> 2;
     const int r = q * 32 + lane;           // this thread's row: TMEM lane, attention row, epilogue row
     const int N = a.N;
@@ -350,7 +381,12 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     // the diagonal entry (j == r) of the attention row is masked out of the packed bf16 words of its 8-column chunk
     const int jdiag8 = (r - sb) & ~7;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* const cf_row = smem + RS_CF + r * 16;     // + (u >> 2) * 2048: 4 fp32 c of units u .. u+3
+    // Gate epilogue ownership (tcgen05.ld 16x256b): lane = 4 g + jp owns unit pair jp of its warp's 8 units in the four
+    // rows q 32 + g + {0, 8, 16, 24}.  Per-unit constants are then 4 + 5 load instructions per pass instead of 14 + 20,
+    // and the state images are written with 32/64-bit accesses (a 128-bit access with 32 distinct addresses occupies the
+    // shared-memory pipe for 8 clk, a 64-bit one for 2: scratch/lds_bench.cu).
+    const int jp = lane & 3, g = lane >> 2;
+    const int rq = q * 32 + g;             // first of this thread's epilogue rows
     uint32_t sc = 0;
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -358,6 +394,12 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       const int gr = row0 + r;
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
+      uint32_t vmask = 0;                   // validity of the four epilogue rows
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int grk = row0 + rq + 8 * k;
+        if (grk < a.R && a.valid[grk] != 0) vmask |= 1u << k;
+      }
       worker_sync();   // every worker has finished the previous tile before the reset
       // zero the recurrent state: h, c (bf16 images + fp32 c) in shared memory and the h columns of the TMEM A operand
       {
@@ -403,7 +445,6 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           xv.y = __fsub_rn(cur.y, prevp.y);
         }
         prevp = cur;
-        if (!v) xv = make_float4(0.f, 0.f, 0.f, 0.f);   // whatever an invalid slot holds (NaN included) stays out of the state
         if (cs == 0) {   // invalid agents sit far away: d2 = inf fails d2 < r2 for every partner
           s_px[r] = v ? cur.x : 3.0e18f;
           s_py[r] = v ? cur.y : 3.0e18f;
@@ -465,6 +506,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
         const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
         const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
+        float inv4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rk = rq + 8 * k;
+          const float sk = (s_sum[rk] + s_sum[128 + rk]) + (s_sum[256 + rk] + s_sum[384 + rk]);
+          inv4[k] = sk > 0.f ? __fdividef(1.0f, sk) : 0.f;
+        }
         // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Computed while
         //      the aggregation MMAs execute; no worker barrier between here and MH_READY, so a warp that finishes early
         //      starts its conversion early (placing e before the attention build delayed the aggregation: +900 clk)
@@ -518,14 +566,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         mbar_arrive_warp(MH_READY);
         if (DIAG && dbg) dbg[4] = clock64();
 
-        // ---- (e) gate epilogue: 4 passes; this thread: row r, units 32 p + 8 cs .. +7, four at a time
-        float2 y2[5];
+        // ---- (e) gate epilogue: 4 passes; this thread: units 32 p + 8 cs + 2 jp, +1 of rows rq + 8 k (k = 0..3)
+        float y[4][5];
 #pragma unroll
-        for (int z = 0; z < 5; ++z) y2[z] = make_float2(0.f, 0.f);
-        const float2 kHalf = make_float2(0.5f, 0.5f), kNegHalf = make_float2(-0.5f, -0.5f), kOne = make_float2(1.f, 1.f);
-        const float2 inv2 = make_float2(inv, inv);
-        // Branch-free body (emitting / observed steps are two instantiations): one basic block per pass, so the two unit quads of a thread interleave and the
-        // MUFU results of one hide behind the FMAs of the other.
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int z = 0; z < 5; ++z) y[k][z] = 0.f;
+        const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
+        // Branch-free body (rows of invalid agents compute on zeros and are masked by selects; emitting / observed steps
+        // are two instantiations): one basic block per pass, so the four rows of a thread interleave and the
+        // MUFU results of one hide behind the FMAs of the others.
         auto gate_epilogue = [&](auto emit_tag) {
           constexpr bool EMIT = decltype(emit_tag)::value;
 #pragma unroll 1
@@ -536,98 +586,91 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             tc_fence_after();
             if (DIAG && dbg) dbg[5 + 2 * p] = clock64();
             const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
-            const int u0 = p * RO_UN + cs * 8;        // first of this thread's 8 units
-            uint32_t hw[4], cw[4];                    // h', c' as bf16 pairs
-            float zi[2][4], zj[2][4], zo[2][4], zm[2][4];
+            const uint32_t t_mc = t_row + RT_MC + p * RO_UN + cs * 8;
+            float zi[2][4], zj[2][4], zo[2][4], zm[2][4];   // [lane half][row g: pair, row g + 8: pair]
 #pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              tmem_ld4(t_acc + hq * 4, zi[hq]);
-              tmem_ld4(t_acc + RO_UN + hq * 4, zj[hq]);
-              tmem_ld4(t_acc + 2 * RO_UN + hq * 4, zo[hq]);
-              tmem_ld4(t_row + RT_MC + u0 + hq * 4, zm[hq]);
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t lo = (uint32_t)(16 * hh) << 16;
+              tmem_ld_16x256b(t_acc + lo, zi[hh]);
+              tmem_ld_16x256b(t_acc + lo + RO_UN, zj[hh]);
+              tmem_ld_16x256b(t_acc + lo + 2 * RO_UN, zo[hh]);
+              tmem_ld_16x256b(t_mc + lo, zm[hh]);
             }
             tmem_wait_ld();
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              const int u = u0 + hq * 4;
-              float4 c4 = *reinterpret_cast<const float4*>(cf_row + (u >> 2) * 2048);
-              float ho[4], fo[4];
-              const float4 bI = *reinterpret_cast<const float4*>(s_bias + u);
-              const float4 bJ = *reinterpret_cast<const float4*>(s_bias + 128 + u);
-              const float4 bO = *reinterpret_cast<const float4*>(s_bias + 256 + u);
-              const float4 pIf = *reinterpret_cast<const float4*>(s_bias + 384 + u);
-              const float4 pIt = *reinterpret_cast<const float4*>(s_bias + 512 + u);
-              const float4 pOf = *reinterpret_cast<const float4*>(s_bias + 640 + u);
-              const float4 pOt = *reinterpret_cast<const float4*>(s_bias + 768 + u);
-#pragma unroll
-              for (int pr = 0; pr < 2; ++pr) {
-                const int i0 = pr * 2;
-                auto sel = [&](const float4& f) { return pr ? make_float2(f.z, f.w) : make_float2(f.x, f.y); };
-                // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes):
-                //   c_x' = x + g (tj - x) = x + (1 + th) d,  d = (tj - x) / 2        (x = mc, c)
-                //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
-                const float2 c2 = sel(c4);
-                const float2 m2 = fmul2(make_float2(zm[hq][i0], zm[hq][i0 + 1]), inv2);
-                const float2 ai = ffma2(sel(pIf), m2, ffma2(sel(pIt), c2, fadd2(make_float2(zi[hq][i0], zi[hq][i0 + 1]), sel(bI))));
-                const float2 th = tanh2(ai);
-                const float2 tjh = fmul2(tanh2(fadd2(make_float2(zj[hq][i0], zj[hq][i0 + 1]), sel(bJ))), kHalf);
-                const float2 dm = ffma2(m2, kNegHalf, tjh), dc = ffma2(c2, kNegHalf, tjh);
-                const float2 g2 = fadd2(th, kOne);                     // 2 g
-                const float2 cf = ffma2(dm, g2, m2);                   // (1-g) mc + g tanh j
-                const float2 ct = ffma2(dc, g2, c2);                   // (1-g) c  + g tanh j
-                const float2 o1 = ffma2(sel(pOf), cf, fadd2(make_float2(zo[hq][i0], zo[hq][i0 + 1]), sel(bO)));
-                const float2 to = tanh2(ffma2(sel(pOt), ct, o1));
-                // rows of invalid agents carry a bounded state of their own (x = 0 input, no neighbours, nobody's neighbour:
-                // their attention column is zero) instead of being re-zeroed by 16 selects per pass
-                if constexpr (EMIT) {
-                  const float2 q2 = ffma2(to, kHalf, kHalf);           // output gate
-                  const float2 h2 = fmul2(tanh2(ct), q2), f2 = fmul2(tanh2(cf), q2);
-                  ho[i0] = h2.x; ho[i0 + 1] = h2.y;
-                  fo[i0] = f2.x; fo[i0 + 1] = f2.y;
-                } else {
-                  const float2 ha = fmul2(tanh2(ct), kHalf);
-                  const float2 h2 = ffma2(to, ha, ha);
-                  ho[i0] = h2.x; ho[i0 + 1] = h2.y;
-                }
-                if (pr) { c4.z = ct.x; c4.w = ct.y; } else { c4.x = ct.x; c4.y = ct.y; }
-              }
-              *reinterpret_cast<float4*>(cf_row + (u >> 2) * 2048) = c4;
-              if constexpr (EMIT) {
-                // head partial sums, two units per packed FMA: y2[z] += (v_u, v_u+1) * (W_hT[z][u], W_hT[z][u+1])
-                // (rows of invalid agents accumulate values nobody reads)
-#pragma unroll
-                for (int hsrc = 0; hsrc < 2; ++hsrc) {
-                  const float2 va = hsrc ? make_float2(fo[0], fo[1]) : make_float2(ho[0], ho[1]);
-                  const float2 vb = hsrc ? make_float2(fo[2], fo[3]) : make_float2(ho[2], ho[3]);
-#pragma unroll
-                  for (int z = 0; z < 5; ++z) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(s_wht + z * 256 + hsrc * RO_U + u);
-                    y2[z] = ffma2(va, make_float2(w4.x, w4.y), y2[z]);
-                    y2[z] = ffma2(vb, make_float2(w4.z, w4.w), y2[z]);
-                  }
-                }
-              }
-              hw[hq * 2] = pack_bf16x2(ho[0], ho[1]);
-              hw[hq * 2 + 1] = pack_bf16x2(ho[2], ho[3]);
-              cw[hq * 2] = pack_bf16x2(c4.x, c4.y);
-              cw[hq * 2 + 1] = pack_bf16x2(c4.z, c4.w);
-            }
+            const int pair = (p * 4 + cs) * 4 + jp;   // unit pair: units 2 pair, 2 pair + 1
+            const int u = 2 * pair;
+            float2 bI, bJ, bO, pIf, pIt, pOf, pOt;
             {
+              const float4* gc = reinterpret_cast<const float4*>(s_gc + ro_gc_index(pair, 0));
+              const float4 g0 = gc[0], g1 = gc[4], g2 = gc[8], g3 = gc[12];
+              bI = make_float2(g0.x, g0.y); bJ = make_float2(g0.z, g0.w);
+              bO = make_float2(g1.x, g1.y); pIf = make_float2(g1.z, g1.w);
+              pIt = make_float2(g2.x, g2.y); pOf = make_float2(g2.z, g2.w);
+              pOt = make_float2(g3.x, g3.y);
+            }
+            // fp32 c: [unit pair][row] float2, the 32-byte groups of a row octet swizzled by pair % 4 (conflict-free per half warp)
+            uint8_t* const cfp = smem + RS_CF + pair * 1024;
+            const uint32_t cfx = (uint32_t)jp << 5;
+            // bf16 images: this thread's word of the 16-byte chunk (u & 63) >> 3 of row R: chunk ^ (R & 7), R & 7 == g
+            const uint32_t img = (uint32_t)(u >> 6) * RO_BLK + (uint32_t)(((((u & 63) >> 3) ^ g) << 4) + (u & 7) * 2);
+            float2 ho[4], fo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int hh = k >> 1, i0 = (k & 1) * 2;
+              const int R = rq + 8 * k;
+              const bool vk = (vmask >> k) & 1u;
+              float2* const cptr = reinterpret_cast<float2*>(cfp + (((uint32_t)R * 8u) ^ cfx));
+              // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes), arranged so that
+              // only one packed FMA separates each MUFU result from its consumer:
+              //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
+              //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
+              const float2 c2 = *cptr;
+              const float2 m2 = fmul2(make_float2(zm[hh][i0], zm[hh][i0 + 1]), make_float2(inv4[k], inv4[k]));
+              const float2 t1 = ffma2(pIf, m2, make_float2(zi[hh][i0], zi[hh][i0 + 1]));
+              const float2 t2 = ffma2(pIt, c2, bI);
+              const float2 th = tanh2(fadd2(t1, t2));
+              const float2 tj = tanh2(fadd2(make_float2(zj[hh][i0], zj[hh][i0 + 1]), bJ));
+              const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
+              const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
+              const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
+              const float2 o1 = ffma2(pOf, cf, fadd2(make_float2(zo[hh][i0], zo[hh][i0 + 1]), bO));
+              const float2 to = tanh2(ffma2(pOt, ct, o1));
+              const float2 ha = fmul2(tanh2(ct), kHalf);
+              const float2 h2 = ffma2(to, ha, ha);
+              ho[k] = make_float2(vk ? h2.x : 0.f, vk ? h2.y : 0.f);
+              const float2 cn = make_float2(vk ? ct.x : 0.f, vk ? ct.y : 0.f);
+              *cptr = cn;
+              if constexpr (EMIT) {
+                const float2 fa = fmul2(tanh2(cf), kHalf);
+                fo[k] = ffma2(to, fa, fa);
+              }
               // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
-              // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass)
-              const uint32_t so = (u0 >> 6) * RO_BLK + r * 128 + ((((u0 & 63) >> 3) ^ (r & 7)) << 4);
-              *reinterpret_cast<uint4*>(smem + RS_C + so) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
-              *reinterpret_cast<uint4*>(smem + RS_H + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass); zeros for invalid rows
+              const uint32_t so = img + (uint32_t)R * 128u;
+              *reinterpret_cast<uint32_t*>(smem + RS_C + so) = pack_bf16x2(cn.x, cn.y);
+              *reinterpret_cast<uint32_t*>(smem + RS_H + so) = pack_bf16x2(ho[k].x, ho[k].y);
+            }
+            if constexpr (EMIT) {
+              // head partial sums of the four rows over this thread's two units (rows of invalid agents accumulate
+              // values nobody reads)
+#pragma unroll
+              for (int z = 0; z < 5; ++z) {
+                const float4 w4 = reinterpret_cast<const float4*>(s_wht)[z * 64 + pair];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  y[k][z] = fmaf(ho[k].x, w4.x, fmaf(ho[k].y, w4.y, fmaf(fo[k].x, w4.z, fmaf(fo[k].y, w4.w, y[k][z]))));
+              }
             }
             if (p == RO_NP - 1) {
               // every gate MMA of this step has completed (ACC_FULL of the last pass): the h columns of the TMEM A
-              // operand may be overwritten.  Each thread re-reads the 4 x 8 units it stored (its own writes) and
-              // copies them: units u, u+1 -> column u/2.
+              // operand may be overwritten.  The warp re-reads the 32 rows x (4 x 8 units) it stored (lane = row here)
+              // and copies them: units u, u+1 -> column u/2.
+              __syncwarp();
 #pragma unroll
               for (int pp = 0; pp < RO_NP; ++pp) {
-                const int u = pp * RO_UN + cs * 8;
-                const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (u >> 6) * RO_BLK + r * 128 +
-                                                                 ((((u & 63) >> 3) ^ (r & 7)) << 4));
+                const int uu = pp * RO_UN + cs * 8;
+                const uint4 t4 = *reinterpret_cast<const uint4*>(smem + RS_H + (uu >> 6) * RO_BLK + r * 128 +
+                                                                 ((((uu & 63) >> 3) ^ (r & 7)) << 4));
                 const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
                 tmem_st4(t_row + RT_A_H + pp * 16 + cs * 4, w4);
               }
@@ -642,11 +685,28 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         // ---- (f) head: combine the four column slices of each row, emit the 5 parameters and the next position
         if (emit) {
           {
-            uint32_t yw[8];
+            // sum over the four lanes of a row group, then lane jp stores parameters 2 jp, 2 jp + 1 of its rows
+            // (16x256b store: columns 2 jp, 2 jp + 1 of the slice's 8 head columns)
 #pragma unroll
-            for (int z = 0; z < 5; ++z) yw[z] = __float_as_uint(y2[z].x + y2[z].y);
-            yw[5] = yw[6] = yw[7] = 0u;
-            tmem_st8(t_row + RT_HEAD + cs * 8, yw);
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int z = 0; z < 5; ++z) {
+                y[k][z] += __shfl_xor_sync(0xffffffffu, y[k][z], 1);
+                y[k][z] += __shfl_xor_sync(0xffffffffu, y[k][z], 2);
+              }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t yw[4];
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) {
+                const int k = hh * 2 + s2;
+                const float c0 = jp == 0 ? y[k][0] : jp == 1 ? y[k][2] : jp == 2 ? y[k][4] : 0.f;
+                const float c1 = jp == 0 ? y[k][1] : jp == 1 ? y[k][3] : 0.f;
+                yw[s2 * 2] = __float_as_uint(c0);
+                yw[s2 * 2 + 1] = __float_as_uint(c1);
+              }
+              tmem_st_16x256b(t_row + ((uint32_t)(16 * hh) << 16) + RT_HEAD + cs * 8, yw);
+            }
             tmem_wait_st();
             tc_fence_before();
           }
