@@ -45,6 +45,10 @@ constexpr int NP_SM_BAR = NP_SM_A + 34 * 1024;      // A block (32 KB); the epil
 constexpr int NP_SM_TOTAL = NP_SM_BAR + 32;
 constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
 
+// BLOCKED: h is the tile-blocked bf16 state of the per-step fast path (cell_tc.cu: piece (g, r) = units 8g..8g+7 of
+// row r of a 128-row tile, 16 bytes at ((tile 16 + g) 128 + r) 16) -- each piece is one 16-byte chunk of the K-major
+// SWIZZLE_128B operand, copied as it is.
+template <bool BLOCKED>
 __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
                                                               const uint8_t* __restrict__ Wp, float* __restrict__ out,
                                                               int num_tiles) {
@@ -72,6 +76,14 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int row0 = tile * 128;
+    if constexpr (BLOCKED) {
+      const uint4* src = reinterpret_cast<const uint4*>(h) + (size_t)tile * 2048;   // 16 pieces x 128 rows
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int pc = tid + 256 * k, g = pc >> 7, rr = pc & 127;
+        *reinterpret_cast<uint4*>(smem + NP_SM_A + (g >> 3) * EM_BLK + sw128_off(rr, (g & 7) * 8)) = __ldg(src + pc);
+      }
+    } else
     // A operand: one warp per row, lane -> 4 consecutive k (fp32 -> bf16), K-major SWIZZLE_128B
     for (int rr = warp; rr < 128; rr += 8) {
       const int g = row0 + rr;
@@ -296,18 +308,21 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __rest
 }
 
 // h[R, U] (row stride ld_h) -> score[S,N,N] on the edges of adj; nab: >= R*256 floats of scratch.
+// ld_h < 0: h is the tile-blocked bf16 state (rows padded to whole tiles) instead of fp32 rows.
 int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
                        int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(node_proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
+    cudaFuncSetAttribute(node_proj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
+    cudaFuncSetAttribute(node_proj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
     cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EE_SM_TOTAL + 1024);
     attr_set = true;
   }
   const uint8_t* Wp = reinterpret_cast<const uint8_t*>(packed);
   int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
-  node_proj_tc_kernel<<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nab, tiles);
+  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nab, tiles);
+  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nab, tiles);
   count_launch();
   int rc = check_launch("node_proj_tc_kernel");
   if (rc) return rc;

@@ -23,7 +23,8 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
                         const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
                         const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
                         cudaStream_t stream);
-int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
+int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
+                               int S, int N,
                                float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
 int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
                        int N, float* score, float* nab, int zero_fill, cudaStream_t stream);
@@ -90,10 +91,14 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
     off += align_up(bytes);
     return p;
   };
-  w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE) && !cfg->relational;
+  // the relational variant takes the bf16-state path when its edge MLP runs on the tensor cores and the graph step is the
+  // MMA kernel (blocked layout, N >= 16): edge scores are added to the logits inside graph_aggregate_mma_kernel
+  const bool tileable = 128 % cfg->N == 0 || (cfg->N % 128 == 0 && cfg->N <= 1024);
+  const bool rel_fast = cfg->relational && U == 128 && He == 128 && tileable && cfg->N >= 16;
+  w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE) && (!cfg->relational || rel_fast);
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
-  w.blocked = w.fast && (128 % cfg->N == 0 || (cfg->N % 128 == 0 && cfg->N <= 1024));
+  w.blocked = w.fast && tileable;
   if (w.fast) {
     const size_t Rp = (R + 127) / 128 * 128;   // state rows padded to whole 128-row tiles
     for (int i = 0; i < 2; ++i) {
@@ -103,7 +108,7 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
     w.mhb = take(Rp * U * 2);
     w.mcb = take(Rp * U * 2);
     w.hc[0] = w.hc[1] = w.mhc = w.mf = w.kern = nullptr;
-    w.adj = nullptr;
+    w.adj = cfg->relational ? (uint8_t*)take(NN) : nullptr;   // the edge kernel walks the adjacency mask
   } else {
     w.hc[0] = (float*)take(R * 2 * U * 4);
     w.hc[1] = (float*)take(R * 2 * U * 4);
@@ -161,7 +166,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
 
   // bf16, non-relational, whole scenes per 128-row tile: the entire recurrence is one persistent kernel with the
   // state on chip (rollout_tc.cu).  MMT_PREC_BF16_STEPWISE keeps the per-step kernels (A/B checks, other N).
-  const bool fused = w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16;
+  const bool fused = w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16 && !cfg->relational;
   if (fused) {
     if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, stream)))
       return rc0;
@@ -185,8 +190,18 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       // bf16 fast path: [pairwise + softmax + aggregation] and [gate GEMM + gates + head], two kernels per step
       const bool emit = t >= T - 1;
       float* po = par + (size_t)(t - (T - 1)) * 5;
+      const float* esc = nullptr;
+      if (cfg->relational) {
+        // adjacency mask only (no kernel matrix) -> node projections from the blocked bf16 state -> edge scores
+        if ((rc = mmt_pairwise_adj_f32(w.pbuf[ic], valid, S, N, cfg->r2, cfg->inv_2sigma2, nullptr, w.adj, nullptr, stream)))
+          return rc;
+        if ((rc = launch_edge_mlp_tc(reinterpret_cast<const float*>(w.hb[hb]), -1, w.adj, w.epacked, ew, S, N, w.score,
+                                     w.ework, 0, stream)))
+          return rc;
+        esc = w.score;
+      }
       if (w.blocked && N >= 16)
-        rc = launch_graph_aggregate_mma(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2, w.mhb,
+        rc = launch_graph_aggregate_mma(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], esc, S, N, cfg->r2, cfg->inv_2sigma2, w.mhb,
                                         w.mcb, stream);
       else if (w.blocked)
         rc = launch_graph_aggregate_blocked(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2,

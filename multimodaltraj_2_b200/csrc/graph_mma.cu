@@ -44,8 +44,8 @@ __device__ __forceinline__ uint64_t gm_desc_mn(uint32_t smem_addr) {   // LBO = 
 
 __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
-    const float* __restrict__ c, int R, int N, float r2, float neg_inv_log2e, __nv_bfloat16* __restrict__ mhb,
-    __nv_bfloat16* __restrict__ mcb, int num_tiles) {
+    const float* __restrict__ c, const float* __restrict__ score, int R, int N, float r2, float neg_inv_log2e,
+    __nv_bfloat16* __restrict__ mhb, __nv_bfloat16* __restrict__ mcb, int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
   uint8_t* const smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -126,8 +126,22 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
         const bool vi = sval[li] != 0;
         const int cb = multi ? kh * 128 : sb;          // staged index of the K block's / scene's first agent
         const int jbeg = jhalf * jn;
+        // relational variant (g2k_lstm_mcr): logits = kern + edge score; score[scene][i][j] row of this agent, columns of
+        // this K block (read only where the adjacency holds: the edge kernel writes the edges only)
+        const float* srow = nullptr;
+        if (score != nullptr) {
+          const size_t gi = (size_t)tile * 128 + i;                  // global agent row; gi / N = scene, gi % N = local index
+          srow = score + gi * N + (multi ? kh * 128 : 0);
+        }
         for (int j8 = jbeg; j8 < jbeg + jn; j8 += 8) {
           uint32_t pk[4];
+          float sc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (srow != nullptr && (size_t)tile * 128 + i < (size_t)R) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(srow + j8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(srow + j8 + 4));
+            sc8[0] = s0.x; sc8[1] = s0.y; sc8[2] = s0.z; sc8[3] = s0.w;
+            sc8[4] = s1.x; sc8[5] = s1.y; sc8[6] = s1.z; sc8[7] = s1.w;
+          }
 #pragma unroll
           for (int q = 0; q < 8; q += 2) {
             float e2[2];
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
               const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
               const bool a = vi && sval[j] != 0 && j != li && d2 < r2;
               const float kern = ex2_fast(d2 * neg_inv_log2e);     // exp(-d2 / 2 sigma^2)
-              e2[z] = a ? ex2_fast(kern * LOG2E) : 0.f;            // exp(kern); softmax numerator
+              e2[z] = a ? ex2_fast((kern + sc8[q + z]) * LOG2E) : 0.f;   // exp(logit); softmax numerator
             }
             pk[q >> 1] = pack_bf16x2(e2[0], e2[1]);
             sum += bf16_lo(pk[q >> 1]) + bf16_hi(pk[q >> 1]);      // normalise by what the MMA really sums
@@ -194,8 +208,9 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
-                               float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
+// score: NULL (g2k_lstm_mc) or [S,N,N] edge scores added to the logits on the edges (g2k_lstm_mcr)
+int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
+                               int S, int N, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   static bool attr_set = false;
   if (!attr_set) {
@@ -204,7 +219,7 @@ int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const voi
   }
   const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
   graph_aggregate_mma_kernel<<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(
-      pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
+      pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, score, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
       reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);
   count_launch();
   return check_launch("graph_aggregate_mma_kernel");

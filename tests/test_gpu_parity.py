@@ -363,10 +363,13 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
     assert np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max() < 5e-2
 
 
-def test_forecast_bf16_relational(cuda):
-    """g2k_lstm_mcr in bf16 mode (tcgen05 edge MLP + tcgen05 cell, per-step kernels): mean trajectory vs the fp32 oracle."""
-    S, N, T, P, K = 6, 64, 8, 12, 20
-    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0, ragged=True)
+@pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
+def test_forecast_bf16_relational(cuda, S, N):
+    """g2k_lstm_mcr in bf16 mode (tcgen05 edge MLP + tcgen05 cell, per-step kernels): mean trajectory vs the fp32 oracle.
+    N = 64, 16: bf16-state path (edge scores inside the MMA graph step); N = 256: a scene spans two tiles;
+    N = 12, 8: fp32-state fallback."""
+    T, P, K = 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0 if N < 100 else 8.0, ragged=True)
     p = synth.init_params(seed=3)
     eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
     fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=True, prec=ops.PREC_BF16, device=cuda)
