@@ -38,7 +38,8 @@ __global__ void pack_edge_weights_kernel(const float* __restrict__ W1, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// node projections: out[R, 256] = h[R, 128 (ld)] x [W1a | W1b]   (fp32 in HBM, bf16 operands)
+// node projections: out[R, 256] = h[R, 128 (ld)] x [W1a | W1b]   (bf16 operands, fp32 accumulation, bf16 result: the edge
+// kernel gathers two 256-byte rows per edge instead of two 512-byte ones and keeps eight edges in flight per warp)
 constexpr int NP_SM_B = 0;                          // 64 KB
 constexpr int NP_SM_A = NP_SM_B + EM_W1_BYTES;      // 32 KB
 constexpr int NP_SM_BAR = NP_SM_A + 34 * 1024;      // A block (32 KB); the epilogue staging [8][32][33] floats needs 33 KB
@@ -50,7 +51,7 @@ constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
 // SWIZZLE_128B operand, copied as it is.
 template <bool BLOCKED>
 __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
-                                                              const uint8_t* __restrict__ Wp, float* __restrict__ out,
+                                                              const uint8_t* __restrict__ Wp, __nv_bfloat16* __restrict__ out,
                                                               int num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
   uint8_t* const smem = smem_dyn;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const int g = row0 + q * 32 + rr;
-          if (g < R) out[(size_t)g * 256 + half * 128 + cb * 32 + lane] = stg[rr * 33 + lane];
+          if (g < R) out[(size_t)g * 256 + half * 128 + cb * 32 + lane] = __float2bfloat16_rn(stg[rr * 33 + lane]);
         }
         __syncwarp();
       }
@@ -153,7 +154,7 @@ constexpr uint32_t kIdescEE = make_idesc_bf16(128, 128);
 
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_fast(x * 1.4426950408889634f) - 1.0f; }
 
-__global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __restrict__ nab,   // [R, 256] = [a | b]
+__global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16* __restrict__ nab,   // [R, 256] = [a | b]
                                                              const uint8_t* __restrict__ adj, const uint8_t* __restrict__ Wp,
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
                                                              const float* __restrict__ w_out, const float* __restrict__ b_out,
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __rest
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
     float* sc = score + (size_t)s * N * N;
     const uint8_t* ad = adj + (size_t)s * N * N;
-    const float* nab_s = nab + (size_t)s * N * 256;
+    const __nv_bfloat16* nab_s = nab + (size_t)s * N * 256;
     if (zero_fill)
       for (int i = tid; i < (N * N) >> 2; i += 256) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r0 = 0; r0 < N; r0 += rows_per_chunk) {
@@ -227,24 +228,26 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const float* __rest
           uint8_t* blk = smem + EE_SM_A + (k >> 6) * EM_BLK + ((k & 7) << 1);
           const int chunk = (k & 63) >> 3;
 #pragma unroll
-          for (int e0 = 0; e0 < 16; e0 += 4) {
-            float4 av[4], bv[4];
+          for (int e0 = 0; e0 < 16; e0 += 8) {
+            uint2 av[8], bv[8];   // 4 bf16 of a_i / b_j each: a 256-byte row per warp load
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
               const int e = warp * 16 + e0 + u;
-              av[u] = bv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              av[u] = bv[u] = make_uint2(0u, 0u);
               if (e < nt) {
                 const uint32_t ij = s_list[t0 + e];
-                av[u] = __ldg(reinterpret_cast<const float4*>(nab_s + (size_t)(ij >> 16) * 256) + lane);
-                bv[u] = __ldg(reinterpret_cast<const float4*>(nab_s + (size_t)(ij & 0xffffu) * 256 + 128) + lane);
+                av[u] = __ldg(reinterpret_cast<const uint2*>(nab_s + (size_t)(ij >> 16) * 256) + lane);
+                bv[u] = __ldg(reinterpret_cast<const uint2*>(nab_s + (size_t)(ij & 0xffffu) * 256 + 128) + lane);
               }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
               const int e = warp * 16 + e0 + u;   // rows beyond nt get elu(b1): finite, never read back
               *reinterpret_cast<uint2*>(blk + e * 128 + ((chunk ^ (e & 7)) << 4)) =
-                  make_uint2(pack_bf16x2(elu_fast(av[u].x + bv[u].x + c4.x), elu_fast(av[u].y + bv[u].y + c4.y)),
-                             pack_bf16x2(elu_fast(av[u].z + bv[u].z + c4.z), elu_fast(av[u].w + bv[u].w + c4.w)));
+                  make_uint2(pack_bf16x2(elu_fast(bf16_lo(av[u].x) + bf16_lo(bv[u].x) + c4.x),
+                                         elu_fast(bf16_hi(av[u].x) + bf16_hi(bv[u].x) + c4.y)),
+                             pack_bf16x2(elu_fast(bf16_lo(av[u].y) + bf16_lo(bv[u].y) + c4.z),
+                                         elu_fast(bf16_hi(av[u].y) + bf16_hi(bv[u].y) + c4.w)));
             }
           }
         }
@@ -321,13 +324,14 @@ int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void*
   }
   const uint8_t* Wp = reinterpret_cast<const uint8_t*>(packed);
   int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
-  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nab, tiles);
-  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nab, tiles);
+  __nv_bfloat16* nabh = reinterpret_cast<__nv_bfloat16*>(nab);   // R x 256 bf16 inside the R x 256 float scratch
+  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nabh, tiles);
+  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nabh, tiles);
   count_launch();
   int rc = check_launch("node_proj_tc_kernel");
   if (rc) return rc;
   grid = S < 2 * kNumSMs ? S : 2 * kNumSMs;
-  edge_mlp_tc_kernel<<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nab, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
+  edge_mlp_tc_kernel<<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nabh, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
                                                                 zero_fill);
   count_launch();
   return check_launch("edge_mlp_tc_kernel");
