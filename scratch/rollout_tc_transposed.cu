@@ -33,7 +33,7 @@
 #include "tc_common.cuh"
 
 #ifndef RO_AGG256
-#define RO_AGG256 0
+#define RO_AGG256 1
 #endif
 #ifndef RO_SETMAXNREG
 #define RO_SETMAXNREG 0   // 1: helpers 64 / workers 112 registers (measured: ptxas then spills in both regions; kept for experiments)
@@ -387,6 +387,12 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     // shared-memory pipe for 8 clk, a 64-bit one for 2: scratch/lds_bench.cu).
     const int jp = lane & 3, g = lane >> 2;
     const int rq = q * 32 + g;             // first of this thread's epilogue rows
+    // byte offsets into shared memory, pinned in registers (asm below): left to itself the compiler re-derives them
+    // from threadIdx in every pass (~50 integer instructions per pass)
+    uint32_t cf_lane = RS_CF + (cs * 4 + jp) * 1024 + (((uint32_t)rq * 8u) ^ ((uint32_t)jp << 5));   // + p 16384, ^ (k << 6)
+    uint32_t img_even = (uint32_t)rq * 128u + (uint32_t)(((cs ^ g) << 4) + jp * 4);        // units 32 p + 8 cs + 2 jp, p even
+    uint32_t img_odd = (uint32_t)rq * 128u + (uint32_t)((((4 + cs) ^ g) << 4) + jp * 4);   // p odd
+    asm volatile("" : "+r"(cf_lane), "+r"(img_even), "+r"(img_odd));
     uint32_t sc = 0;
 
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -394,12 +400,6 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       const int gr = row0 + r;
       const bool rok = gr < a.R;
       const bool v = rok && a.valid[gr] != 0;
-      uint32_t vmask = 0;                   // validity of the four epilogue rows
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int grk = row0 + rq + 8 * k;
-        if (grk < a.R && a.valid[grk] != 0) vmask |= 1u << k;
-      }
       worker_sync();   // every worker has finished the previous tile before the reset
       // zero the recurrent state: h, c (bf16 images + fp32 c) in shared memory and the h columns of the TMEM A operand
       {
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           xv.y = __fsub_rn(cur.y, prevp.y);
         }
         prevp = cur;
+        if (!v) xv = make_float4(0.f, 0.f, 0.f, 0.f);   // whatever an invalid slot holds (NaN included) stays out of the state
         if (cs == 0) {   // invalid agents sit far away: d2 = inf fails d2 < r2 for every partner
           s_px[r] = v ? cur.x : 3.0e18f;
           s_py[r] = v ? cur.y : 3.0e18f;
@@ -506,13 +507,6 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         worker_sync();   // all four partial sums of every attention row are written; next observed frame landed
         const float ssum = (s_sum[r] + s_sum[128 + r]) + (s_sum[256 + r] + s_sum[384 + r]);
         const float inv = ssum > 0.f ? __fdividef(1.0f, ssum) : 0.f;
-        float inv4[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rk = rq + 8 * k;
-          const float sk = (s_sum[rk] + s_sum[128 + rk]) + (s_sum[256 + rk] + s_sum[384 + rk]);
-          inv4[k] = sk > 0.f ? __fdividef(1.0f, sk) : 0.f;
-        }
         // ---- (c) e = relu(x W_e + b_e): row r, k in [16 cs, 16 cs + 16) -> A-operand columns 8 cs .. +7.  Computed while
         //      the aggregation MMAs execute; no worker barrier between here and MH_READY, so a warp that finishes early
         //      starts its conversion early (placing e before the attention build delayed the aggregation: +900 clk)
@@ -567,14 +561,21 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         if (DIAG && dbg) dbg[4] = clock64();
 
         // ---- (e) gate epilogue: 4 passes; this thread: units 32 p + 8 cs + 2 jp, +1 of rows rq + 8 k (k = 0..3)
+        //      1 / sum of its four rows first (in the wait for gate pass 0; the sums stay until the next attention build)
+        float inv4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rk = rq + 8 * k;
+          const float sk = (s_sum[rk] + s_sum[128 + rk]) + (s_sum[256 + rk] + s_sum[384 + rk]);
+          inv4[k] = sk > 0.f ? __fdividef(1.0f, sk) : 0.f;
+        }
         float y[4][5];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
           for (int z = 0; z < 5; ++z) y[k][z] = 0.f;
-        const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
-        // Branch-free body (rows of invalid agents compute on zeros and are masked by selects; emitting / observed steps
-        // are two instantiations): one basic block per pass, so the four rows of a thread interleave and the
+        const float2 kHalf = make_float2(0.5f, 0.5f), kNegHalf = make_float2(-0.5f, -0.5f), kOne = make_float2(1.f, 1.f);
+        // Branch-free body (emitting / observed steps are two instantiations): one basic block per pass, so the four rows of a thread interleave and the
         // MUFU results of one hide behind the FMAs of the others.
         auto gate_epilogue = [&](auto emit_tag) {
           constexpr bool EMIT = decltype(emit_tag)::value;
@@ -587,18 +588,18 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             if (DIAG && dbg) dbg[5 + 2 * p] = clock64();
             const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
             const uint32_t t_mc = t_row + RT_MC + p * RO_UN + cs * 8;
+            // the two lane halves (rows rq, rq + 8 | rq + 16, rq + 24) one after the other: 16 accumulator registers live
+            // instead of 32, which is what keeps the per-thread address constants in registers
             float zi[2][4], zj[2][4], zo[2][4], zm[2][4];   // [lane half][row g: pair, row g + 8: pair]
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            auto load_half = [&](int hh) {
               const uint32_t lo = (uint32_t)(16 * hh) << 16;
               tmem_ld_16x256b(t_acc + lo, zi[hh]);
               tmem_ld_16x256b(t_acc + lo + RO_UN, zj[hh]);
               tmem_ld_16x256b(t_acc + lo + 2 * RO_UN, zo[hh]);
               tmem_ld_16x256b(t_mc + lo, zm[hh]);
-            }
-            tmem_wait_ld();
+            };
+            load_half(0);
             const int pair = (p * 4 + cs) * 4 + jp;   // unit pair: units 2 pair, 2 pair + 1
-            const int u = 2 * pair;
             float2 bI, bJ, bO, pIf, pIt, pOf, pOt;
             {
               const float4* gc = reinterpret_cast<const float4*>(s_gc + ro_gc_index(pair, 0));
@@ -608,47 +609,49 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               pIt = make_float2(g2.x, g2.y); pOf = make_float2(g2.z, g2.w);
               pOt = make_float2(g3.x, g3.y);
             }
-            // fp32 c: [unit pair][row] float2, the 32-byte groups of a row octet swizzled by pair % 4 (conflict-free per half warp)
-            uint8_t* const cfp = smem + RS_CF + pair * 1024;
-            const uint32_t cfx = (uint32_t)jp << 5;
-            // bf16 images: this thread's word of the 16-byte chunk (u & 63) >> 3 of row R: chunk ^ (R & 7), R & 7 == g
-            const uint32_t img = (uint32_t)(u >> 6) * RO_BLK + (uint32_t)(((((u & 63) >> 3) ^ g) << 4) + (u & 7) * 2);
+            // fp32 c: [unit pair][row] float2, the 32-byte groups of a row octet swizzled by pair % 4 (conflict-free per
+            // half warp): row offset (rq + 8 k) 8 ^ (jp << 5) == cf_row0 ^ (k << 6) -- no carries between the fields
+            const uint32_t cfo = cf_lane + p * 16384;   // bits 6-7 of the row offset are clear for k = 0: ^ (k << 6) below
+            // bf16 images: this thread's word of the 16-byte chunk (u & 63) >> 3 = 4 (p & 1) + cs of row R, swizzled by
+            // R & 7 == g; rows rq + 8 k are 1024 k bytes further
+            uint8_t* const imp = smem + (p >> 1) * RO_BLK + ((p & 1) ? img_odd : img_even);
             float2 ho[4], fo[4];
+            tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int hh = k >> 1, i0 = (k & 1) * 2;
-              const int R = rq + 8 * k;
-              const bool vk = (vmask >> k) & 1u;
-              float2* const cptr = reinterpret_cast<float2*>(cfp + (((uint32_t)R * 8u) ^ cfx));
-              // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes), arranged so that
-              // only one packed FMA separates each MUFU result from its consumer:
-              //   c_x' = x + g (tj - x) = (x + d) + th d,  d = (tj - x) / 2        (x = mc, c)
-              //   h'   = q tanh(c_t') = to a + a,          a = tanh(c_t') / 2
+              if (k == 2) {
+                load_half(1);
+                tmem_wait_ld();
+              }
+              float2* const cptr = reinterpret_cast<float2*>(smem + (cfo ^ (uint32_t)(k << 6)));
+              // sigmoid = 0.5 + 0.5 tanh (the inner 1/2 is folded into weights/biases/peepholes):
+              //   c_x' = x + g (tj - x) = x + (1 + th) d,  d = (tj - x) / 2        (x = mc, c)
               const float2 c2 = *cptr;
               const float2 m2 = fmul2(make_float2(zm[hh][i0], zm[hh][i0 + 1]), make_float2(inv4[k], inv4[k]));
-              const float2 t1 = ffma2(pIf, m2, make_float2(zi[hh][i0], zi[hh][i0 + 1]));
-              const float2 t2 = ffma2(pIt, c2, bI);
-              const float2 th = tanh2(fadd2(t1, t2));
-              const float2 tj = tanh2(fadd2(make_float2(zj[hh][i0], zj[hh][i0 + 1]), bJ));
-              const float2 dm = fmul2(fadd2(tj, fmul2(m2, kNeg)), kHalf), dc = fmul2(fadd2(tj, fmul2(c2, kNeg)), kHalf);
-              const float2 cf = ffma2(th, dm, fadd2(m2, dm));        // (1-g) mc + g tanh j
-              const float2 ct = ffma2(th, dc, fadd2(c2, dc));        // (1-g) c  + g tanh j
+              const float2 ai = ffma2(pIf, m2, ffma2(pIt, c2, fadd2(make_float2(zi[hh][i0], zi[hh][i0 + 1]), bI)));
+              const float2 th = tanh2(ai);
+              const float2 tjh = fmul2(tanh2(fadd2(make_float2(zj[hh][i0], zj[hh][i0 + 1]), bJ)), kHalf);
+              const float2 dm = ffma2(m2, kNegHalf, tjh), dc = ffma2(c2, kNegHalf, tjh);
+              const float2 g2 = fadd2(th, kOne);                     // 2 g
+              const float2 cf = ffma2(dm, g2, m2);                   // (1-g) mc + g tanh j
+              const float2 ct = ffma2(dc, g2, c2);                   // (1-g) c  + g tanh j
               const float2 o1 = ffma2(pOf, cf, fadd2(make_float2(zo[hh][i0], zo[hh][i0 + 1]), bO));
               const float2 to = tanh2(ffma2(pOt, ct, o1));
-              const float2 ha = fmul2(tanh2(ct), kHalf);
-              const float2 h2 = ffma2(to, ha, ha);
-              ho[k] = make_float2(vk ? h2.x : 0.f, vk ? h2.y : 0.f);
-              const float2 cn = make_float2(vk ? ct.x : 0.f, vk ? ct.y : 0.f);
-              *cptr = cn;
+              // rows of invalid agents carry a bounded state of their own (x = 0 input, no neighbours, nobody's neighbour)
               if constexpr (EMIT) {
-                const float2 fa = fmul2(tanh2(cf), kHalf);
-                fo[k] = ffma2(to, fa, fa);
+                const float2 q2 = ffma2(to, kHalf, kHalf);           // output gate
+                ho[k] = fmul2(tanh2(ct), q2);
+                fo[k] = fmul2(tanh2(cf), q2);
+              } else {
+                const float2 ha = fmul2(tanh2(ct), kHalf);
+                ho[k] = ffma2(to, ha, ha);
               }
+              *cptr = ct;
               // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
-              // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass); zeros for invalid rows
-              const uint32_t so = img + (uint32_t)R * 128u;
-              *reinterpret_cast<uint32_t*>(smem + RS_C + so) = pack_bf16x2(cn.x, cn.y);
-              *reinterpret_cast<uint32_t*>(smem + RS_H + so) = pack_bf16x2(ho[k].x, ho[k].y);
+              // complete; the gate MMAs read h from TMEM, whose copy follows after the last pass)
+              *reinterpret_cast<uint32_t*>(imp + RS_C + k * 1024) = pack_bf16x2(ct.x, ct.y);
+              *reinterpret_cast<uint32_t*>(imp + RS_H + k * 1024) = pack_bf16x2(ho[k].x, ho[k].y);
             }
             if constexpr (EMIT) {
               // head partial sums of the four rows over this thread's two units (rows of invalid agents accumulate
@@ -684,48 +687,49 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         if (DIAG && dbg) dbg[13] = clock64();
         // ---- (f) head: combine the four column slices of each row, emit the 5 parameters and the next position
         if (emit) {
-          {
-            // sum over the four lanes of a row group, then lane jp stores parameters 2 jp, 2 jp + 1 of its rows
-            // (16x256b store: columns 2 jp, 2 jp + 1 of the slice's 8 head columns)
+          // every warp is through with the accumulators of this step: columns RT_MH .. RT_MH + 95 carry the head partial sums.
+          // Slice cs, parameter pair m = z / 2: 8 columns, lane group jp writes columns 2 jp, 2 jp + 1 (16x256b store)
+          worker_sync();
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+          for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-              for (int z = 0; z < 5; ++z) {
-                y[k][z] += __shfl_xor_sync(0xffffffffu, y[k][z], 1);
-                y[k][z] += __shfl_xor_sync(0xffffffffu, y[k][z], 2);
-              }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t yw[4];
-#pragma unroll
-              for (int s2 = 0; s2 < 2; ++s2) {
-                const int k = hh * 2 + s2;
-                const float c0 = jp == 0 ? y[k][0] : jp == 1 ? y[k][2] : jp == 2 ? y[k][4] : 0.f;
-                const float c1 = jp == 0 ? y[k][1] : jp == 1 ? y[k][3] : 0.f;
-                yw[s2 * 2] = __float_as_uint(c0);
-                yw[s2 * 2 + 1] = __float_as_uint(c1);
-              }
-              tmem_st_16x256b(t_row + ((uint32_t)(16 * hh) << 16) + RT_HEAD + cs * 8, yw);
+            for (int m = 0; m < 3; ++m) {
+              const uint32_t yw[4] = {__float_as_uint(y[2 * hh][2 * m]), m < 2 ? __float_as_uint(y[2 * hh][2 * m + 1]) : 0u,
+                                      __float_as_uint(y[2 * hh + 1][2 * m]), m < 2 ? __float_as_uint(y[2 * hh + 1][2 * m + 1]) : 0u};
+              tmem_st_16x256b(t_row + ((uint32_t)(16 * hh) << 16) + RT_MH + (cs * 3 + m) * 8, yw);
             }
-            tmem_wait_st();
-            tc_fence_before();
-          }
+          tmem_wait_st();
+          tc_fence_before();
           worker_sync();
           if (cs == 0) {
             tc_fence_after();
-            float p0[8], p1[8], p2[8], p3[8];
-            tmem_ld8(t_row + RT_HEAD, p0);
-            tmem_ld8(t_row + RT_HEAD + 8, p1);
-            tmem_ld8(t_row + RT_HEAD + 16, p2);
-            tmem_ld8(t_row + RT_HEAD + 24, p3);
-            tmem_wait_ld();
             float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+              float p0[8], p1[8], p2[8], p3[8];
+              tmem_ld8(t_row + RT_MH + m * 8, p0);
+              tmem_ld8(t_row + RT_MH + (3 + m) * 8, p1);
+              tmem_ld8(t_row + RT_MH + (6 + m) * 8, p2);
+              tmem_ld8(t_row + RT_MH + (9 + m) * 8, p3);
+              tmem_wait_ld();
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (2 * m + e < 5) {
+                  float acc = 0.f;
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) acc += (p0[2 * jj + e] + p1[2 * jj + e]) + (p2[2 * jj + e] + p3[2 * jj + e]);
+                  o[2 * m + e] = acc;
+                }
+            }
             if (v) {
 #pragma unroll
-              for (int z = 0; z < 5; ++z) o[z] = (p0[z] + p1[z]) + (p2[z] + p3[z]) + __ldg(a.b_h + z);
+              for (int z = 0; z < 5; ++z) o[z] += __ldg(a.b_h + z);
               o[2] = __expf(o[2]);
               o[3] = __expf(o[3]);
               o[4] = tanh_fast(o[4]);
+            } else {
+#pragma unroll
+              for (int z = 0; z < 5; ++z) o[z] = 0.f;
             }
             if (rok) {
               float* po = a.params + ((size_t)gr * a.P + (t - (a.T - 1))) * 5;
