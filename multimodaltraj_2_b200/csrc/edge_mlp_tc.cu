@@ -149,7 +149,7 @@ constexpr int EE_SM_LIST = EE_SM_A + 2 * EM_BLK;    // u32[EE_LIST]: i << 16 | j
 constexpr int EE_SM_PAR = EE_SM_LIST + EE_LIST * 4; // b1[128] b2[128] w_out[128]
 constexpr int EE_SM_PART = EE_SM_PAR + 3 * 128 * 4; // float[128]: partial sums of the upper column half
 constexpr int EE_SM_BAR = EE_SM_PART + 512;
-constexpr int EE_SM_TOTAL = EE_SM_BAR + 48;
+constexpr int EE_SM_TOTAL = EE_SM_BAR + 48 + 32;
 constexpr uint32_t kIdescEE = make_idesc_bf16(128, 128);
 
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_fast(x * 1.4426950408889634f) - 1.0f; }
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_w = sbase + EE_SM_BAR, bar_mma = bar_w + 8;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + EE_SM_BAR + 16);
-  int* s_count = reinterpret_cast<int*>(smem + EE_SM_BAR + 24);
+  int* s_wtot = reinterpret_cast<int*>(smem + EE_SM_BAR + 48);   // 8 warp totals of the edge scan
   uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + EE_SM_LIST);
   float* s_b1 = reinterpret_cast<float*>(smem + EE_SM_PAR);
   float* s_b2 = s_b1 + 128;
@@ -201,22 +201,55 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
     if (zero_fill)
       for (int i = tid; i < (N * N) >> 2; i += 256) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r0 = 0; r0 < N; r0 += rows_per_chunk) {
-      if (tid == 0) *s_count = 0;
-      __syncthreads();
-      // ---- compact the edges of rows [r0, r1) (ballot + one shared atomic per warp)
+      // ---- compact the edges of rows [r0, r1): every thread takes 16 consecutive entries of the adjacency block (one
+      //      128-bit load; the byte-at-a-time walk with a ballot and a shared atomic per 256 entries was 57 % of the
+      //      kernel's stall samples, almost all of it the latency of 16 dependent rounds of 1-byte loads), counts its
+      //      edges, and a block-wide exclusive scan gives its place in the list -- ascending (row, column) order
       const int r1 = min(N, r0 + rows_per_chunk);
-      const int tot = (r1 - r0) * N;
-      for (int e0 = 0; e0 < tot; e0 += 256) {
-        const int e = e0 + tid;
-        const bool is = e < tot && ad[(size_t)r0 * N + e] != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, is);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(s_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (is) s_list[base + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)(r0 + e / N) << 16) | (uint32_t)(e % N);
+      const int tot = (r1 - r0) * N;             // <= EE_LIST = 16 x 256
+      const uint8_t* src = ad + (size_t)r0 * N;
+      const int e_base = tid * 16;
+      uint32_t wv[4] = {0u, 0u, 0u, 0u};
+      if (e_base < tot) {
+        if (e_base + 16 <= tot && (reinterpret_cast<uintptr_t>(src + e_base) & 15u) == 0u) {
+          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(src + e_base));
+          wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
+        } else {
+          for (int bb = 0; bb < 16; ++bb)
+            if (e_base + bb < tot && src[e_base + bb] != 0) wv[bb >> 2] |= 1u << ((bb & 3) * 8);
+        }
+      }
+      uint32_t em = 0;                           // bit b: entry e_base + b is an edge
+#pragma unroll
+      for (int bb = 0; bb < 16; ++bb) em |= ((wv[bb >> 2] >> ((bb & 3) * 8)) & 0xffu) ? (1u << bb) : 0u;
+      const int cnt = __popc(em);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      __syncthreads();                           // the previous chunk's list and warp totals are consumed
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      int base = incl - cnt, ne = 0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        const int tw = s_wtot[w8];
+        if (w8 < warp) base += tw;
+        ne += tw;
+      }
+      if (em) {
+        int row = r0 + e_base / N, col = e_base % N;
+        for (int bb = 0; bb < 16; ++bb) {
+          if (em & (1u << bb)) s_list[base++] = ((uint32_t)row << 16) | (uint32_t)col;
+          if (++col == N) {
+            col = 0;
+            ++row;
+          }
+        }
       }
       __syncthreads();
-      const int ne = *s_count;
       for (int t0 = 0; t0 < ne; t0 += 128, ++it) {
         const int nt = min(128, ne - t0);
         // ---- e1 tile: warp w builds edges 16 w .. 16 w + 15; lane -> 4 consecutive k, so every gather of a_i / b_j
