@@ -457,6 +457,35 @@ def test_rollout_full_size_properties(cuda):
     assert float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()) < 2.5e-2
 
 
+@pytest.mark.parametrize("prec,relational", [("bf16", False), ("bf16-stepwise", False), ("bf16", True), ("f32", False),
+                                             ("f32", True)])
+def test_invalid_slots_never_reach_valid_agents(cuda, prec, relational):
+    """Padding slots of ragged scenes may hold anything -- NaN and Inf included: every output of the valid agents is
+    bit-identical to the run with zeros in those slots (adjacency, aggregation, edge scores and the recurrent state never
+    read them), and the invalid agents' own scores come back as 0 / -1."""
+    S, N, T, P, K = 5, 64, 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=91, half_extent=4.0, ragged=True)
+    assert (valid == 0).any() and (valid != 0).any()
+    dirty_p, dirty_v = pos.copy(), vis.copy()
+    bad = valid == 0
+    fill = np.array([np.nan, np.inf, -np.inf, 1e30], dtype=np.float32)
+    dirty_p[bad] = fill[np.arange(dirty_p[bad].size).reshape(dirty_p[bad].shape) % 4]
+    dirty_v[bad] = np.nan
+    mode = {"bf16": ops.PREC_BF16, "bf16-stepwise": ops.PREC_BF16_STEPWISE, "f32": ops.PREC_F32}[prec]
+    cp = ops.CellParams.from_numpy(synth.init_params(seed=3), cuda)
+    outs = []
+    for a, b in ((pos, vis), (dirty_p, dirty_v)):
+        fc = ops.Forecaster(cp, S, N, T, P, K, relational=relational, prec=mode, seed=7, device=cuda)
+        o = fc(dev(a, cuda), dev(b, cuda), dev(valid, cuda))
+        torch.cuda.synchronize()
+        outs.append({k: v.clone() for k, v in o.items() if v is not None})
+    vm = dev(valid, cuda) != 0
+    for k in ("params", "best_k", "best_ade", "best_fde", "best_traj"):
+        assert torch.equal(outs[0][k][vm], outs[1][k][vm]), k
+        assert bool(torch.isfinite(outs[1][k][vm].float()).all()), k
+    assert bool((outs[1]["best_k"][~vm] == -1).all()) and bool((outs[1]["best_ade"][~vm] == 0).all())
+
+
 # ------------------------------------------------------------------------------------------------
 # training step (teacher-forced NLL, BPTT, RMSProp): oracle = PyTorch autograd in fp64 on the CPU (oracle/train_b.py)
 def test_train_gradients_match_autograd_oracle(cuda):
