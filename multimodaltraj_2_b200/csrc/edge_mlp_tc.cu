@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
 constexpr int EE_LIST = 4096;                       // candidate pairs scanned per chunk (>= edges found)
 constexpr int EE_SM_W2 = 0;                         // 32 KB
 constexpr int EE_SM_A = EE_SM_W2 + EM_W2_BYTES;     // 32 KB
-constexpr int EE_SM_LIST = EE_SM_A + 2 * EM_BLK;    // u32[EE_LIST]: i << 16 | j (scene-local)
-constexpr int EE_SM_PAR = EE_SM_LIST + EE_LIST * 4; // b1[128] b2[128] w_out[128]
+constexpr int EE_SM_LIST = EE_SM_A + 2 * EM_BLK;    // u64[EE_LIST + 128]: scene << 32 | i << 16 | j; + a carried partial tile
+constexpr int EE_SM_PAR = EE_SM_LIST + (EE_LIST + 128) * 8; // b1[128] b2[128] w_out[128]
 constexpr int EE_SM_PART = EE_SM_PAR + 3 * 128 * 4; // float[128]: partial sums of the upper column half
 constexpr int EE_SM_BAR = EE_SM_PART + 512;
 constexpr int EE_SM_TOTAL = EE_SM_BAR + 48 + 32;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
   const uint32_t bar_w = sbase + EE_SM_BAR, bar_mma = bar_w + 8;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + EE_SM_BAR + 16);
   int* s_wtot = reinterpret_cast<int*>(smem + EE_SM_BAR + 48);   // 8 warp totals of the edge scan
-  uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + EE_SM_LIST);
+  unsigned long long* s_list = reinterpret_cast<unsigned long long*>(smem + EE_SM_LIST);
   float* s_b1 = reinterpret_cast<float*>(smem + EE_SM_PAR);
   float* s_b2 = s_b1 + 128;
   float* s_wo = s_b2 + 128;
@@ -194,64 +194,8 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
   const int rows_per_chunk = EE_LIST / N > 0 ? EE_LIST / N : 1;
   uint32_t it = 0;
 
-  for (int s = blockIdx.x; s < S; s += gridDim.x) {
-    float* sc = score + (size_t)s * N * N;
-    const uint8_t* ad = adj + (size_t)s * N * N;
-    const __nv_bfloat16* nab_s = nab + (size_t)s * N * 256;
-    if (zero_fill)
-      for (int i = tid; i < (N * N) >> 2; i += 256) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r0 = 0; r0 < N; r0 += rows_per_chunk) {
-      // ---- compact the edges of rows [r0, r1): every thread takes 16 consecutive entries of the adjacency block (one
-      //      128-bit load; the byte-at-a-time walk with a ballot and a shared atomic per 256 entries was 57 % of the
-      //      kernel's stall samples, almost all of it the latency of 16 dependent rounds of 1-byte loads), counts its
-      //      edges, and a block-wide exclusive scan gives its place in the list -- ascending (row, column) order
-      const int r1 = min(N, r0 + rows_per_chunk);
-      const int tot = (r1 - r0) * N;             // <= EE_LIST = 16 x 256
-      const uint8_t* src = ad + (size_t)r0 * N;
-      const int e_base = tid * 16;
-      uint32_t wv[4] = {0u, 0u, 0u, 0u};
-      if (e_base < tot) {
-        if (e_base + 16 <= tot && (reinterpret_cast<uintptr_t>(src + e_base) & 15u) == 0u) {
-          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(src + e_base));
-          wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
-        } else {
-          for (int bb = 0; bb < 16; ++bb)
-            if (e_base + bb < tot && src[e_base + bb] != 0) wv[bb >> 2] |= 1u << ((bb & 3) * 8);
-        }
-      }
-      uint32_t em = 0;                           // bit b: entry e_base + b is an edge
-#pragma unroll
-      for (int bb = 0; bb < 16; ++bb) em |= ((wv[bb >> 2] >> ((bb & 3) * 8)) & 0xffu) ? (1u << bb) : 0u;
-      const int cnt = __popc(em);
-      int incl = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      __syncthreads();                           // the previous chunk's list and warp totals are consumed
-      if (lane == 31) s_wtot[warp] = incl;
-      __syncthreads();
-      int base = incl - cnt, ne = 0;
-#pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) {
-        const int tw = s_wtot[w8];
-        if (w8 < warp) base += tw;
-        ne += tw;
-      }
-      if (em) {
-        int row = r0 + e_base / N, col = e_base % N;
-        for (int bb = 0; bb < 16; ++bb) {
-          if (em & (1u << bb)) s_list[base++] = ((uint32_t)row << 16) | (uint32_t)col;
-          if (++col == N) {
-            col = 0;
-            ++row;
-          }
-        }
-      }
-      __syncthreads();
-      for (int t0 = 0; t0 < ne; t0 += 128, ++it) {
-        const int nt = min(128, ne - t0);
+  // one tile of up to 128 edges of the list: gather -> e1 operand -> MMA against W2 -> epilogue -> scatter
+  auto edge_tile = [&](int t0, int nt) {
         // ---- e1 tile: warp w builds edges 16 w .. 16 w + 15; lane -> 4 consecutive k, so every gather of a_i / b_j
         //      is one coalesced 512-byte row (a thread-per-edge walk made each load instruction touch 32 sectors
         //      and the tile took ~20 k clk); four edges in flight per warp
@@ -268,7 +212,9 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
               const int e = warp * 16 + e0 + u;
               av[u] = bv[u] = make_uint2(0u, 0u);
               if (e < nt) {
-                const uint32_t ij = s_list[t0 + e];
+                const unsigned long long en = s_list[t0 + e];
+                const uint32_t ij = (uint32_t)en;
+                const __nv_bfloat16* nab_s = nab + (size_t)(en >> 32) * N * 256;
                 av[u] = __ldg(reinterpret_cast<const uint2*>(nab_s + (size_t)(ij >> 16) * 256) + lane);
                 bv[u] = __ldg(reinterpret_cast<const uint2*>(nab_s + (size_t)(ij & 0xffffu) * 256 + 128) + lane);
               }
@@ -329,15 +275,82 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
           tc_fence_before();
           __syncthreads();   // partial sums visible; TMEM drained; A block free
           if (half == 0 && r < nt) {
-            const uint32_t ij = s_list[t0 + r];
+            const unsigned long long en = s_list[t0 + r];
+            const uint32_t ij = (uint32_t)en;
             const float z = part + s_part[r] + bo;
-            sc[(size_t)(ij >> 16) * N + (ij & 0xffffu)] = 1.0f / (1.0f + __expf(-z));
+            score[((size_t)(en >> 32) * N + (ij >> 16)) * N + (ij & 0xffffu)] = 1.0f / (1.0f + __expf(-z));
+          }
+        }
+    ++it;
+  };
+  // A 64-agent scene has ~190 edges = 1.5 tiles: the partial tile at the end of a scene (or chunk) is not run half empty but
+  // carried to the front of the next list (entries name their scene), and flushed once after the CTA's last scene
+  int carry = 0;
+  for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    float* sc = score + (size_t)s * N * N;
+    const uint8_t* ad = adj + (size_t)s * N * N;
+    if (zero_fill)
+      for (int i = tid; i < (N * N) >> 2; i += 256) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < N; r0 += rows_per_chunk) {
+      // ---- compact the edges of rows [r0, r1): every thread takes 16 consecutive entries of the adjacency block (one
+      //      128-bit load; the byte-at-a-time walk with a ballot and a shared atomic per 256 entries was 57 % of the
+      //      kernel's stall samples, almost all of it the latency of 16 dependent rounds of 1-byte loads), counts its
+      //      edges, and a block-wide exclusive scan gives its place in the list -- ascending (row, column) order
+      const int r1 = min(N, r0 + rows_per_chunk);
+      const int tot = (r1 - r0) * N;             // <= EE_LIST = 16 x 256
+      const uint8_t* src = ad + (size_t)r0 * N;
+      const int e_base = tid * 16;
+      uint32_t wv[4] = {0u, 0u, 0u, 0u};
+      if (e_base < tot) {
+        if (e_base + 16 <= tot && (reinterpret_cast<uintptr_t>(src + e_base) & 15u) == 0u) {
+          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(src + e_base));
+          wv[0] = v4.x; wv[1] = v4.y; wv[2] = v4.z; wv[3] = v4.w;
+        } else {
+          for (int bb = 0; bb < 16; ++bb)
+            if (e_base + bb < tot && src[e_base + bb] != 0) wv[bb >> 2] |= 1u << ((bb & 3) * 8);
+        }
+      }
+      uint32_t em = 0;                           // bit b: entry e_base + b is an edge
+#pragma unroll
+      for (int bb = 0; bb < 16; ++bb) em |= ((wv[bb >> 2] >> ((bb & 3) * 8)) & 0xffu) ? (1u << bb) : 0u;
+      const int cnt = __popc(em);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      __syncthreads();                           // the previous chunk's list and warp totals are consumed
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      int base = carry + incl - cnt, ne = 0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        const int tw = s_wtot[w8];
+        if (w8 < warp) base += tw;
+        ne += tw;
+      }
+      if (em) {
+        int row = r0 + e_base / N, col = e_base % N;
+        for (int bb = 0; bb < 16; ++bb) {
+          if (em & (1u << bb)) s_list[base++] = ((unsigned long long)s << 32) | ((uint32_t)row << 16) | (uint32_t)col;
+          if (++col == N) {
+            col = 0;
+            ++row;
           }
         }
       }
+      __syncthreads();
+      const int n_all = carry + ne;
+      const int n_full = n_all & ~127;
+      for (int t0 = 0; t0 < n_full; t0 += 128) edge_tile(t0, 128);
+      __syncthreads();   // the scatter of the last tile has read the list
+      carry = n_all - n_full;
+      if (n_full > 0 && tid < carry) s_list[tid] = s_list[n_full + tid];   // n_full >= 128 > carry: no overlap
       __syncthreads();   // the list is rebuilt by the next chunk
     }
   }
+  if (carry > 0) edge_tile(0, carry);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 128);
