@@ -556,14 +556,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
             const int u0 = p * RO_UN + cs * 8;        // first of this thread's 8 units
             uint32_t hw[4], cw[4];                    // h', c' as bf16 pairs
-            float zi[2][4], zj[2][4], zo[2][4], zm[2][4];
-#pragma unroll
-            for (int hq = 0; hq < 2; ++hq) {
-              tmem_ld4(t_acc + hq * 4, zi[hq]);
-              tmem_ld4(t_acc + RO_UN + hq * 4, zj[hq]);
-              tmem_ld4(t_acc + 2 * RO_UN + hq * 4, zo[hq]);
-              tmem_ld4(t_row + RT_MC + u0 + hq * 4, zm[hq]);
-            }
+            float zi[2][4], zj[2][4], zo[2][4], zm[2][4];   // [unit quad][unit]: one 8-column load per array
+            tmem_ld8(t_acc, &zi[0][0]);
+            tmem_ld8(t_acc + RO_UN, &zj[0][0]);
+            tmem_ld8(t_acc + 2 * RO_UN, &zo[0][0]);
+            tmem_ld8(t_row + RT_MC + u0, &zm[0][0]);
             tmem_wait_ld();
 #pragma unroll
             for (int hq = 0; hq < 2; ++hq) {
