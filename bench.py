@@ -24,9 +24,30 @@ from pathlib import Path
 
 import numpy as np
 
-# rank 0 prints ONE JSON line on stdout: NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print its version line there too
+# rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+# communicator of a process whenever NCCL_DEBUG=VERSION comes from the environment or from a configuration file): file
+# descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved original descriptor.
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -154,7 +175,7 @@ def run_reference(args, rank, world):
                                        f"oracle of the whole path on {cores} processes, 1 BLAS thread each "
                                        f"(TF 1.14 reference not installable offline)"},
             "e2e": {"value": val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config(args, scenes_per_rank, reference=False):
@@ -400,7 +421,7 @@ def run_ours(args, rank, world, local_rank):
                                            f"(host has {cores} cores; TF 1.14 reference not installable offline)"},
                 "ade_fde": {"best_of_k_ade": ade, "best_of_k_fde": fde, "note": "random-init weights, synthetic data"},
                 "lib": str(_lib.lib_path().relative_to(ROOT))}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -453,7 +474,7 @@ def run_train(args, rank, world, local_rank):
     else:
         in_sync = True
     if rank == 0:
-        print(json.dumps({"mode": "train", "metric": "agent-trajectories/sec (training step: teacher-forced NLL + BPTT + gradient all-reduce + RMSProp)",
+        emit({"mode": "train", "metric": "agent-trajectories/sec (training step: teacher-forced NLL + BPTT + gradient all-reduce + RMSProp)",
                           "value": int(valid_h.sum()) * world / (ms_step * 1e-3), "unit": "agent-trajectories/s", "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None,
@@ -463,7 +484,7 @@ def run_train(args, rank, world, local_rank):
                                      "backward_gemm": args.train_gemm, "lr": 1e-3,
                                      "gradient_bucket_bytes": int(w.numel() * 4), "collective": "one NCCL all-reduce (SUM) per step" if world > 1 else "none (1 GPU)"},
                           "loss_first": losses[0], "loss_last": float(loss), "weights_identical_across_ranks": in_sync,
-                          "gpu_launches": int(ops.launch_count() - l0)}), flush=True)
+                          "gpu_launches": int(ops.launch_count() - l0)})
     if world > 1:
         dist.destroy_process_group()
 
@@ -487,6 +508,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.mode == "train":
