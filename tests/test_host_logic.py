@@ -231,3 +231,17 @@ def test_checkpoint_save_resume_round_trip(tmp_path):
     save_checkpoint(tmp_path / "w.pt", p)
     p3 = load_checkpoint(tmp_path / "w.pt", device="cpu")
     assert torch.equal(p3.W, p.W)
+
+
+def test_bench_prints_one_json_line_on_stdout():
+    """bench.py's contract: ONE JSON line on stdout.  Anything a library prints to file descriptor 1 (NCCL's version
+    banner at N > 1) must end up on stderr: the line goes to the saved original descriptor."""
+    import json
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._claim_stdout(); "
+            "print('library noise'); os.write(1, b'raw noise\\n'); bench.emit({'metric': 'm', 'value': 1.5})" % str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"metric": "m", "value": 1.5}
+    assert "library noise" in r.stderr and "raw noise" in r.stderr
