@@ -198,3 +198,40 @@ def test_ade_fde_world_oracle_identities():
     valid = np.array([1, 0, 1, 1, 0, 1, 1], np.uint8)
     ade3, fde3 = o_sc.ade_fde_world(pred, gt, Hs, valid)
     assert np.all(ade3[valid == 0] == 0) and np.all(fde3[valid == 0] == 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases of the batched path on the oracle: empty scene, lone agent, no scenes at all, and
+# noise keyed by the global agent index (two shards == the whole batch)
+def test_track_b_edge_cases_empty_scene_lone_agent_and_shard_independence():
+    sys.path.insert(0, str(ROOT))
+    from multimodaltraj_2_b200 import synth
+    S, N, T, P, K = 4, 8, 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=11, half_extent=2.0, ragged=True)
+    valid[1] = 0                      # a scene with nobody in it
+    valid[2] = 0
+    valid[2, 3] = 1                   # a lone agent in a middle slot: no neighbours at any step
+    p = synth.init_params(seed=2)
+    eps = o_b.philox_eps(7, S, N, K, P)
+    o = o_b.forecast(pos, vis, valid, p, eps, T, P)
+    assert np.all(np.isfinite(o["params"])) and np.all(np.isfinite(o["ade"]))
+    assert np.all(o["best_k"][1] == -1) and np.all(o["params"][1] == 0) and np.all(o["best_traj"][1] == 0)
+    assert o["best_k"][2, 3] >= 0 and np.all(np.delete(o["best_k"][2], 3) == -1)
+    # the lone agent aggregates nothing: same result as a scene holding only that agent
+    solo = o_b.forecast(pos[2:3, 3:4], vis[2:3, 3:4], valid[2:3, 3:4], p, eps[2:3, 3:4], T, P)
+    # (to rounding: the BLAS contraction order depends on the batch shape)
+    np.testing.assert_allclose(solo["params"][0, 0], o["params"][2, 3], rtol=1e-5, atol=1e-6)
+    assert solo["best_k"][0, 0] == o["best_k"][2, 3]
+    tr = o_b.rollout(pos, vis, valid, p, T, P, trace=True)["trace"]
+    assert all(d[1].sum() == 0 and d[2].sum() == 0 for d in tr["deg"])
+    # zero scenes: shapes survive, nothing is computed
+    z = o_b.forecast(pos[:0], vis[:0], valid[:0], p, eps[:0], T, P)
+    assert z["params"].shape == (0, N, P, 5) and z["best_k"].shape == (0, N)
+    # shards: rank r draws the noise of its own global agent indices
+    lo, hi = o_b.philox_eps(7, 2, N, K, P), o_b.philox_eps(7, 2, N, K, P, agent_offset=2 * N)
+    np.testing.assert_array_equal(np.concatenate([lo, hi]), eps)
+    a = o_b.forecast(pos[:2], vis[:2], valid[:2], p, lo, T, P)
+    b = o_b.forecast(pos[2:], vis[2:], valid[2:], p, hi, T, P)
+    np.testing.assert_array_equal(np.concatenate([a["best_k"], b["best_k"]]), o["best_k"])
+    for k in ("ade", "fde", "best_traj"):
+        np.testing.assert_allclose(np.concatenate([a[k], b[k]]), o[k], rtol=1e-5, atol=1e-6)
