@@ -52,6 +52,39 @@ def emit(line):
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+_STAGE = ["start"]
+
+
+def stage(name):
+    """Progress marker on stderr (one line per phase and rank): a failure names the phase it happened in."""
+    _STAGE[0] = name
+    sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] {name} t={time.perf_counter():.1f}\n")
+    sys.stderr.flush()
+
+
+def record_failure(exc):
+    """Per-rank post-mortem under gpurun_out/ (and stderr): traceback, phase, libmmt's last error and trap record."""
+    import traceback
+    rank = os.environ.get("RANK", "0")
+    info = {"rank": rank, "stage": _STAGE[0], "error": repr(exc)}
+    try:
+        from multimodaltraj_2_b200 import _lib
+        if _lib._lib is not None:
+            msg = _lib._lib.mmt_last_error()
+            info["mmt_last_error"] = msg.decode() if msg else ""
+            info["mmt_last_trap"] = _lib.last_trap()
+    except Exception as e2:          # the post-mortem must not mask the failure
+        info["postmortem_error"] = repr(e2)
+    text = json.dumps(info) + "\n" + traceback.format_exc()
+    sys.stderr.write(f"[bench rank {rank}] FAILED in stage '{_STAGE[0]}':\n{text}\n")
+    sys.stderr.flush()
+    try:
+        out = ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        (out / f"rank{rank}.err").write_text(text)
+    except OSError:
+        pass
+
 T_OBS, P_PRED, K_SAMPLES, HIDDEN, EMBED = 8, 12, 20, 128, 64
 R2, INV_2SIGMA2 = 4.0, 0.5
 
@@ -155,9 +188,9 @@ def run_reference(args, rank, world):
     per = 8                                        # scenes per process per step (~40 ms of numpy each)
     N = args.agents
     n_scenes = per * cores
-    steps = max(1, min(args.steps, 5))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)   # as given: a step is ~0.1 s of wall time (8 scenes per core)
     with mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(per, N, args.variant, 7)) as pool:
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(warmup):
             pool.map(_cpu_step, range(cores), chunksize=1)
         ts = []
         for _ in range(steps):
@@ -167,7 +200,7 @@ def run_reference(args, rank, world):
     t = float(np.mean(ts))
     val = n_scenes * N / t
     line = {"impl": "reference", "metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": val,
-            "unit": "agent-trajectories/s", "n_gpus": world, "steps": len(ts), "warmup": max(1, min(args.warmup, 2)),
+            "unit": "agent-trajectories/s", "n_gpus": world, "steps": len(ts), "warmup": warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config(args, n_scenes, reference=True),
             "cpu_baseline": {"value": val, "unit": "agent-trajectories/s", "cores": cores, "kind": "port",
@@ -224,11 +257,14 @@ def run_ours(args, rank, world, local_rank):
         step_no[0] += 1
         return fc(p_, v_, m_)
 
+    stage("graph capture")
     for st in sets:                      # first call per input set: eager validation + CUDA-graph capture (untimed)
         fc(*st)
+    stage("warmup")
     for _ in range(args.warmup):
         step()
     barrier()
+    stage("timed steps")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -239,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
         out = step()
     e1.record()
     barrier()
+    stage("timed steps done")
     launches = ops.launch_count() - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
@@ -283,8 +320,10 @@ def run_ours(args, rank, world, local_rank):
         ev_done[(n - 1) & 1].synchronize()
         return res_h[(n - 1) & 1]
 
+    stage("e2e warmup")
     e2e_run(3)
     barrier()
+    stage("e2e timed")
     n_e2e = max(4, min(args.steps, 50))       # long enough that the fill of the two-deep pipeline (one exposed H2D copy) is amortised
     t0 = time.perf_counter()
     last = e2e_run(n_e2e)
@@ -296,6 +335,7 @@ def run_ours(args, rank, world, local_rank):
     h2d = pos_p.numel() * 4 + vis_p.numel() * 4 + valid_p.numel()
     ade, fde = float(last[0]), float(last[1])
 
+    stage("roofline kernels")
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream
     R = S * N
     pk = peaks()
@@ -398,6 +438,8 @@ def run_ours(args, rank, world, local_rank):
                "traffic": None, "ms_per_launch": pw_ms,
                "workload": f"{S * T_OBS} scene-frames x {N} agents (all observed frames of the batch), 690 MB written"}
 
+    torch.cuda.synchronize()
+    stage("gpu phases done")
     if rank == 0:
         cores = os.cpu_count() or 1
         # CPU baseline on a bounded sample of the same workload: a small probe sizes it for ~10 s of CPU work
@@ -422,8 +464,11 @@ def run_ours(args, rank, world, local_rank):
                 "ade_fde": {"best_of_k_ade": ade, "best_of_k_fde": fde, "note": "random-init weights, synthetic data"},
                 "lib": str(_lib.lib_path().relative_to(ROOT))}
         emit(line)
+    stage("teardown")
     if world > 1:
+        dist.barrier()               # rank 0 spent ~20 s in the CPU baseline: leave together
         dist.destroy_process_group()
+    stage("done")
 
 
 def run_train(args, rank, world, local_rank):
@@ -509,13 +554,23 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     _claim_stdout()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    elif args.mode == "train":
-        run_train(args, rank, world, local_rank)
-    else:
-        run_ours(args, rank, world, local_rank)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        elif args.mode == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
+    except BaseException as exc:     # noqa: BLE001 -- post-mortem, then the original failure propagates
+        if not isinstance(exc, SystemExit) or exc.code not in (0, None):
+            record_failure(exc)
+        raise
 
 
 if __name__ == "__main__":
+    try:
+        from torch.distributed.elastic.multiprocessing.errors import record
+        main = record(main)          # torchrun then shows this rank's traceback instead of "error_file: <N/A>"
+    except Exception:                # noqa: BLE001
+        pass
     main()

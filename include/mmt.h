@@ -40,6 +40,16 @@ extern "C" {
 
 int mmt_version(void);
 const char* mmt_last_error(void);
+/* SM count of the current device (grids are sized from it; queried once per device). */
+int mmt_num_sms(void);
+/* Diagnostics of a device-side trap.  The tcgen05 kernels bound every mbarrier wait and check the alignment of
+ * their shared-memory base; a violated bound ends the launch with cudaErrorLaunchFailure (719), which by itself
+ * names nothing.  Before trapping, the kernel writes (site, CTA, thread, barrier address, parity) into a block
+ * of host-mapped pinned memory owned by the library (64 bytes, allocated at the first tensor-core launch, the one
+ * exception to "never allocates": it is HOST memory and survives the dead context).  Returns 1 and fills out[8]
+ * = {site (kernel << 8 | wait), CTA, thread, barrier smem address, parity, extra, 0, 0} if a trap was recorded,
+ * else 0.  The same text is appended to mmt_last_error() of the first failing launch check after the trap. */
+int mmt_last_trap(uint32_t out[8]);
 
 /* ---- pairwise distance kernel + adjacency ------------------------------------------------
  * Replaces networkx_graph.py:71 (dist_mat, never filled) and :83-85 (L2 edge norm) with the

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mmt_version": (C.c_int, []),
     "mmt_last_error": (C.c_char_p, []),
     "mmt_launch_count": (C.c_uint64, []),
+    "mmt_num_sms": (C.c_int, []),
+    "mmt_last_trap": (C.c_int, [C.POINTER(C.c_uint32)]),
     "mmt_pairwise_adj_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),
     "mmt_neighbor_index_i32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "mmt_aggregate_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
@@ -113,6 +115,16 @@ def load(build_if_missing: bool = True):
         raise RuntimeError(f"libmmt version mismatch: {lib.mmt_version()}")
     _lib = lib
     return lib
+
+
+def last_trap():
+    """Record a trapping tcgen05 kernel left in host-mapped memory (mmt_last_trap), or None."""
+    if _lib is None:
+        return None
+    out = (C.c_uint32 * 8)()
+    if not _lib.mmt_last_trap(out):
+        return None
+    return {"site": hex(out[0]), "cta": out[1], "thread": out[2], "barrier_smem": hex(out[3]), "parity": out[4]}
 
 
 def check(rc: int, what: str = "libmmt"):

@@ -88,8 +88,12 @@ int launch_aggregate(const float* logits, const float* logits2, const uint8_t* a
                      int C, int ld_feat, float* attn, float* out, int ld_out, cudaStream_t stream) {
   const long rows = (long)S * N;
   long blocks = (rows + kAggWarps - 1) / kAggWarps;
-  int grid = blocks < (long)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   const size_t smem = (size_t)kAggWarps * N * 8;
+  if (smem > 48 * 1024) {   // N > 768: beyond the default dynamic shared-memory limit (N <= 1024 -> 64 KB)
+    static unsigned long long smem_opted[1] = {};
+    if (int rc = opt_in_smem(reinterpret_cast<const void*>(&aggregate_kernel), kAggWarps * 1024 * 8, &smem_opted[0])) return rc;
+  }
   aggregate_kernel<<<grid, kAggWarps * 32, smem, stream>>>(logits, logits2, adj, feat, (int)rows, N, C, ld_feat, attn,
                                                            out, ld_out);
   count_launch();

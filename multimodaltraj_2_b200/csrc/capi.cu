@@ -2,7 +2,10 @@
 // mmt_gsk_cell entry point that dispatches between the fp32 and the tcgen05/bf16 cell kernels.
 #include <atomic>
 #include <cstdarg>
+#include <climits>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "mmt_common.cuh"
 
@@ -20,13 +23,84 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+static std::atomic<uint32_t*> g_trap{nullptr};
+static std::mutex g_mu;
+
+uint32_t* trap_record() {
+  uint32_t* p = g_trap.load(std::memory_order_acquire);
+  if (p) return p;
+  std::lock_guard<std::mutex> lk(g_mu);
+  p = g_trap.load(std::memory_order_relaxed);
+  if (p) return p;
+  void* h = nullptr;
+  if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();   // not sticky: the kernels then trap without a record
+    return nullptr;
+  }
+  memset(h, 0, 64);
+  g_trap.store(static_cast<uint32_t*>(h), std::memory_order_release);
+  return static_cast<uint32_t*>(h);
+}
+
+// "<kernel>/<wait>" of a trap site code (tc_common.cuh: trap_report).  Kernel ids: 1 rollout_tc, 2 gsk_cell_tc,
+// 3 graph_aggregate_mma, 4 node_proj_tc, 5 edge_mlp_tc; wait 0xFF = shared-memory base not 1024-byte aligned.
+static void describe_trap(char* out, size_t n) {
+  const uint32_t* r = g_trap.load(std::memory_order_acquire);
+  if (!r || r[0] == 0) { out[0] = 0; return; }
+  static const char* kern[] = {"?", "rollout_tc_kernel", "gsk_cell_tc_kernel", "graph_aggregate_mma_kernel",
+                               "node_proj_tc_kernel", "edge_mlp_tc_kernel"};
+  const uint32_t k = r[0] >> 8, w = r[0] & 0xFFu;
+  snprintf(out, n, " [device trap: %s site 0x%02x%s, CTA %u thread %u, barrier smem 0x%x parity %u]",
+           k < 6 ? kern[k] : "?", w, w == 0xFF ? " (smem base misaligned)" : " (bounded mbarrier wait expired)", r[1], r[2],
+           r[3], r[4]);
+}
+
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    set_error("%s: %s", what, cudaGetErrorString(e));
+    char trap[256];
+    describe_trap(trap, sizeof(trap));
+    set_error("%s: %s%s", what, cudaGetErrorString(e), trap);
     return MMT_ECUDA;
   }
   return MMT_OK;
+}
+
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
+int opt_in_smem(const void* func, int bytes, unsigned long long* done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+  const unsigned long long bit = 1ull << (dev & 63);
+  auto* mask = reinterpret_cast<std::atomic<unsigned long long>*>(done);
+  if (mask->load(std::memory_order_acquire) & bit) return MMT_OK;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) on device %d: %s", bytes, dev, cudaGetErrorString(e));
+    return MMT_ECUDA;
+  }
+  mask->fetch_or(bit, std::memory_order_release);
+  return MMT_OK;
+}
+
+int env_int_once(const char* name, int* cache) {   // *cache: INT_MIN until read
+  auto* c = reinterpret_cast<std::atomic<int>*>(cache);
+  int v = c->load(std::memory_order_relaxed);
+  if (v != INT_MIN) return v;
+  const char* s = getenv(name);
+  v = s ? atoi(s) : 0;
+  c->store(v, std::memory_order_relaxed);
+  return v;
 }
 
 int launch_cell_f32(const float* x, const float* h, const float* c, const float* mh, const float* mc,
@@ -45,6 +119,12 @@ int launch_cell_tc(const float* x, const float* h, const float* c, const float* 
 extern "C" int mmt_version(void) { return MMT_VERSION; }
 extern "C" const char* mmt_last_error(void) { return mmt::g_err; }
 extern "C" uint64_t mmt_launch_count(void) { return mmt::g_launches.load(std::memory_order_relaxed); }
+extern "C" int mmt_last_trap(uint32_t out[8]) {
+  const uint32_t* r = mmt::g_trap.load(std::memory_order_acquire);
+  for (int i = 0; i < 8; ++i) out[i] = r ? r[i] : 0u;
+  return (r && r[0]) ? 1 : 0;
+}
+extern "C" int mmt_num_sms(void) { return mmt::num_sms(); }
 
 extern "C" int mmt_gsk_cell(const float* x, const float* h, const float* c, const float* mh, const float* mc,
                             const uint8_t* valid, const mmt_cell_weights* w, int R, int prec, float* h_out,

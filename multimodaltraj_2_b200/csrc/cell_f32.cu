@@ -216,7 +216,7 @@ int launch_cell_f32(const float* x, const float* h, const float* c, const float*
 int launch_head(const float* mt, int ld, const float* mf, int ld_mf, const uint8_t* valid, const mmt_cell_weights* w, int R,
                 const float* cur_pos, float* params_out, int params_stride, float* next_pos, cudaStream_t stream) {
   long blocks = ((long)R + 7) / 8;
-  int grid = blocks < (long)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   head_kernel<<<grid, 256, 0, stream>>>(mt, ld, mf, ld_mf, valid, w->W_h, w->b_h, R, w->U, cur_pos, params_out,
                                         params_stride, next_pos);
   count_launch();

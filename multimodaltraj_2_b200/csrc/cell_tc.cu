@@ -66,6 +66,7 @@ struct TcArgs {
   float *params_out, *next_pos;
   int R, ld, ld_mf, params_stride, num_tiles;
   long long* dbg;  // optional [CTA][tile_iter][16] clock64 timestamps of worker thread 0 (diagnostics)
+  uint32_t* trap;  // host-mapped trap record (tc_common.cuh: trap_report); may be null
 };
 
 // State layouts.  LAY 0: fp32 row-major [R,ld] in/out (the mmt_gsk_cell API).  LAY 1: bf16 h/mh/mc, fp32 c,
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
   // constant and the barrier addresses / descriptors derived from it are uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* const smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  require_smem_alignment(smem, a.trap, 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         for (int p = 0; p < TC_NP; ++p)
           for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
             const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
-            mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
+            mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, a.trap, 0x201);
             mbar_arrive_expect_tx(W_FULL + 8 * s, TC_STAGE_BYTES);
             bulk_g2s(sbase + SM_W + s * TC_STAGE_BYTES, a.Wp + (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES,
                      TC_STAGE_BYTES, W_FULL + 8 * s);
@@ -145,16 +146,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
     if (lane == 0) {
       uint32_t it = 0, pc = 0, tc = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tc) {
-        mbar_wait(A_READY, tc & 1u);
+        mbar_wait(A_READY, tc & 1u, a.trap, 0x202);
         tc_fence_after();
         for (int p = 0; p < TC_NP; ++p, ++pc) {
           const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
-          mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u);
+          mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u, a.trap, 0x203);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + b * TC_ACC_STRIDE;
           for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
             const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
-            mbar_wait(W_FULL + 8 * s, ph);   // written by the async proxy: no tcgen05 fence needed
+            mbar_wait(W_FULL + 8 * s, ph, a.trap, 0x204);   // written by the async proxy: no tcgen05 fence needed
             const uint64_t da = make_desc_sw128(sbase + SM_A + kc * TC_A_BLOCK);
             const uint64_t db = make_desc_sw128(sbase + SM_W + s * TC_STAGE_BYTES);
 #pragma unroll
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
         if (sub == 0) {
           if (dbg) dbg[2 + 3 * p] = clock64();
-          mbar_wait(ACC_FULL + 8 * b, bph);
+          mbar_wait(ACC_FULL + 8 * b, bph, a.trap, 0x205);
           if (dbg) dbg[3 + 3 * p] = clock64();
           tc_fence_after();
         }
@@ -468,12 +469,10 @@ static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
 template <int LAY>
 static int tc_launch(TcArgs& a, cudaStream_t stream) {
   a.num_tiles = (a.R + TC_M - 1) / TC_M;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gsk_cell_tc_kernel<LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024);
-    attr_set = true;
-  }
-  const int grid = a.num_tiles < 2 * kNumSMs ? a.num_tiles : 2 * kNumSMs;
+  a.trap = trap_record();
+  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY>), SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  const int grid = a.num_tiles < 2 * num_sms() ? a.num_tiles : 2 * num_sms();
   gsk_cell_tc_kernel<LAY><<<grid, TC_THREADS, SM_TOTAL + 1024, stream>>>(a);
   count_launch();
   return check_launch("gsk_cell_tc_kernel");

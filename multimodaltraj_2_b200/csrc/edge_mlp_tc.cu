@@ -52,10 +52,10 @@ constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
 template <bool BLOCKED>
 __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
                                                               const uint8_t* __restrict__ Wp, __nv_bfloat16* __restrict__ out,
-                                                              int num_tiles) {
+                                                              int num_tiles, uint32_t* trap) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
   uint8_t* const smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  require_smem_alignment(smem, trap, 4);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_w = sbase + NP_SM_BAR, bar_mma = bar_w + 8;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  mbar_wait(bar_w, 0);
+  mbar_wait(bar_w, 0, trap, 0x401);
 
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
       }
       umma_commit(bar_mma);
     }
-    mbar_wait(bar_mma, it & 1u);
+    mbar_wait(bar_mma, it & 1u, trap, 0x402);
     tc_fence_after();
     // epilogue: warp w -> rows 32 (w % 4) .., columns 128 (w / 4) ..  TMEM gives a lane one ROW; stored directly that
     // is 32 rows x 16 B per instruction.  Each warp instead transposes 32 x 32 blocks through its 4 KB slice of the
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
                                                              const uint8_t* __restrict__ adj, const uint8_t* __restrict__ Wp,
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
                                                              const float* __restrict__ w_out, const float* __restrict__ b_out,
-                                                             int S, int N, float* __restrict__ score, int zero_fill) {
+                                                             int S, int N, float* __restrict__ score, int zero_fill, uint32_t* trap) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
   uint8_t* const smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  require_smem_alignment(smem, trap, 5);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_w = sbase + EE_SM_BAR, bar_mma = bar_w + 8;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const float bo = __ldg(b_out);
-  mbar_wait(bar_w, 0);
+  mbar_wait(bar_w, 0, trap, 0x501);
   const int rows_per_chunk = EE_LIST / N > 0 ? EE_LIST / N : 1;
   uint32_t it = 0;
 
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
           }
           umma_commit(bar_mma);
         }
-        mbar_wait(bar_mma, it & 1u);
+        mbar_wait(bar_mma, it & 1u, trap, 0x502);
         tc_fence_after();
         // ---- epilogue: thread -> (edge row, 64 columns): sum_c elu(acc + b2) * w_out
         {
@@ -361,24 +361,21 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
 int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
                        int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(node_proj_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
-    cudaFuncSetAttribute(node_proj_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_SM_TOTAL + 1024);
-    cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EE_SM_TOTAL + 1024);
-    attr_set = true;
-  }
+  static unsigned long long smem_opted[3] = {};   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<false>), NP_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<true>), NP_SM_TOTAL + 1024, &smem_opted[1])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&edge_mlp_tc_kernel), EE_SM_TOTAL + 1024, &smem_opted[2])) return rc;
   const uint8_t* Wp = reinterpret_cast<const uint8_t*>(packed);
-  int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   __nv_bfloat16* nabh = reinterpret_cast<__nv_bfloat16*>(nab);   // R x 256 bf16 inside the R x 256 float scratch
-  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nabh, tiles);
-  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nabh, tiles);
+  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nabh, tiles, trap_record());
+  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nabh, tiles, trap_record());
   count_launch();
   int rc = check_launch("node_proj_tc_kernel");
   if (rc) return rc;
-  grid = S < 2 * kNumSMs ? S : 2 * kNumSMs;
+  grid = S < 2 * num_sms() ? S : 2 * num_sms();
   edge_mlp_tc_kernel<<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nabh, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
-                                                                zero_fill);
+                                                                zero_fill, trap_record());
   count_launch();
   return check_launch("edge_mlp_tc_kernel");
 }

@@ -94,7 +94,7 @@ int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const vo
   }
   const long rows = (long)S * N;
   long blocks = (rows + kGaWarps - 1) / kGaWarps;
-  int grid = blocks < (long)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   const size_t smem = (size_t)kGaWarps * N * 8;
   graph_aggregate_bf16_kernel<<<grid, kGaWarps * 32, smem, stream>>>(
       pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, (int)rows, N, U, r2, inv_2sigma2,
@@ -234,12 +234,9 @@ int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const
                                    float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   const size_t smem = 128 * GB_HROW * 2 + 128 * GB_CROW * 4 + 128 * 8 + (size_t)8 * N * 8 + 128 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(graph_aggregate_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    attr_set = true;
-  }
-  const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_blocked_kernel), 112 * 1024, &smem_opted[0])) return rc;
+  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   graph_aggregate_blocked_kernel<<<grid, GB_THREADS, smem, stream>>>(
       pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, R, N, r2, inv_2sigma2,
       reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);

@@ -45,10 +45,10 @@ __device__ __forceinline__ uint64_t gm_desc_mn(uint32_t smem_addr) {   // LBO = 
 __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
     const float* __restrict__ c, const float* __restrict__ score, int R, int N, float r2, float neg_inv_log2e,
-    __nv_bfloat16* __restrict__ mhb, __nv_bfloat16* __restrict__ mcb, int num_tiles) {
+    __nv_bfloat16* __restrict__ mhb, __nv_bfloat16* __restrict__ mcb, int num_tiles, uint32_t* trap) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];   // link-time constant base: uniform addresses / descriptors
   uint8_t* const smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  require_smem_alignment(smem, trap, 3);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float2* spos = reinterpret_cast<float2*>(smem + GM_SM_POS);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
         }
         umma_commit(bar);
       }
-      mbar_wait(bar, it & 1u);   // operands free for the next K block / accumulator complete
+      mbar_wait(bar, it & 1u, trap, 0x301);   // operands free for the next K block / accumulator complete
       tc_fence_after();
     }
     ssum[jhalf * 128 + i] = sum;
@@ -212,15 +212,12 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
                                int S, int N, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(graph_aggregate_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SM_TOTAL + 1024);
-    attr_set = true;
-  }
-  const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_mma_kernel), GM_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   graph_aggregate_mma_kernel<<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(
       pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, score, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
-      reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);
+      reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles, trap_record());
   count_launch();
   return check_launch("graph_aggregate_mma_kernel");
 }

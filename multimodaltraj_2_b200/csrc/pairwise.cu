@@ -236,7 +236,7 @@ extern "C" int mmt_pairwise_adj_f32(const float* pos, const uint8_t* valid, int 
     const int un = N == 16 ? 2 : UN;
     const long long nchunks = rows / (un * rpi);
     long long blocks = (nchunks + 7) / 8;
-    int grid = blocks < (long long)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+    int grid = blocks < (long long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 256)
       pairwise_rows_kernel<UN, 2><<<grid, 256, 0, st>>>(pos, valid, nchunks, N, lpr, lpr_shift, n_shift, r2,
@@ -252,7 +252,7 @@ extern "C" int mmt_pairwise_adj_f32(const float* pos, const uint8_t* valid, int 
   }
   long long blocks = (nquads + 256LL * UN - 1) / (256LL * UN);
   // a multiple of the SM count with 8 resident CTAs per SM; larger inputs grid-stride
-  int grid = blocks < (long long)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < (long long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   pairwise_adj_kernel<UN><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, valid, nquads, N, lpr, lpr_shift, n_shift, r2,
                                                                   neg_inv_log2e, kern, adj, deg);
   count_launch();
@@ -268,7 +268,7 @@ extern "C" int mmt_neighbor_index_i32(const uint8_t* adj, int S, int N, int max_
   if (S == 0) return MMT_OK;
   const long rows = (long)S * N;
   long blocks = (rows + 7) / 8;
-  int grid = blocks < kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < num_sms() * 8 ? (int)blocks : num_sms() * 8;
   neighbor_index_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adj, (int)rows, N, max_nbr, nbr, cnt);
   count_launch();
   return check_launch("neighbor_index_kernel");

@@ -25,7 +25,7 @@
 // own shared-memory traffic, ran at 83-90 clk in situ; one thread managing a bulk-copy ring sustains one
 // copy per ~360 clk; MUFU.TANH / EX2 issue 16 lanes/clk/SM.
 #include <cuda_bf16.h>
-#include <stdlib.h>
+#include <limits.h>
 
 #include <type_traits>
 
@@ -95,6 +95,13 @@ struct RoArgs {
   float r2, neg_inv_log2e;
   int flags;  // diagnostics: 1 = no weight streaming (timing experiments only), 16 = time the W_FULL waits
   long long* dbg;        // optional [64 steps][32] clock64 stamps of CTA 0: [0,16) worker thread 0, [16,32) MMA thread
+  uint32_t* trap;        // host-mapped trap record (tc_common.cuh: trap_report); may be null
+};
+// trap sites of this kernel (kernel id 1): which bounded wait expired
+enum : uint32_t {
+  RT_W_EMPTY = 0x101, RT_W_FULL = 0x102, RT_ACC_EMPTY = 0x103, RT_ACC_EMPTY_P0 = 0x104, RT_ACC1_EMPTY_P0 = 0x105,
+  RT_ATT_READY = 0x106, RT_E_READY = 0x107, RT_MH_READY_I0 = 0x108, RT_MH_READY_I1 = 0x109, RT_P0_ISSUED = 0x10A,
+  RT_P1_ISSUED = 0x10B, RT_P2_ISSUED = 0x10C, RT_AGG_FULL = 0x10D, RT_ACC_FULL = 0x10E
 };
 
 // MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) contiguous, 8 k-rows of 128 B per atom;
@@ -132,8 +139,8 @@ __device__ __forceinline__ float2 half_tanh_unit2(float2 x) {   // tanh(x) / 2: 
 }
 
 // wait executed by a whole (convergent) warp: reconverge before the next elect.sync
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  mbar_wait(bar, parity);
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, uint32_t* trap, uint32_t site) {
+  mbar_wait(bar, parity, trap, site);
   __syncwarp();
 }
 
@@ -155,13 +162,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   // then a link-time constant and every barrier address / UMMA descriptor derived from it is uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* const smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  require_smem_alignment(smem, a.trap, 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + RS_BAR;
   const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * RO_NSTAGE, ACC_FULL = bar0 + 16 * RO_NSTAGE,
                  ACC_EMPTY = ACC_FULL + 16, ATT_READY = ACC_EMPTY + 16, E_READY = ATT_READY + 8,
-                 MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8, P0_ISSUED = AGG_FULL + 8;
+                 MH_READY = E_READY + 8, AGG_FULL = MH_READY + 8, P0_ISSUED = AGG_FULL + 8, P1_ISSUED = P0_ISSUED + 8,
+                 P2_ISSUED = P1_ISSUED + 8;
   float* s_bias = reinterpret_cast<float*>(smem + RS_BIAS);
   float* s_we = reinterpret_cast<float*>(smem + RS_WE);
   float* s_wht = reinterpret_cast<float*>(smem + RS_WHT);
@@ -187,6 +195,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
     mbar_init(MH_READY, RO_WWARPS);
     mbar_init(AGG_FULL, 1);
     mbar_init(P0_ISSUED, 1);
+    mbar_init(P1_ISSUED, 1);
+    mbar_init(P2_ISSUED, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == RO_WWARPS) tmem_alloc(sbase + RS_TMEM, 512);
@@ -220,7 +230,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       const uint32_t total = (DIAG && (a.flags & 1)) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
       for (uint32_t it = warp - RO_WWARPS; it < total; it += RO_NPROD) {
         const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, j = it % RO_NCH;
-        if (DIAG && (a.flags & 64)) mbar_wait_spin(W_EMPTY + 8 * s, ph ^ 1u); else mbar_wait(W_EMPTY + 8 * s, ph ^ 1u);
+        if (DIAG && (a.flags & 64)) mbar_wait_spin(W_EMPTY + 8 * s, ph ^ 1u, a.trap, RT_W_EMPTY); else mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, a.trap, RT_W_EMPTY);
+        if (DIAG && (a.flags & 512) && j == 6 && ((it / RO_NCH) % 5u) == 2u) {   // fault injection: a late weight chunk (tests/test_gpu_parity.py)
+          const long long t0 = clock64();
+          while (clock64() - t0 < 6000) {}
+        }
         mbar_arrive_expect_tx(W_FULL + 8 * s, RO_STAGE_BYTES);
         bulk_g2s(sbase + RS_W + s * RO_STAGE_BYTES, a.Wp + (size_t)(j - j % RO_NKC + ro_perm(j % RO_NKC)) * RO_STAGE_BYTES,
                  RO_STAGE_BYTES, W_FULL + 8 * s);
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               const long long w0 = timed ? clock64() : 0;
               // no tcgen05.fence here: the stage was written by the async proxy (bulk copy -> mbarrier), not by another
               // thread's tcgen05 operation; a fence per chunk drained the MMA pipeline (pass 2650 -> see profiles/)
-              if (!(DIAG && (a.flags & 128))) mbar_wait_warp(W_FULL + 8 * s, (sc + (j / RO_NSTAGE)) & 1u);   // 128: timing experiment
+              if (!(DIAG && (a.flags & 128))) mbar_wait_warp(W_FULL + 8 * s, (sc + (j / RO_NSTAGE)) & 1u, a.trap, RT_W_FULL);   // 128: timing experiment
               if (timed) wwait += clock64() - w0;
             }
             const uint64_t db = d_w + (uint64_t)((s * RO_STAGE_BYTES) >> 4);
@@ -275,7 +289,17 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             constexpr int p = decltype(p_tag)::value;
             const uint32_t pc = pc0 + p;       // global pass counter: accumulator p & 1, use number pc >> 1
             constexpr uint32_t b = p & 1u;
-            mbar_wait_warp(ACC_EMPTY + 8 * b, ((pc >> 1) & 1u) ^ 1u);
+            mbar_wait_warp(ACC_EMPTY + 8 * b, ((pc >> 1) & 1u) ^ 1u, a.trap, RT_ACC_EMPTY);
+            // The weight ring is ONE ring shared by the two issuers, and an mbarrier parity wait is only meaningful for a
+            // waiter at most one phase ahead: chunk j of this pass re-uses the stage of chunk j - 4 of the previous pass,
+            // which the OTHER issuer consumes.  Were that chunk still in flight when this issuer reached its wait, the
+            // parity of the phase before it would read as "complete", the MMAs would run on a half-written stage and
+            // the extra W_EMPTY arrival would derail the producers (seen as an expired bounded wait = CUDA 719 once the
+            // weight stream ran > ~1000 clk late).  So a pass starts only after the previous pass has been issued whole.
+#ifndef RO_NO_PASS_ORDER   // (defined only by scratch/ro_race.py's build of the pre-fix protocol)
+            if constexpr (p == 2) mbar_wait_warp(P1_ISSUED, par, a.trap, RT_P1_ISSUED);
+            if constexpr (p == 3) mbar_wait_warp(P2_ISSUED, par, a.trap, RT_P2_ISSUED);
+#endif
             tc_fence_after();
             const uint32_t d_tmem = tmem_u + (b ? RT_ACC1 : RT_ACC0);
             if (DIAG && dbg) dbg[3 + 2 * p] = clock64();
@@ -285,6 +309,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 3>{});
             gate_chunk(d_tmem, std::integral_constant<int, p * RO_NKC + 4>{});
             umma_commit_elect(ACC_FULL + 8 * b);
+            if constexpr (p == 1 || p == 2) {
+              if (lane == 0) mbar_arrive(p == 1 ? P1_ISSUED : P2_ISSUED);
+              __syncwarp();
+            }
             if (DIAG && dbg) dbg[4 + 2 * p] = clock64();
           };
           if constexpr (me == 0) {
@@ -293,15 +321,15 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             //      have released accumulator 1 after its last pass (on a tile's first step: once E_READY has published
             //      the zeroed state).
             const uint32_t d0 = tmem_u + RT_ACC0;
-            mbar_wait_warp(ACC_EMPTY, ((pc0 >> 1) & 1u) ^ 1u);
+            mbar_wait_warp(ACC_EMPTY, ((pc0 >> 1) & 1u) ^ 1u, a.trap, RT_ACC_EMPTY_P0);
             if (t > 0) {
-              mbar_wait_warp(ACC_EMPTY + 8, (((pc0 + 1) >> 1) & 1u) ^ 1u);
+              mbar_wait_warp(ACC_EMPTY + 8, (((pc0 + 1) >> 1) & 1u) ^ 1u, a.trap, RT_ACC1_EMPTY_P0);
               tc_fence_after();
               if (DIAG && dbg) dbg[3] = clock64();
               gate_chunk(d0, std::integral_constant<int, 0>{});
               gate_chunk(d0, std::integral_constant<int, 1>{});
             }
-            mbar_wait_warp(ATT_READY, par);
+            mbar_wait_warp(ATT_READY, par, a.trap, RT_ATT_READY);
             tc_fence_after();
             if (DIAG && dbg) dbg[0] = clock64();
 #if RO_AGG256
@@ -326,7 +354,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                         kIdescAggMN, ks ? 1u : 0u);
 #endif
             if (DIAG && dbg) dbg[1] = clock64();
-            mbar_wait_warp(E_READY, par);
+            mbar_wait_warp(E_READY, par, a.trap, RT_E_READY);
             tc_fence_after();
             if (DIAG && dbg) dbg[2] = clock64();
             if (t == 0) {
@@ -335,7 +363,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               gate_chunk(d0, std::integral_constant<int, 1>{});
             }
             gate_chunk(d0, std::integral_constant<int, 2>{});
-            mbar_wait_warp(MH_READY, par);   // the mh chunks wait for the conversion
+            mbar_wait_warp(MH_READY, par, a.trap, RT_MH_READY_I0);   // the mh chunks wait for the conversion
             tc_fence_after();
             if (DIAG && dbg) dbg[12] = clock64();
             gate_chunk(d0, std::integral_constant<int, 3>{});
@@ -348,8 +376,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             __syncwarp();
             gate_pass(std::integral_constant<int, 2>{});
           } else {
-            mbar_wait_warp(MH_READY, par);   // accumulator 1 aliases the mh accumulator: wait for its conversion
-            mbar_wait_warp(P0_ISSUED, par);
+            mbar_wait_warp(MH_READY, par, a.trap, RT_MH_READY_I1);   // accumulator 1 aliases the mh accumulator: wait for its conversion
+            mbar_wait_warp(P0_ISSUED, par, a.trap, RT_P0_ISSUED);
             tc_fence_after();
             gate_pass(std::integral_constant<int, 1>{});
             gate_pass(std::integral_constant<int, 3>{});
@@ -514,7 +542,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         mbar_arrive_warp(E_READY);
         if (DIAG && dbg) dbg[2] = clock64();
         // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 32 cs .. +31)
-        mbar_wait(AGG_FULL, par);
+        mbar_wait(AGG_FULL, par, a.trap, RT_AGG_FULL);
         tc_fence_after();
         if (DIAG && dbg) dbg[3] = clock64();
 #pragma unroll
@@ -550,7 +578,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           for (int p = 0; p < RO_NP; ++p) {
             const uint32_t pc = sc * RO_NP + p;
             const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
-            mbar_wait(ACC_FULL + 8 * b, bph);
+            mbar_wait(ACC_FULL + 8 * b, bph, a.trap, RT_ACC_FULL);
             tc_fence_after();
             if (DIAG && dbg) dbg[5 + 2 * p] = clock64();
             const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;
@@ -714,15 +742,16 @@ int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, 
   a.num_tiles = (a.R + 127) / 128;
   a.r2 = r2; a.neg_inv_log2e = -inv_2sigma2 * 1.4426950408889634f;
   a.dbg = dbg;
-  a.flags = getenv("MMT_RO_FLAGS") ? atoi(getenv("MMT_RO_FLAGS")) : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(rollout_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
-    cudaFuncSetAttribute(rollout_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TOTAL + 1024);
-    attr_set = true;
-  }
-  int grid = a.num_tiles < kNumSMs ? a.num_tiles : kNumSMs;
-  if (getenv("MMT_RO_GRID") && atoi(getenv("MMT_RO_GRID")) > 0 && atoi(getenv("MMT_RO_GRID")) < grid) grid = atoi(getenv("MMT_RO_GRID"));   // diagnostics
+  a.trap = trap_record();
+  // diagnostic switches of scratch/ro_*.py (timing experiments, fault injection): read once per process
+  static int env_flags = INT_MIN, env_grid = INT_MIN;
+  a.flags = env_int_once("MMT_RO_FLAGS", &env_flags);
+  static unsigned long long smem_opted[2] = {};   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<false>), RS_TOTAL + 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<true>), RS_TOTAL + 1024, &smem_opted[1])) return rc;
+  int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  const int dgrid = env_int_once("MMT_RO_GRID", &env_grid);
+  if (dgrid > 0 && dgrid < grid) grid = dgrid;
   if (a.dbg || a.flags)
     rollout_tc_kernel<true><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
   else

@@ -103,7 +103,7 @@ extern "C" int mmt_scene_batch_f32(const int32_t* frame_ids_sorted, const int32_
   MMT_REQUIRE(!visout || vis, "visout requires vis");
   if (S == 0) return MMT_OK;
   int blocks = (S + 3) / 4;
-  int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
+  int grid = blocks < num_sms() * 8 ? blocks : num_sms() * 8;
   scene_batch_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(frame_ids_sorted, frame_row_start, n_frames, ped_id, xy,
                                                              vis, win_start, S, N, F, fstride, pos, visout, valid,
                                                              ped_of_slot);

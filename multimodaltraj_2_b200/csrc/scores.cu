@@ -265,7 +265,7 @@ extern "C" int mmt_mcr_forward_f32(const float* outputs, const float* rel, const
               "need D <= 16, T <= 16, 2P <= 32");
   if (S == 0) return MMT_OK;
   MMT_REQUIRE(outputs && rel && ngh && w && w->W_v && w->b_v && w->W_r && w->W_c && w->W_o, "pointers required");
-  int grid = S < kNumSMs * 8 ? S : kNumSMs * 8;
+  int grid = S < num_sms() * 8 ? S : num_sms() * 8;
   mcr_forward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(outputs, rel, ngh, w->W_v, w->b_v, w->W_r, w->W_c, w->W_o,
                                                              S, n, D, T, P, lam, variant, attn, cost, band);
   count_launch();
@@ -277,7 +277,7 @@ extern "C" int mmt_sigmoid_f32(const float* x, float* y, size_t n, void* stream)
   if (n == 0) return MMT_OK;
   MMT_REQUIRE(x && y, "pointers required");
   size_t blocks = (n + 255) / 256;
-  int grid = blocks < (size_t)kNumSMs * 8 ? (int)blocks : kNumSMs * 8;
+  int grid = blocks < (size_t)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   sigmoid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n);
   count_launch();
   return check_launch("sigmoid_kernel");
@@ -289,7 +289,7 @@ extern "C" int mmt_rowsoftmax_f32(const float* x, float* y, int rows, int cols, 
   if (rows == 0) return MMT_OK;
   MMT_REQUIRE(x && y, "pointers required");
   int blocks = (rows + 7) / 8;
-  int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
+  int grid = blocks < num_sms() * 8 ? blocks : num_sms() * 8;
   rowsoftmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, rows, cols);
   count_launch();
   return check_launch("rowsoftmax_kernel");
@@ -306,7 +306,7 @@ extern "C" int mmt_ade_fde_world_f32(const float* pred, const float* gt, const u
               "pred / gt must be 8-byte aligned");
   if (sums) cudaMemsetAsync(sums, 0, 3 * sizeof(float), (cudaStream_t)stream);
   const int blocks = (n + 15) / 16;
-  const int grid = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;
+  const int grid = blocks < num_sms() * 8 ? blocks : num_sms() * 8;
   ade_fde_world_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, valid, n, P, Hm, scale0, scale1, ade, fde, sums);
   count_launch();
   return check_launch("ade_fde_world_kernel");

@@ -97,7 +97,7 @@ extern "C" int mmt_static_context_f32(const float* img, int H, int W, int C, con
   a.img = img; a.filt = filt; a.H = H; a.W = W; a.C = C; a.FH = FH; a.FW = FW; a.D = D;
   a.part = static_cast<float*>(workspace);
   const size_t smem = sizeof(float) * ((size_t)D * (SC_BCH + D - 1) * C + (size_t)SC_BCH * C);
-  const int grid = FH < kNumSMs * 4 ? FH : kNumSMs * 4;
+  const int grid = FH < num_sms() * 4 ? FH : num_sms() * 4;
   static_ctx_partial_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   count_launch();
   int rc = check_launch("static_ctx_partial_kernel");

@@ -30,17 +30,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// A trap names itself first: the kernel's trap record is a 16-word block of host-mapped pinned memory (capi.cu:
+// trap_record(); reported by mmt_last_trap and appended to the error text of the next failing launch check), written
+// with a system-scope fence before __trap() kills the context.  word 0 = site code (kernel << 8 | wait), 1 = CTA,
+// 2 = thread, 3 = barrier shared address, 4 = awaited parity, 5 = extra.
+static __device__ __forceinline__ void trap_report(uint32_t* rec, uint32_t site, uint32_t bar, uint32_t parity, uint32_t extra = 0) {
+  if (rec) {
+    volatile uint32_t* r = rec;
+    r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = bar; r[4] = parity; r[5] = extra;
+    r[0] = site;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void require_smem_alignment(const void* smem, uint32_t* rec, uint32_t kernel_id) {
+  if ((smem_u32(smem) & 1023u) != 0u) trap_report(rec, (kernel_id << 8) | 0xFFu, smem_u32(smem), 0);
+}
 // bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  One iteration of the hinted
 // try_wait measured ~40 clk while the barrier is pending (ncu: 15 k iterations per warp in 0.33 ms of waiting), so
 // 2^26 iterations are >= 1.4 s -- three orders of magnitude above any legitimate wait in these kernels.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* rec = nullptr, uint32_t site = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 26)) trap_report(rec, site, bar, parity);
   }
 }
 // spinning wait (no suspend hint): lowest wake-up latency, costs issue slots -- for single-thread roles on a latency-critical ring
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t* rec = nullptr, uint32_t site = 0) {
   uint32_t ok = 0, spins = 0;
   while (!ok) {
     asm volatile(
@@ -50,7 +66,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 28)) trap_report(rec, site, bar, parity);
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -268,7 +268,7 @@ extern "C" int mmt_mcr_step_f32(const float* X, const float* V, const float* C, 
   a.W_i = w->W_i; a.W_ii = w->W_ii; a.W_v = w->W_v; a.b_v = w->b_v; a.W_r = w->W_r; a.W_c = w->W_c; a.W_o = w->W_o;
   a.S = S; a.n = n; a.D = D; a.T = T; a.P = P; a.H = H; a.variant = variant; a.lam = lam;
   a.attn = attn; a.cost = cost; a.band = band; a.Hs_out = Hs_out; a.adj = adj; a.vemb_out = vemb_out;
-  int grid = S < kNumSMs * 8 ? S : kNumSMs * 8;
+  int grid = S < num_sms() * 8 ? S : num_sms() * 8;
   mcr_step_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   count_launch();
   return check_launch("mcr_step_kernel");

@@ -161,7 +161,7 @@ extern "C" int mmt_head_nll_f32(const float* m_t, const float* m_f, const uint8_
   MMT_REQUIRE(R >= 0 && U > 0, "need R >= 0, U > 0");
   if (R == 0) return MMT_OK;
   MMT_REQUIRE(m_t && m_f && valid && W_h && b_h && target && loss_sum && dy, "all pointers required");
-  const int grid = (R + 7) / 8 < kNumSMs * 8 ? (R + 7) / 8 : kNumSMs * 8;
+  const int grid = (R + 7) / 8 < num_sms() * 8 ? (R + 7) / 8 : num_sms() * 8;
   head_nll_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m_t, m_f, valid, W_h, b_h, target, R, U, scale, loss_sum, dy);
   count_launch();
   return check_launch("head_nll_kernel");
@@ -176,7 +176,7 @@ extern "C" int mmt_gsk_cell_backward_f32(const float* z, const float* c, const f
   if (R == 0) return MMT_OK;
   MMT_REQUIRE(z && c && mc && valid && w_If && w_It && w_Of && w_Ot && d_mt && dz && dc && dmc && dpeep,
               "z/c/mc/valid/peepholes/d_mt/outputs required");
-  const int grid = R < kNumSMs * 16 ? R : kNumSMs * 16;
+  const int grid = R < num_sms() * 16 ? R : num_sms() * 16;
   gsk_cell_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, c, mc, valid, w_If, w_It, w_Of, w_Ot, d_mt, d_mf,
                                                                    d_ct, R, U, dz, dc, dmc, dpeep);
   count_launch();
@@ -193,7 +193,7 @@ extern "C" int mmt_gsk_gates_f32(const float* z, const float* c, const float* mc
   MMT_ALIGNED(z); MMT_ALIGNED(c); MMT_ALIGNED(mc); MMT_ALIGNED(h_out); MMT_ALIGNED(c_out); MMT_ALIGNED(mf_out);
   MMT_ALIGNED(w_If); MMT_ALIGNED(w_It); MMT_ALIGNED(w_Of); MMT_ALIGNED(w_Ot);
   const long blocks = ((long)R * (U / 4) + 255) / 256;
-  const int grid = blocks < (long)kNumSMs * 16 ? (int)blocks : kNumSMs * 16;
+  const int grid = blocks < (long)num_sms() * 16 ? (int)blocks : num_sms() * 16;
   gsk_gates_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, c, mc, valid, w_If, w_It, w_Of, w_Ot, R, U, h_out, c_out, mf_out);
   count_launch();
   return check_launch("gsk_gates_kernel");
