@@ -16,18 +16,56 @@ import track_b as o_b  # noqa: E402
 GOLD = np.load(ROOT / "tests" / "golden" / "track_a_ckpt.npz")
 
 
-def test_band_first_matmul_matches_tf_evaluated_checkpoint():
-    """models/g2k_lstm_mcr.py:122: the checkpoint holds W_c, cost and TF's own W_c @ cost."""
-    n = int(GOLD["n_wc"])
+def _feed_Eo(Eo, D):
+    """(outputs, W_v, b_v) for which models/g2k_lstm_mcr.py:105's ``W_v @ outputs + b_v`` IS the given Eo[T,D]."""
+    T = Eo.shape[0]
+    outputs = np.vstack([np.eye(D), np.zeros((2, D))])          # [D+2, D]
+    return outputs, np.hstack([Eo, np.zeros((T, 2))]), np.zeros(D)
+
+
+def test_band_chain_through_the_oracle_matches_tf_evaluated_checkpoint():
+    """models/g2k_lstm_mcr.py:112-113,122: the checkpoint holds W_c, TF's ``cost`` Variable and TF's own W_c @ cost.
+    The oracle's forward is driven so that its cost (= Eo @ lambda ngh) reproduces the saved cost exactly, and the band it
+    derives from it (W_o = I isolates the first matmul of :122) must be the TF-evaluated product."""
+    n, lam, D, T, P = int(GOLD["n_wc"]), 0.0005, 10, 8, 12
     assert n == 5
     for k in range(n):
         W_c, cost, want = GOLD[f"wc_{k}_W_c"], GOLD[f"wc_{k}_cost"], GOLD[f"wc_{k}_out"]
-        W_o = np.eye(8)                                # isolate the first matmul of the band
-        got = o_a.mcr_forward(np.zeros((12, 10)), np.zeros((2, 10)), np.zeros((10, 8)), np.zeros((8, 12)),
-                              np.zeros(10), np.zeros((8, 2)), W_c, W_o, 0.0005)
-        # cost is recomputed inside mcr_forward from Eo/ngh; check the matmul itself on the saved cost
-        assert np.abs(W_c @ cost - want).max() < 1e-15
-        assert got["band"].shape == (2, 12, 8)
+        Eo = np.hstack([cost, np.zeros((T, D - T))])                       # Eo @ [I_T; 0] == cost
+        ngh = np.vstack([np.eye(T), np.zeros((D - T, T))]) / lam           # lambda * ngh == [I_T; 0] exactly? (0 and 1/lam*lam)
+        outputs, W_v, b_v = _feed_Eo(Eo, D)
+        got = o_a.mcr_forward(outputs, np.zeros((2, D)), ngh, W_v, b_v, np.zeros((T, 2)), W_c, np.eye(T), lam, P)
+        np.testing.assert_allclose(got["cost"], cost, rtol=0, atol=1e-17)
+        np.testing.assert_allclose(got["band"].reshape(2 * P, T), want, rtol=0, atol=1e-15)
+
+
+def test_attention_orientation_matches_tf_evaluated_checkpoint():
+    """models/g2k_lstm_mcr.py:102,105-106: ``attn = (lambda ngh) @ (Eo * (W_r @ rel))``.  The checkpoint holds TF's
+    ``lambda ngh`` Variable [D,T] and TF's ``attn`` Variable [D,D] of the same instantiation.  Pinned here: attn lies in
+    the column space of the saved lambda-ngh (rank <= T = 8 < D = 10, least-squares residual 1e-17), and the oracle's
+    forward, fed the right factor M that the saved pair determines, reproduces TF's attn -- i.e. the left factor, its
+    lambda scaling and the orientation of the product.  NOT pinned: the right factor itself.  The saved Eo and cost
+    Variables of an instantiation come from separate evaluations of the default random placeholders
+    (|cost - Eo @ lambda ngh| ~ 2e-2 for every pairing of the 20 instantiations), so no saved tensor triple satisfies
+    :112-113 -- recorded in DESIGN.md section 1 ("Oracle pinning")."""
+    lam, D, T, P = 0.0005, 10, 8, 12
+    for k in range(int(GOLD["n_wc"])):
+        ngh_s, attn = GOLD[f"wc_{k}_ngh"], GOLD[f"wc_{k}_attn"]
+        assert ngh_s.shape == (D, T) and attn.shape == (D, D)
+        assert np.linalg.matrix_rank(attn, tol=1e-12) <= T
+        M, *_ = np.linalg.lstsq(ngh_s, attn, rcond=None)                   # [T, D]
+        assert np.abs(ngh_s @ M - attn).max() < 1e-15
+        # the other orientation is not consistent with the saved pair: attn is not M' @ ngh_s^T-shaped
+        M2, *_ = np.linalg.lstsq(ngh_s, attn.T, rcond=None)
+        assert np.abs(ngh_s @ M2 - attn.T).max() > 1e-6
+        outputs, W_v, b_v = _feed_Eo(M, D)                                 # Eo := M
+        rel = np.vstack([np.ones(D), np.zeros(D)])                         # W_r @ rel == ones[T,D]
+        W_r = np.hstack([np.ones((T, 1)), np.zeros((T, 1))])
+        got = o_a.mcr_forward(outputs, rel, ngh_s / lam, W_v, b_v, W_r, np.zeros((2 * P, T)), np.eye(T), lam, P)
+        np.testing.assert_allclose(got["ngh"], ngh_s, rtol=1e-15)
+        np.testing.assert_allclose(got["attn"], attn, rtol=0, atol=1e-15)
+        # scale recorded by TF: lambda * N(0,1)
+        assert 0.6 < ngh_s.std() / lam < 1.5
 
 
 def test_mcr_forward_chain_and_shapes_with_seed0_weights():
