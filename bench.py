@@ -98,20 +98,48 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons of ONE GPU sampled DURING the timed region: NVML polled every ~5 ms from a
+    thread (the timed region of 20 steps lasts ~50 ms -- `nvidia-smi -lms 100` saw 0-2 samples of it); nvidia-smi
+    as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc, self.h, self.stop_flag = index, uuid, [], None, None, False
+        self.sm, self.reasons, self.mx, self.thread = [], set(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = (pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid) if uuid
+                      else pynvml.nvmlDeviceGetHandleByIndex(index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:            # noqa: BLE001
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.reasons |= {n for b, n in self.BITS.items() if r & b}
+            except Exception:        # noqa: BLE001
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
+        except Exception:            # noqa: BLE001
             self.proc = None
 
     def _read(self):
@@ -119,6 +147,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            if not self.sm:
+                return None
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -130,7 +165,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -222,6 +257,45 @@ def config(args, scenes_per_rank, reference=False):
 
 
 # ------------------------------------------------------------------------------------------------
+_PARITY_CACHE = {}
+
+
+def parity_sample(ops, synth, params, dev, prec, variant, n_scenes, N):
+    """ADE/FDE (best of K) and predicted positions of the benched mode against the CPU oracle on a sample of the
+    benched workload (the first `n_scenes` scenes of rank 0's C3 batch).  The K-sample noise is FED to both sides
+    (the oracle's Philox restatement), so the deltas measure the arithmetic of the rollout, not the generator."""
+    import torch
+    key = (n_scenes, N, variant)
+    if key not in _PARITY_CACHE:          # the oracle's answer is computed once and shared by the modes
+        o_b = _oracle()
+        pos, vis, valid = synth.make_crowd(n_scenes, N, seed=synth.SEED)
+        eps = o_b.philox_eps(0xB200, n_scenes, N, K_SAMPLES, P_PRED)
+        _PARITY_CACHE[key] = (pos, vis, valid, eps, o_b.forecast(pos, vis, valid, synth.init_params(seed=0), eps, T_OBS, P_PRED,
+                                                                R2, INV_2SIGMA2, relational=(variant == "mcr")))
+    pos, vis, valid, eps, want = _PARITY_CACHE[key]
+    fc = ops.Forecaster(params, n_scenes, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(variant == "mcr"),
+                        prec=prec, device=dev, want_all=True)
+    o = fc(*(torch.from_numpy(a).to(dev) for a in (pos, vis, valid)), eps=torch.from_numpy(eps).to(dev))
+    torch.cuda.synchronize()
+    g = {k: o[k].cpu().numpy() for k in ("ade", "fde", "best_k", "params")}
+    v = valid.astype(bool)
+    idx = np.arange(K_SAMPLES)[None, None, :]
+    w_best = want["best_k"][..., None] == idx
+    g_best = g["best_k"][..., None] == idx
+    w_ade, w_fde = (want["ade"] * w_best).sum(-1)[v], (want["fde"] * w_best).sum(-1)[v]
+    g_ade, g_fde = (g["ade"] * g_best).sum(-1)[v], (g["fde"] * g_best).sum(-1)[v]
+    # mean predicted trajectory (cumulative mu) of the rollout, relative to the largest displacement
+    w_mu, g_mu = want["params"][..., :2].cumsum(2)[v], g["params"][..., :2].cumsum(2)[v]
+    return {"sample": f"{n_scenes} scenes x {N} agents of the benched batch, fed noise",
+            "max_abs_d_ade": float(np.abs(g["ade"][v] - want["ade"][v]).max()),
+            "max_abs_d_fde": float(np.abs(g["fde"][v] - want["fde"][v]).max()),
+            "d_mean_best_ade": float(abs(g_ade.mean() - w_ade.mean())), "d_mean_best_fde": float(abs(g_fde.mean() - w_fde.mean())),
+            "oracle_mean_best_ade": float(w_ade.mean()), "oracle_mean_best_fde": float(w_fde.mean()),
+            "best_k_equal_frac": float((g["best_k"][v] == want["best_k"][v]).mean()),
+            "pos_rel_err": float(np.abs(g_mu - w_mu).max() / max(np.abs(w_mu).max(), 1e-30)),
+            "within_1e-3": bool(np.abs(g["ade"][v] - want["ade"][v]).max() <= 1e-3 and np.abs(g["fde"][v] - want["fde"][v]).max() <= 1e-3)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     if not torch.cuda.is_available():
@@ -234,10 +308,14 @@ def run_ours(args, rank, world, local_rank):
     from multimodaltraj_2_b200 import _lib, ops, synth
 
     S, N = args.scenes, args.agents
-    prec = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}[args.prec]
+    PRECS = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}
+    if hasattr(ops, "PREC_BF16X3"):
+        PRECS["bf16x3"] = ops.PREC_BF16X3
+    prec = PRECS[args.prec]
+    relational = args.variant == "mcr"
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
-    fc = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(args.variant == "mcr"),
+    fc = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=relational,
                         prec=prec, seed=0xB200, agent_offset=rank * S * N, device=dev, use_graph=not args.no_graph)
     pos_p, vis_p, valid_p = (torch.from_numpy(a).pin_memory() for a in (pos_h, vis_h, valid_h))
     pos, vis, valid = pos_p.to(dev), vis_p.to(dev), valid_p.to(dev)
@@ -245,82 +323,111 @@ def run_ours(args, rank, world, local_rank):
     # (one set = pos 42 MB + vis 17 MB; outputs and workspace add ~150 MB per step)
     NSETS = 4
     sets = [(pos, vis, valid)] + [(pos.clone(), vis.clone(), valid.clone()) for _ in range(NSETS - 1)]
-    step_no = [0]
+    n_valid = int(valid_h.sum())
+    units = n_valid * world          # every rank holds the same number of valid agents (all valid)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        p_, v_, m_ = sets[step_no[0] % NSETS]
-        step_no[0] += 1
-        return fc(p_, v_, m_)
+    n_launch = [0]
 
-    stage("graph capture")
-    for st in sets:                      # first call per input set: eager validation + CUDA-graph capture (untimed)
-        fc(*st)
-    stage("warmup")
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    stage("timed steps")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    stage("timed steps done")
-    launches = ops.launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    n_valid = int(valid_h.sum())
-    units = n_valid * world          # every rank holds the same number of valid agents (all valid)
+    def timed_steps(f, n_warm, n_steps, sampler=None):
+        """W untimed + K timed steps of forecaster f on this rank, CUDA events on the launching stream,
+        barrier + synchronize on both sides, MAX over ranks.  Returns ms per step."""
+        k = [0]
+
+        def one():
+            st = sets[k[0] % NSETS]
+            k[0] += 1
+            return f(*st)
+        for st in sets:                  # first call per input set: eager validation + CUDA-graph capture (untimed)
+            f(*st)
+        for _ in range(n_warm):
+            one()
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            one()
+        e1.record()
+        barrier()
+        n_launch[0] = ops.launch_count() - l0
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps
+
+    stage("warmup + timed steps")
+    uuid = getattr(torch.cuda.get_device_properties(dev), "uuid", None)
+    sampler = ClockSampler(local_rank, f"GPU-{uuid}" if uuid is not None else None) if rank == 0 else None
+    ms_step = timed_steps(fc, args.warmup, args.steps, sampler)
+    launches = n_launch[0]           # this rank's kernels launched between the two events (graph replays counted per node)
+    clocks = sampler.stop() if sampler is not None else None
     value = units / (ms_step * 1e-3)
+    stage("timed steps done")
 
-    # ---- e2e: host buffers in, scores out, copies inside the timed region.  A two-deep pipeline as a serving loop
-    # would run it: the H2D copy of step i+1 (copy stream, pinned host memory) overlaps the kernels of step i; every
-    # step still uploads its own inputs and reads back its own result.
-    res_h = [torch.empty((2,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    # ---- the other precision modes of the same workload, a few steps each, in the same line ("modes"):
+    # f32 = the parity mode of the north_star tolerance (CUDA-core FMA); bf16x3 = split-bf16 tensor-core mode
+    modes = {args.prec: {"value": value, "ms_per_step": ms_step}}
+    if args.modes and not relational and args.prec == "bf16":
+        for name in [m for m in ("bf16x3", "f32") if m in PRECS]:
+            stage(f"mode {name}")
+            fm = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, prec=PRECS[name], seed=0xB200,
+                                agent_offset=rank * S * N, device=dev, use_graph=not args.no_graph)
+            ms_m = timed_steps(fm, 3, 5 if name == "f32" else 10)
+            modes[name] = {"value": units / (ms_m * 1e-3), "ms_per_step": ms_m}
+            del fm
+
+    # ---- e2e: host buffers in, forecast out, copies inside the timed region.  A two-deep pipeline as a serving loop
+    # would run it: the H2D copy of step i+1 (copy stream, pinned host memory) and the D2H copy of step i-1's
+    # forecast (best trajectory of every agent + its ADE / FDE, second copy stream, pinned host memory) overlap the
+    # kernels of step i; every step uploads its own inputs and the host holds every step's forecast.
+    stage("e2e warmup")
+    o0 = fc.out
+    res_h = [{k: torch.empty(o0[k].shape, dtype=o0[k].dtype).pin_memory() for k in ("best_traj", "best_ade", "best_fde")}
+             for _ in range(2)]
+    stage_d = [{k: torch.empty_like(o0[k]) for k in ("best_traj", "best_ade", "best_fde")} for _ in range(2)]
     bufs = [(torch.empty_like(pos), torch.empty_like(vis), torch.empty_like(valid)) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_staged = [torch.cuda.Event() for _ in range(2)]
     ev_done = [torch.cuda.Event() for _ in range(2)]
 
     def e2e_run(n):
         for i in range(n):
             b = i & 1
-            with torch.cuda.stream(copy_stream):
+            with torch.cuda.stream(h2d_stream):
                 if i >= 2:
-                    copy_stream.wait_event(ev_free[b])          # the kernels of step i-2 have consumed this buffer
+                    h2d_stream.wait_event(ev_free[b])           # the kernels of step i-2 have consumed this buffer
                 bufs[b][0].copy_(pos_p, non_blocking=True)
                 bufs[b][1].copy_(vis_p, non_blocking=True)
                 bufs[b][2].copy_(valid_p, non_blocking=True)
-                ev_copied[b].record(copy_stream)
+                ev_copied[b].record(h2d_stream)
             main_stream.wait_event(ev_copied[b])
+            if i >= 2:
+                main_stream.wait_event(ev_done[b])              # staging buffer b has left the device
             o = fc(*bufs[b])
             ev_free[b].record(main_stream)
-            res = torch.stack([o["best_ade"].sum(), o["best_fde"].sum()]) / n_valid
-            res_h[b].copy_(res, non_blocking=True)
-            ev_done[b].record(main_stream)
+            for k, t in stage_d[b].items():                     # device-side hand-over (25 MB at HBM speed), so that the
+                t.copy_(o[k], non_blocking=True)                # next step may overwrite the forecaster's outputs
+            ev_staged[b].record(main_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(ev_staged[b])
+                for k, t in stage_d[b].items():
+                    res_h[b][k].copy_(t, non_blocking=True)
+                ev_done[b].record(d2h_stream)
             if i >= 1:
-                ev_done[(i - 1) & 1].synchronize()              # the host consumes the previous step's result
+                ev_done[(i - 1) & 1].synchronize()              # the host consumes the previous step's forecast
         ev_done[(n - 1) & 1].synchronize()
         return res_h[(n - 1) & 1]
 
-    stage("e2e warmup")
     e2e_run(3)
     barrier()
     stage("e2e timed")
@@ -333,7 +440,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = units / float(te.item())
     h2d = pos_p.numel() * 4 + vis_p.numel() * 4 + valid_p.numel()
-    ade, fde = float(last[0]), float(last[1])
+    d2h = sum(t.numel() * t.element_size() for t in res_h[0].values())
+    ade, fde = float(last["best_ade"].sum() / n_valid), float(last["best_fde"].sum() / n_valid)
 
     stage("roofline kernels")
     # ---- roofline of the dominant kernel, timed alone with CUDA events on the launching stream
@@ -344,9 +452,11 @@ def run_ours(args, rank, world, local_rank):
     nsteps = T_OBS + P_PRED - 1
     fused = prec == ops.PREC_BF16 and args.variant == "mc" and 128 % N == 0 and N >= 8
     prof = {}
-    pf = ROOT / "profiles" / "r01_traffic.json"
-    if pf.exists():
-        prof = json.loads(pf.read_text())
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        pf = ROOT / "profiles" / name
+        if pf.exists():
+            prof = json.loads(pf.read_text())
+            break
     if fused:
         # rollout_tc_kernel: the whole T+P-1 step recurrence (pairwise + softmax -> aggregation MMA -> gate MMA ->
         # gate update -> head) in one launch.  Algorithmic FLOPs per agent-step: gate GEMM 2*320*384 + aggregation
@@ -441,6 +551,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     stage("gpu phases done")
     if rank == 0:
+        # ---- parity of the benched arithmetic where the headline lives: deltas against the CPU oracle on a sample of C3
+        stage("parity sample vs oracle")
+        n_par = min(S, args.parity_scenes)
+        delta = {args.prec: parity_sample(ops, synth, params, dev, prec, args.variant, n_par, N)}
+        for name in modes:
+            if name not in delta:
+                delta[name] = parity_sample(ops, synth, params, dev, PRECS[name], args.variant, n_par, N)
+        for name, m in modes.items():
+            m["max_abs_d_ade_vs_oracle"] = delta[name]["max_abs_d_ade"]
+            m["max_abs_d_fde_vs_oracle"] = delta[name]["max_abs_d_fde"]
+            m["pos_rel_err_vs_oracle"] = delta[name]["pos_rel_err"]
+            m["within_1e-3"] = delta[name]["within_1e-3"]
+        stage("cpu baseline")
         cores = os.cpu_count() or 1
         # CPU baseline on a bounded sample of the same workload: a small probe sizes it for ~10 s of CPU work
         cpu_forecast_sample(8, N, args.variant)                      # warm-up (imports, allocator)
@@ -454,14 +577,18 @@ def run_ours(args, rank, world, local_rank):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if prec == ops.PREC_F32 else "bf16", "data": "synthetic", "config": config(args, S),
+                "modes": modes,
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": 8},
+                        "d2h_bytes_per_step": d2h,
+                        "d2h": "best trajectory [S,N,P,2] + best-of-K ADE and FDE [S,N] of every agent, every step"},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_pairwise": roof_pw, "roofline_decode": roof_dec,
                 "cpu_baseline": {"value": n_cpu * N / t_cpu, "unit": "agent-trajectories/s", "cores": 1, "kind": "port",
                                  "sample": f"{n_cpu} scenes x {N} agents ({t_cpu:.1f} s of CPU work), numpy fp32 oracle of the whole path "
                                            f"(host has {cores} cores; TF 1.14 reference not installable offline)"},
-                "ade_fde": {"best_of_k_ade": ade, "best_of_k_fde": fde, "note": "random-init weights, synthetic data"},
+                "ade_fde": {"best_of_k_ade": ade, "best_of_k_fde": fde, "note": "random-init weights, synthetic data",
+                            "delta_vs_oracle": delta[args.prec],
+                            "tolerance": "north_star: ADE/FDE within 1e-3, positions 1e-4 relative in fp32; bf16 stated separately"},
                 "lib": str(_lib.lib_path().relative_to(ROOT))}
         emit(line)
     stage("teardown")
@@ -469,6 +596,89 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()               # rank 0 spent ~20 s in the CPU baseline: leave together
         dist.destroy_process_group()
     stage("done")
+
+
+def run_config(args, rank, world, local_rank):
+    """--config c1 | c5: the real-data configurations of BASELINE.json on the ETH / UCY tables shipped under data/.
+      c1  g2k_lstm_mc forward + ADE/FDE on the ETH-univ split (configs[0]),
+      c5  best-of-20 ADE/FDE over all five ETH/UCY splits, scenes sharded over the ranks (configs[4]).
+    Per split: device-side scene batching of every obs 8 + pred 12 window -> forecaster on this rank's shard -> ONE
+    all-reduce of (sum ADE, sum FDE, agents[, metres]).  Beside every score: the CPU oracle's value on the first
+    --parity-scenes windows with the same fed noise, and the delta.  Weights are the seed-0 random init (the reference
+    ships no trained model: SURVEY F2/F3), so the scores are parity evidence, not accuracy."""
+    import types
+
+    import torch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from multimodaltraj_2_b200 import ops, realdata, synth
+    a = types.SimpleNamespace(batch_size=16, seq_length=12, pred_len=P_PRED, obs_len=T_OBS, K=K_SAMPLES, data_root=None)
+    prec = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}[args.prec]
+    relational = args.variant == "mcr"
+    params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
+    splits = [1] if args.config == "c1" else [0, 1, 2, 3, 4]
+    rows, total_agents, total_ms = {}, 0, 0.0
+    for d in splits:
+        stage(f"split {d}")
+        t0 = time.perf_counter()
+        sc = realdata.scene_windows(a, d, "all", dev)
+        torch.cuda.synchronize()
+        t_batch = time.perf_counter() - t0
+        res = realdata.evaluate_split(a, d, params, part="all", prec=prec, relational=relational, rank=rank, world=world,
+                                      device=dev, scenes=sc)                      # warm-up + the reported scores
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 3
+        for _ in range(reps):
+            realdata.evaluate_split(a, d, params, part="all", prec=prec, relational=relational, rank=rank, world=world,
+                                    device=dev, scenes=sc)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        row = realdata.public(res)
+        row.update(ms_forecast=float(t.item()), s_scene_batching=t_batch)
+        if rank == 0:
+            o_b = _oracle()
+            n = min(args.parity_scenes, sc["pos"].shape[0])
+            pos, vis, valid = (sc[k][:n].cpu().numpy() for k in ("pos", "vis", "valid"))
+            eps = o_b.philox_eps(d, n, sc["N"], K_SAMPLES, P_PRED)
+            want = o_b.forecast(pos, vis, valid, synth.init_params(seed=0), eps, T_OBS, P_PRED, R2, INV_2SIGMA2,
+                                relational=relational)
+            v = valid.astype(bool)
+            pick = want["best_k"][..., None] == np.arange(K_SAMPLES)[None, None, :]
+            w_ade, w_fde = (want["ade"] * pick).sum(-1)[v], (want["fde"] * pick).sum(-1)[v]
+            sub = {k: sc[k][:n].contiguous() for k in ("pos", "vis", "valid")}
+            sub["N"] = sc["N"]
+            got = realdata.evaluate_split(a, d, params, part="all", prec=prec, relational=relational, device=dev, scenes=sub,
+                                          eps=torch.from_numpy(eps).to(dev))
+            g_ade = got["_out"]["best_ade"].cpu().numpy()[v]
+            g_fde = got["_out"]["best_fde"].cpu().numpy()[v]
+            row["oracle"] = {"sample": f"first {n} windows, fed noise", "ade": float(w_ade.mean()), "fde": float(w_fde.mean()),
+                             "ours_ade": float(g_ade.mean()), "ours_fde": float(g_fde.mean()),
+                             "max_abs_d_ade": float(np.abs(g_ade - w_ade).max()), "max_abs_d_fde": float(np.abs(g_fde - w_fde).max()),
+                             "best_k_equal_frac": float((got["_out"]["best_k"].cpu().numpy()[v] == want["best_k"][v]).mean())}
+        rows[realdata.DATASET_NAMES[d]] = row
+        total_agents += row["n_agents"]
+        total_ms += row["ms_forecast"]
+    if rank == 0:
+        emit({"metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": total_agents / (total_ms * 1e-3),
+              "unit": "agent-trajectories/s", "n_gpus": world, "steps": 3, "warmup": 1, "ms_per_step": total_ms,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f32" if prec == ops.PREC_F32 else "bf16", "data": "ETH/UCY tables under data/ (real), seed-0 random-init weights",
+              "config": {"workload": {"c1": "C1: g2k_lstm forward + best-of-20 ADE/FDE on the ETH-univ split",
+                                      "c5": "C5: best-of-20 ADE/FDE over all five ETH/UCY splits, scene-sharded"}[args.config],
+                         "variant": f"g2k_lstm_{args.variant}", "precision_mode": args.prec,
+                         "units": "ADE/FDE in the tables' units (normalised pixels / z-scores); *_m in metres (ETH homographies)"},
+              "splits": rows})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_train(args, rank, world, local_rank):
@@ -540,11 +750,15 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32", "bf16-stepwise"])
+    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32", "bf16-stepwise", "bf16x3"])
     ap.add_argument("--variant", default="mc", choices=["mc", "mcr"])
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly (no CUDA graph)")
+    ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the short runs of the other precision modes")
+    ap.add_argument("--parity-scenes", type=int, default=256, help="scenes of the batch compared with the CPU oracle")
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c5"],
+                    help="c3 (default): synthetic crowds, the headline; c1 / c5: the real-data configs on data/ (extra)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
     ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32"], help="--mode train: arithmetic of the backward GEMMs")
     args = ap.parse_args()
@@ -557,6 +771,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args, rank, world)
+        elif args.config in ("c1", "c5"):
+            run_config(args, rank, world, local_rank)
         elif args.mode == "train":
             run_train(args, rank, world, local_rank)
         else:

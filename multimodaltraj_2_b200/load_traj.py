@@ -19,10 +19,17 @@ DATASET_DIRS = ['eth/hotel/', 'eth/univ/', 'ucy/zara/zara01/', 'ucy/zara/zara02/
                 'town_center.csv', 'annotation_tc.txt']          # load_traj.py:25-33
 
 
+def default_data_root():
+    """``data/`` of the working directory if it exists, else the tables shipped at the repository root."""
+    if os.path.isdir("data"):
+        return "data"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+
+
 class DataLoader():
     def __init__(self, args, datasets=(0, 1, 2, 3, 4, 5, 6), sel=None, start=0, processFrame=False, infer=False,
                  parent_dir=None, csv=None):
-        parent_dir = parent_dir or getattr(args, "data_root", None) or "data"
+        parent_dir = parent_dir or getattr(args, "data_root", None) or default_data_root()
         self.data_dirs = [os.path.join(parent_dir, d) for d in DATASET_DIRS]
         self.used_data_dirs = [self.data_dirs[x] for x in datasets]
         self.infer = infer
@@ -37,7 +44,10 @@ class DataLoader():
             self.sel_file = "<memory>"
             self._load_array(np.asarray(csv, np.float64), val=infer)
         elif os.path.isdir(self.current_dir):
-            files = sorted(glob.glob(self.current_dir + "*.csv"))
+            # the reference takes the alphabetically first *.csv (load_traj.py:77-86); the tables shipped under data/
+            # are gzip-compressed (numpy reads them transparently): order by the name without the .gz suffix
+            files = sorted(glob.glob(self.current_dir + "*.csv") + glob.glob(self.current_dir + "*.csv.gz"),
+                           key=lambda f: f[:-3] if f.endswith(".gz") else f)
             if sel is None:
                 sel = 0 if len(files) == 1 else int(input('select which file you want for loading:'))
             self.dataset_pointer = sel

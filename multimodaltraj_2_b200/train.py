@@ -72,6 +72,116 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
 
 
 # --------------------------------------------------------------------------------------------
+def track_a_batch(args, batch, target_traj, graph, fp, sess_g=None, C=None, hidden_state=None, frame=1, device="cuda",
+                  vislet=None, vemb_prev=None):
+    """One batch of the reference's per-frame loop as written (train.py:423-674, the same lines as :61-276 of the
+    training branch): ConstructGraph -> batch_v (node-axis slice, n <= obs_len: defect F-4, kept) -> model ->
+    per-frame state step with the carried hidden state -> the per-agent scores of :639-662.
+    Returns None for a batch the reference skips (:428-429, :434-435, :442-444), else
+    dict(pred[n,P,2], euc[n], err[n,2], num_nodes, hidden_state, frames)."""
+    import numpy as np
+    from .models import g2k_lstm_mcr as mcr
+    if len(batch) == 0:
+        return None
+    graph_t = graph.ConstructGraph(current_batch=batch, framenum=fp, future_traj=target_traj)
+    batch_v = list(graph_t.get_node_attr(param='node_pos_list').values())
+    if len(batch_v) == 0 or np.array(batch_v).ndim <= 1:
+        return None
+    batch_v = np.array(batch_v)[frame:frame + args.obs_len]             # :438 slices the NODE axis
+    if batch_v.shape[0] == 0:
+        return None
+    X = np.linalg.norm(batch_v, axis=2).T                                # [T, n]  (:439-444)
+    T, n = X.shape
+    dim = int(args.neighborhood_size / args.grid_size)
+    H = args.rnn_size
+    dev = torch.device(device)
+    f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(dev)  # noqa: E731
+    m = mcr.g2k_lstm_mcr(in_features=torch.zeros((dim, dim)), num_nodes=n, obs_len=T, hidden_size=H,
+                         lambda_reg=args.lambda_param, sess_g=sess_g, pred_len=args.pred_len, device=dev)
+    rng = np.random.default_rng(0)                                       # init_w: N(0,1), seed 0 (:446, :514-521)
+    W_i, W_ii = rng.standard_normal((n, dim)), rng.standard_normal((dim, T))
+    # vislet = first two rows of the batch's vislet table cut to n columns (:182-183 / :529-530)
+    V = np.zeros((2, n))
+    if vislet is not None and vislet.shape[0] == 2 and vislet.shape[1] >= n:
+        V = np.asarray(vislet[:, :n], np.float64)
+    if C is None:                                                        # ctxt.png is absent upstream: no static context
+        C = np.zeros((dim, dim))
+    Hs = torch.zeros((1, dim, H), device=dev) if hidden_state is None else hidden_state
+    out = None
+    for _ in batch:                                                      # :556: every frame of the batch, state carried
+        out = m.forward_batched(f32(X[None]), f32(V[None]), f32(C[None]), Hs, f32(W_i), f32(W_ii), vemb_prev)
+        Hs = out["Hs"]
+    pred = out["pred"][0].contiguous()                                   # [n, P, 2]  (:636)
+    ids = list(target_traj)[:n]                                          # zip(range(num_nodes), iter(target_traj)) :641
+    P = args.pred_len
+    tgt = np.zeros((len(ids), P, 2), np.float32)
+    lens = np.zeros(len(ids), np.int32)
+    for i, k in enumerate(ids):
+        t = np.asarray(target_traj[k], np.float32)[:P]
+        lens[i] = len(t)
+        tgt[i, :len(t)] = t
+    euc, err = ops.train_val_scores(pred[:len(ids)].contiguous(), f32(tgt), torch.as_tensor(lens).to(dev), len(target_traj))
+    return dict(pred=pred, euc=euc, err=err, num_nodes=n, hidden_state=Hs, frames=len(batch), vemb=out["vemb"])
+
+
+def validate(args, params=None, l=None, rank=None, world=None, device=None, sess_g=None, max_batches=None):
+    """The validation branch (train.py:371-695) on the leave-out split ``l`` (default ``args.leaveDataset``).
+
+    Two scores come back, labelled:
+      * ``cv_ade`` / ``cv_fde`` -- the reference's own reductions (:639-674, :688-689: spectral norm / 12 per agent,
+        ||stack(err)||_F / len(batch) per batch, means over batches) of the AS-WRITTEN Track-A model on the batches
+        ``DataLoader.next_step`` yields, scene at a time as the reference runs them (rank 0; these are a few hundred tiny
+        matrix products).  The reference resets ``frame_pointer`` to 0 here (:377) and gets an empty first batch
+        (SURVEY F12); the pointer starts at the split's first frame instead.
+      * ``best_of_k`` -- the north_star metric: best-of-K ADE / FDE of the batched forecaster over every obs+pred window
+        of the validation columns (the 30 % of load_traj.py:125-134), scenes sharded over the ranks
+        (``realdata.evaluate_split``).
+    """
+    import numpy as np
+    from . import networkx_graph as nx_g
+    from . import realdata
+    rank = int(os.environ.get("RANK", 0)) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", getattr(args, "world_size", 1))) if world is None else world
+    device = device or torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    l = args.leaveDataset if l is None else l
+    t0 = time.time()
+    graph = nx_g.online_graph(args)
+    dataloader = load.DataLoader(args=args, datasets=[0, 1, 2, 3, 4, 5], start=l, sel=0)
+    dataloader.reset_data_pointer(valid=True, frame_pointer=dataloader.seed)          # :377 (see docstring)
+    dataloader.valid_frame_pointer = int((dataloader.len - int(dataloader.max * .7)) / dataloader.val_max)   # :409-410
+    dataloader.valid_num_batches = int(dataloader.val_max / dataloader.batch_size)     # :412
+    cv_ade_err, cv_fde_err, n_scored = [], [], 0
+    hidden = None
+    nb = dataloader.valid_num_batches if max_batches is None else min(max_batches, dataloader.valid_num_batches)
+    for vb in range(nb):
+        batch, target_traj, fp = dataloader.next_step()
+        vfp = int(dataloader.valid_frame_pointer)                                       # :527-528
+        r = track_a_batch(args, batch, target_traj, graph, fp, sess_g=sess_g, hidden_state=hidden, device=device,
+                          vislet=dataloader.vislet[:, vfp:vfp + args.obs_len] if dataloader.vislet.shape[0] == 2 else None)
+        if r is None:
+            break
+        hidden = r["hidden_state"]
+        euc, err = r["euc"].double().cpu().numpy(), r["err"].double().cpu().numpy()
+        if len(euc):
+            cv_ade_err.append(float(np.mean(euc)))                                         # :668-669
+            cv_fde_err.append(float(np.linalg.norm(err) / (r["num_nodes"] if l == 5 else r["frames"])))   # :670-674
+            n_scored += len(euc)
+    res = dict(dataset=l, cv_ade=float(np.mean(cv_ade_err)) if cv_ade_err else float("nan"),
+               cv_fde=float(np.mean(cv_fde_err)) if cv_fde_err else float("nan"), batches=len(cv_ade_err),
+               agents_scored=n_scored)
+    if rank == 0:
+        print('Cross-Validation total mean error (ADE) for dataset {0} = '.format(l), res["cv_ade"])       # :688
+        print('Cross-Validation total final error (FDE) for dataset {0} = '.format(l), res["cv_fde"])      # :689
+    prec = ops.PREC_BF16 if getattr(args, "precision", "bf16") == "bf16" else ops.PREC_F32
+    p = params if params is not None else ops.CellParams.from_numpy(
+        synth.init_params(seed=0, E=args.embedding_size, U=args.rnn_size), device)
+    res["best_of_k"] = realdata.public(realdata.evaluate_split(args, l, p, part="val", prec=prec, rank=rank, world=world,
+                                                              device=device))
+    res["seconds"] = time.time() - t0
+    return res
+
+
+# --------------------------------------------------------------------------------------------
 # training step (SURVEY App. C.5 "Training loss (fills F2)", section 8e): the reference has no loss or optimiser
 # (train.py:23-366 only logs raw errors); the step defined for it is
 #   teacher-forced rollout -> mean bivariate-Gaussian NLL of the next displacement + (lambda/2) ||W||^2
