@@ -37,6 +37,9 @@ extern "C" {
 #define MMT_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM   */
 #define MMT_PREC_BF16_STEPWISE 2 /* mmt_forecast_f32 only: bf16 as above but one kernel pair per step
                                     (state in HBM) instead of the fused persistent rollout           */
+#define MMT_PREC_BF16X3 3 /* tolerance-meeting tensor-core mode: fp32 state and aggregation, gate GEMM as split bf16
+                             (a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 accumulate in TMEM: 16 operand mantissa bits),
+                             tanhf / expf in the epilogue -- the north_star's 1e-4 / 1e-3 tolerance on tcgen05      */
 
 int mmt_version(void);
 const char* mmt_last_error(void);
@@ -120,6 +123,7 @@ typedef struct mmt_cell_weights {
   const void* W_packed_bf16; /* tcgen05 operand image of W (mmt_pack_gate_weights_bf16) or NULL */
   int E;
   int U;
+  const void* W_packed_bf16x3; /* split-bf16 image [W_hi ; W_hi ; W_lo] (mmt_pack_gate_weights_bf16x3) or NULL */
 } mmt_cell_weights;
 
 int mmt_gsk_cell(const float* x, const float* h, const float* c, const float* mh, const float* mc,
@@ -129,6 +133,9 @@ int mmt_gsk_cell(const float* x, const float* h, const float* c, const float* mh
 
 /* bytes of the packed bf16 operand image for W[E+2U,3U] */
 size_t mmt_gate_weights_packed_bytes(int E, int U);
+/* the split-bf16 image of MMT_PREC_BF16X3 (three times the size) */
+size_t mmt_gate_weights_packed_x3_bytes(int E, int U);
+int mmt_pack_gate_weights_bf16x3(const float* W, int E, int U, void* packed, void* stream);
 int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* packed, void* stream);
 
 /* ---- GridLSTMCell exactly as helper.py:31-39 / :131-139 instantiate it -------

@@ -19,7 +19,8 @@ vp = C.c_void_p
 
 class CellWeights(C.Structure):
     _fields_ = [("W_e", vp), ("b_e", vp), ("W", vp), ("b", vp), ("w_If", vp), ("w_It", vp), ("w_Of", vp),
-                ("w_Ot", vp), ("W_h", vp), ("b_h", vp), ("W_packed_bf16", vp), ("E", C.c_int), ("U", C.c_int)]
+                ("w_Ot", vp), ("W_h", vp), ("b_h", vp), ("W_packed_bf16", vp), ("E", C.c_int), ("U", C.c_int),
+                ("W_packed_bf16x3", vp)]
 
 
 class McrWeights(C.Structure):
@@ -56,6 +57,8 @@ SIGNATURES = {
                                C.c_int, vp, vp]),
     "mmt_gate_weights_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mmt_pack_gate_weights_bf16": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "mmt_gate_weights_packed_x3_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mmt_pack_gate_weights_bf16x3": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "mmt_gridlstm_step_f32": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                         C.c_int, vp, vp, vp]),
     "mmt_mcr_step_f32": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(McrWeights), C.c_int, C.c_int, C.c_int, C.c_int,

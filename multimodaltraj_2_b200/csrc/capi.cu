@@ -111,7 +111,7 @@ int launch_head(const float* mt, int ld, const float* mf, int ld_mf, const uint8
                 cudaStream_t stream);
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
                    const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
-                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos, int x3,
                    cudaStream_t stream);
 
 }  // namespace mmt
@@ -135,7 +135,7 @@ extern "C" int mmt_gsk_cell(const float* x, const float* h, const float* c, cons
   MMT_REQUIRE(w->W_e && w->b_e && w->W && w->b && w->w_If && w->w_It && w->w_Of && w->w_Ot, "cell weights required");
   MMT_REQUIRE(R >= 0, "R must be >= 0");
   MMT_REQUIRE(w->E == 64 && w->U == 128, "cell is built for E = 64, U = 128");
-  MMT_REQUIRE(prec == MMT_PREC_F32 || prec == MMT_PREC_BF16, "unknown precision mode");
+  MMT_REQUIRE(prec == MMT_PREC_F32 || prec == MMT_PREC_BF16 || prec == MMT_PREC_BF16X3, "unknown precision mode");
   MMT_REQUIRE(!params_out || (w->W_h && w->b_h && cur_pos && params_stride >= 5), "head needs W_h, b_h, cur_pos");
   MMT_REQUIRE(h_out != h && c_out != c, "outputs must not alias the input state (rows are re-read by other CTAs)");
   MMT_ALIGNED(x); MMT_ALIGNED(h); MMT_ALIGNED(c); MMT_ALIGNED(mh); MMT_ALIGNED(mc);
@@ -149,7 +149,9 @@ extern "C" int mmt_gsk_cell(const float* x, const float* h, const float* c, cons
     if (params_out) rc = launch_head(h_out, U, mf_out, U, valid, w, R, cur_pos, params_out, params_stride, next_pos, st);
     return rc;
   }
-  MMT_REQUIRE(w->W_packed_bf16, "bf16 mode needs W_packed_bf16 (mmt_pack_gate_weights_bf16)");
+  const int x3 = prec == MMT_PREC_BF16X3;
+  MMT_REQUIRE(x3 ? w->W_packed_bf16x3 != nullptr : w->W_packed_bf16 != nullptr,
+              "bf16 modes need the packed operand image (mmt_pack_gate_weights_bf16 / _bf16x3)");
   return launch_cell_tc(x, h, c, mh, mc, U, valid, w, R, h_out, c_out, mf_out, U, cur_pos, params_out, params_stride,
-                        next_pos, st);
+                        next_pos, x3, st);
 }

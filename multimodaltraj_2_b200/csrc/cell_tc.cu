@@ -54,6 +54,19 @@ static_assert(SM_TOTAL + 1024 <= 113 * 1024, "two CTAs per SM must fit");
 
 constexpr uint32_t kIdesc = make_idesc_bf16(TC_M, TC_N);
 
+// Split-bf16 ("bf16x3") mode: the fp32 operands are split a = a_hi + a_lo, w = w_hi + w_lo (bf16 each: 16 mantissa bits
+// together) and the product is taken as a_hi w_hi + a_lo w_hi + a_hi w_lo in the fp32 accumulator (the dropped a_lo w_lo
+// term is 2^-16 of a product that is itself rounded to 2^-24): the gate GEMM at fp32-grade accuracy on the bf16 tensor
+// pipe, at three MMAs per k-step.  To the kernel it is the same GEMM with K' = 3 K: the k-chunks of a pass run
+// [A_hi | A_lo | A_hi] against the packed stream [W_hi ; W_hi ; W_lo].  The epilogue then uses tanhf / expf.
+constexpr int TC_X3_NKC = 3 * TC_NKC;                         // 15 weight chunks per pass
+constexpr int SM_ALO = ((SM_TOTAL + 1023) / 1024) * 1024;     // A_lo blocks (x3 only), after the common map
+constexpr int SM_TOTAL_X3 = SM_ALO + TC_A_BYTES;
+static_assert(SM_TOTAL_X3 + 1024 <= 227 * 1024, "x3 mode: one CTA per SM");
+__device__ __forceinline__ uint32_t pack_bf16x2_lo(float a, float b, uint32_t hi) {   // residuals of a pair
+  return pack_bf16x2(a - bf16_lo(hi), b - bf16_hi(hi));
+}
+
 struct TcArgs {
   const float *x, *h, *c, *mh, *mc;
   const __nv_bfloat16 *hb, *mhb, *mcb;  // bf16-state mode: h, mh, mc as [R,U] bf16 (c stays fp32, row stride ld)
@@ -78,9 +91,11 @@ __host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  //
   return ((size_t)(tile * (TC_U / 8) + (u >> 3)) * TC_M + r) * 8;
 }
 
-template <int LAY>
-__global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
+template <int LAY, bool X3 = false>
+__global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
   constexpr bool BF = LAY != 0;
+  static_assert(!X3 || LAY == 0, "split-bf16 mode takes the fp32 state layout");
+  constexpr int NKC = X3 ? TC_X3_NKC : TC_NKC;
   // SWIZZLE_128B atoms need a 1024-byte aligned base: requested from the toolchain, so that the base is a link-time
   // constant and the barrier addresses / descriptors derived from it are uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -132,11 +147,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         for (int p = 0; p < TC_NP; ++p)
-          for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
+          for (int kc = 0; kc < NKC; ++kc, ++it) {
             const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
             mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, a.trap, 0x201);
             mbar_arrive_expect_tx(W_FULL + 8 * s, TC_STAGE_BYTES);
-            bulk_g2s(sbase + SM_W + s * TC_STAGE_BYTES, a.Wp + (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES,
+            bulk_g2s(sbase + SM_W + s * TC_STAGE_BYTES, a.Wp + (size_t)(p * NKC + kc) * TC_STAGE_BYTES,
                      TC_STAGE_BYTES, W_FULL + 8 * s);
           }
       }
@@ -153,10 +168,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           mbar_wait(ACC_EMPTY + 8 * b, bph ^ 1u, a.trap, 0x203);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + b * TC_ACC_STRIDE;
-          for (int kc = 0; kc < TC_NKC; ++kc, ++it) {
+          for (int kc = 0; kc < NKC; ++kc, ++it) {
             const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
             mbar_wait(W_FULL + 8 * s, ph, a.trap, 0x204);   // written by the async proxy: no tcgen05 fence needed
-            const uint64_t da = make_desc_sw128(sbase + SM_A + kc * TC_A_BLOCK);
+            // x3: chunks 0-4 A_hi (x W_hi), 5-9 A_lo (x W_hi), 10-14 A_hi (x W_lo)
+            const uint32_t a_off = !X3 ? (uint32_t)(SM_A + kc * TC_A_BLOCK)
+                                       : (kc >= TC_NKC && kc < 2 * TC_NKC) ? (uint32_t)(SM_ALO + (kc - TC_NKC) * TC_A_BLOCK)
+                                                                           : (uint32_t)(SM_A + (kc % TC_NKC) * TC_A_BLOCK);
+            const uint64_t da = make_desc_sw128(sbase + a_off);
             const uint64_t db = make_desc_sw128(sbase + SM_W + s * TC_STAGE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < TC_KC / 16; ++ks)  // advance 32 B (16 bf16) inside the swizzle row
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
 #pragma unroll
         for (int kk = 0; kk < 32; kk += 8) {
           uint32_t pk[4];
+          [[maybe_unused]] uint32_t pl[4];
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
             float e2[2];
@@ -200,8 +220,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
             }
             __nv_bfloat162 b2 = __floats2bfloat162_rn(e2[0], e2[1]);
             pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+            if constexpr (X3) pl[j >> 1] = pack_bf16x2_lo(e2[0], e2[1], pk[j >> 1]);
           }
           *reinterpret_cast<uint4*>(smem + SM_A + sw128_off(r, k0 + kk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if constexpr (X3)
+            *reinterpret_cast<uint4*>(smem + SM_ALO + sw128_off(r, k0 + kk)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
       }
       const int r = q * 32 + lane;  // epilogue row within tile == TMEM lane
@@ -285,10 +308,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           }
           const int k = lane * 4;  // 0..124 within the 128-wide part
           const int blk = k >> 6, kk = k & 63;
-          *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-              make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
-          *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-              make_uint2(pack_bf16x2(mv.x, mv.y), pack_bf16x2(mv.z, mv.w));
+          const uint2 hh = make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
+          const uint2 mm = make_uint2(pack_bf16x2(mv.x, mv.y), pack_bf16x2(mv.z, mv.w));
+          *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = hh;
+          *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = mm;
+          if constexpr (X3) {
+            *reinterpret_cast<uint2*>(smem + SM_ALO + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+                make_uint2(pack_bf16x2_lo(hv.x, hv.y, hh.x), pack_bf16x2_lo(hv.z, hv.w, hh.y));
+            *reinterpret_cast<uint2*>(smem + SM_ALO + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+                make_uint2(pack_bf16x2_lo(mv.x, mv.y, mm.x), pack_bf16x2_lo(mv.z, mv.w, mm.y));
+          }
         }
       }
       if (dbg) dbg[1] = clock64();
@@ -322,6 +351,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
         float ho[8], co[8], fo[8];
         if (v) {
           const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
+          auto tanh2 = [](float2 t) {   // x3: accurate tanhf; bf16: tanh.approx (error below the operand rounding)
+            if constexpr (X3) return make_float2(tanhf(t.x), tanhf(t.y));
+            else return mmt::tanh2(t);
+          };
 #pragma unroll
           for (int hq = 0; hq < 2; ++hq) {   // 4 units at a time: parameters come as 128-bit smem loads
             const int uu = u + hq * 4;
@@ -425,9 +458,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gsk_cell_tc_kernel(TcArgs a) {
           if (v) {
 #pragma unroll
             for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + __ldg(a.b_h + z);
-            o[2] = __expf(o[2]);
-            o[3] = __expf(o[3]);
-            o[4] = tanh_fast(o[4]);
+            o[2] = X3 ? expf(o[2]) : __expf(o[2]);
+            o[3] = X3 ? expf(o[3]) : __expf(o[3]);
+            o[4] = X3 ? tanhf(o[4]) : tanh_fast(o[4]);
           }
           float* po = a.params_out + (size_t)gr * a.params_stride;
 #pragma unroll
@@ -461,21 +494,40 @@ __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* _
   *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(g == 1 ? W[idx] : 0.5f * W[idx]);
 }
 
+// split-bf16 image: [pass][15 chunks][96 rows][64 k]: chunks 0-4 and 5-9 hold W_hi (against A_hi, A_lo), 10-14 W_lo
+__global__ void pack_gate_weights_x3_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TC_K * 3 * TC_U) return;
+  const int k = idx / (3 * TC_U), col = idx - k * (3 * TC_U);
+  const int g = col / TC_U, u = col - g * TC_U;
+  const int p = u / TC_UN, ul = u - p * TC_UN;
+  const int n = g * TC_UN + ul;
+  const int kc = k / TC_KC, kk = k - kc * TC_KC;
+  const float w = g == 1 ? W[idx] : 0.5f * W[idx];           // sigmoid as 0.5 tanh(z/2) + 0.5: the 1/2 is exact
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const size_t base = (size_t)(p * TC_X3_NKC) * TC_STAGE_BYTES + sw128_off(n, kk);
+  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)kc * TC_STAGE_BYTES) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)(TC_NKC + kc) * TC_STAGE_BYTES) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)(2 * TC_NKC + kc) * TC_STAGE_BYTES) = lo;
+}
+
 static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
   a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
   a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
 }
 
-template <int LAY>
+template <int LAY, bool X3 = false>
 static int tc_launch(TcArgs& a, cudaStream_t stream) {
   a.num_tiles = (a.R + TC_M - 1) / TC_M;
   a.trap = trap_record();
+  constexpr int kSmem = (X3 ? SM_TOTAL_X3 : SM_TOTAL) + 1024, kPerSM = X3 ? 1 : 2;
   static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY>), SM_TOTAL + 1024, &smem_opted[0])) return rc;
-  const int grid = a.num_tiles < 2 * num_sms() ? a.num_tiles : 2 * num_sms();
-  gsk_cell_tc_kernel<LAY><<<grid, TC_THREADS, SM_TOTAL + 1024, stream>>>(a);
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3>), kSmem, &smem_opted[0])) return rc;
+  const int grid = a.num_tiles < kPerSM * num_sms() ? a.num_tiles : kPerSM * num_sms();
+  gsk_cell_tc_kernel<LAY, X3><<<grid, TC_THREADS, kSmem, stream>>>(a);
   count_launch();
-  return check_launch("gsk_cell_tc_kernel");
+  return check_launch(X3 ? "gsk_cell_tc_kernel<x3>" : "gsk_cell_tc_kernel");
 }
 
 // bf16-state variant used by the rollout: h, mh, mc as bf16 [R,U]; c fp32 [R,U]
@@ -497,17 +549,34 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
 
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
                    const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
-                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos, int x3,
                    cudaStream_t stream) {
   TcArgs a = {};
   a.x = x; a.h = h; a.c = c; a.mh = mh; a.mc = mc; a.valid = valid;
   tc_fill_weights(a, w);
+  if (x3) a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16x3);
   a.h_out = h_out; a.c_out = c_out; a.mf_out = mf_out; a.cur_pos = cur_pos; a.params_out = params_out;
   a.next_pos = next_pos; a.R = R; a.ld = ld; a.ld_mf = ld_mf; a.params_stride = params_stride;
-  return tc_launch<0>(a, stream);
+  return x3 ? tc_launch<0, true>(a, stream) : tc_launch<0>(a, stream);
 }
 
 }  // namespace mmt
+
+extern "C" size_t mmt_gate_weights_packed_x3_bytes(int E, int U) {
+  if (E != mmt::TC_E || U != mmt::TC_U) return 0;
+  return (size_t)mmt::TC_NP * mmt::TC_X3_NKC * mmt::TC_STAGE_BYTES;
+}
+
+extern "C" int mmt_pack_gate_weights_bf16x3(const float* W, int E, int U, void* packed, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(W && packed, "W/packed must not be NULL");
+  MMT_REQUIRE(E == TC_E && U == TC_U, "packing is built for E = 64, U = 128");
+  MMT_ALIGNED(packed);
+  const int n = TC_K * 3 * TC_U;
+  pack_gate_weights_x3_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
+  count_launch();
+  return check_launch("pack_gate_weights_x3_kernel");
+}
 
 extern "C" size_t mmt_gate_weights_packed_bytes(int E, int U) {
   if (E != mmt::TC_E || U != mmt::TC_U) return 0;

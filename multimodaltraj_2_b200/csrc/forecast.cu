@@ -16,7 +16,7 @@ int launch_edge_mlp_f32(const float* h, int ld_h, const uint8_t* adj, const mmt_
                         float* score, float* work, cudaStream_t stream);
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
                    const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
-                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos, int x3,
                    cudaStream_t stream);
 
 int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
@@ -119,7 +119,7 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   }
   w.score = (float*)take(cfg->relational ? NN * 4 : 0);
   w.ework = (float*)take(cfg->relational ? 2 * R * He * 4 : 0);
-  w.epacked = take(cfg->relational && cfg->prec != MMT_PREC_F32 && U == 128 && He == 128 ? 96 * 1024 : 0);
+  w.epacked = take(cfg->relational && cfg->prec != MMT_PREC_F32 && cfg->prec != MMT_PREC_BF16X3 && U == 128 && He == 128 ? 96 * 1024 : 0);
   w.params = (float*)take(R * cfg->P * 5 * 4);
   w.last_obs = (float*)take(R * 2 * 4);
   w.gt = (float*)take(R * cfg->P * 2 * 4);
@@ -145,9 +145,11 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   MMT_REQUIRE(cw->U == 128 && cw->E == 64, "cell is built for U = 128, E = 64");
   MMT_REQUIRE(cw->W_h && cw->b_h, "head weights required");
   MMT_REQUIRE(!cfg->relational || (ew && ew->He > 0), "relational mode needs edge weights");
-  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE,
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE ||
+                  cfg->prec == MMT_PREC_BF16X3,
               "unknown precision mode");
-  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16X3 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
+  MMT_REQUIRE(cfg->prec != MMT_PREC_BF16X3 || cw->W_packed_bf16x3, "bf16x3 mode needs W_packed_bf16x3");
   MMT_ALIGNED(pos);
   MMT_ALIGNED(vis);
   MMT_ALIGNED(work);
@@ -180,7 +182,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   int ic = 0, ip = 1, in = 2, hb = 0;
   int rc;
   // relational bf16 modes: the edge MLP runs on the tensor cores (edge_mlp_tc.cu); weights packed once per call
-  const bool edge_tc = cfg->relational && cfg->prec != MMT_PREC_F32 && U == 128 && He == 128;
+  const bool edge_tc = cfg->relational && cfg->prec != MMT_PREC_F32 && cfg->prec != MMT_PREC_BF16X3 && U == 128 && He == 128;
   if (edge_tc && (rc = launch_pack_edge_weights(ew->W1, ew->W2, w.epacked, stream))) return rc;
   for (int t = 0; t < (fused ? 0 : T + P - 1); ++t) {
     prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
@@ -250,7 +252,8 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       const float* hc = w.hc[hb];
       float* hco = w.hc[hb ^ 1];
       if ((rc = launch_cell_tc(w.x, hc, hc + U, w.mhc, w.mhc + U, 2 * U, valid, cw, R, hco, hco + U, nullptr, 0,
-                               w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr, stream)))
+                               w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr,
+                               cfg->prec == MMT_PREC_BF16X3, stream)))
         return rc;
     }
     hb ^= 1;

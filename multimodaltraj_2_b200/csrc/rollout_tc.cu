@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* const smem = smem_dyn;
   require_smem_alignment(smem, a.trap, 1);
+  if (DIAG && (a.flags & 1024) && blockIdx.x == 1 && threadIdx.x == 33) trap_report(a.trap, 0x1EE, 0xABCD, 1);   // self-test of the trap record
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + RS_BAR;

@@ -70,6 +70,7 @@ class online_graph():
         writes row ``itr`` of each of its pedestrians' position arrays."""
         g = self.onlineGraph
         g.step = framenum
+        framenum = int(framenum)                 # the loader's frame pointer is a float (load_traj.py:141-142)
         self.pos_list_len = len(current_batch)
         for itr, key in enumerate(current_batch):
             for item in current_batch[key]:

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-PREC_F32, PREC_BF16, PREC_BF16_STEPWISE = 0, 1, 2
+PREC_F32, PREC_BF16, PREC_BF16_STEPWISE, PREC_BF16X3 = 0, 1, 2, 3
 
 
 def _p(t):
@@ -113,6 +113,7 @@ class CellParams:
     W1: torch.Tensor = None; b1: torch.Tensor = None; W2: torch.Tensor = None; b2: torch.Tensor = None
     w_out: torch.Tensor = None; b_out: torch.Tensor = None
     W_packed: torch.Tensor = field(default=None, repr=False)
+    W_packed_x3: torch.Tensor = field(default=None, repr=False)
 
     @property
     def E(self):
@@ -128,9 +129,30 @@ class CellParams:
         nbytes = lib.mmt_gate_weights_packed_bytes(self.E, self.U)
         if nbytes == 0:
             raise RuntimeError("bf16 packing is built for E=64, U=128")
-        self.W_packed = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
+        if self.W_packed is None:     # re-packed IN PLACE afterwards: forecasters (and their CUDA graphs) hold its address
+            self.W_packed = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
         _lib.check(lib.mmt_pack_gate_weights_bf16(_p(self.W), self.E, self.U, _p(self.W_packed), _stream()),
                    "mmt_pack_gate_weights_bf16")
+        return self
+
+    def pack_x3(self):
+        """Split-bf16 operand image [W_hi ; W_hi ; W_lo] of PREC_BF16X3 (mmt_pack_gate_weights_bf16x3)."""
+        lib = _lib.load()
+        nbytes = lib.mmt_gate_weights_packed_x3_bytes(self.E, self.U)
+        if nbytes == 0:
+            raise RuntimeError("bf16x3 packing is built for E=64, U=128")
+        if self.W_packed_x3 is None:
+            self.W_packed_x3 = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
+        _lib.check(lib.mmt_pack_gate_weights_bf16x3(_p(self.W), self.E, self.U, _p(self.W_packed_x3), _stream()),
+                   "mmt_pack_gate_weights_bf16x3")
+        return self
+
+    def repack(self):
+        """After the weights changed (a training step): refresh the operand images that exist, in place."""
+        if self.W_packed is not None:
+            self.pack()
+        if self.W_packed_x3 is not None:
+            self.pack_x3()
         return self
 
     def c_cell(self):
@@ -139,6 +161,7 @@ class CellParams:
             t = getattr(self, n)
             setattr(w, n, None if t is None else t.data_ptr())
         w.W_packed_bf16 = None if self.W_packed is None else self.W_packed.data_ptr()
+        w.W_packed_bf16x3 = None if self.W_packed_x3 is None else self.W_packed_x3.data_ptr()
         w.E, w.U = self.E, self.U
         return w
 
@@ -175,6 +198,8 @@ def gsk_cell(x, h, c, mh, mc, valid, params: CellParams, prec=PREC_F32, cur_pos=
         _chk(cur_pos, torch.float32, "cur_pos")
     if prec == PREC_BF16 and params.W_packed is None:
         params.pack()
+    if prec == PREC_BF16X3 and params.W_packed_x3 is None:
+        params.pack_x3()
     w = params.c_cell()
     _lib.check(lib.mmt_gsk_cell(_p(x), _p(h), _p(c), _p(mh), _p(mc), _p(valid), C.byref(w), R, prec, _p(h_out),
                                 _p(c_out), _p(mf), _p(cur_pos), _p(par), 5, _p(nxt), _stream()), "mmt_gsk_cell")
@@ -335,8 +360,10 @@ class Forecaster:
         self._graphs = {}      # input-pointer tuple -> (CUDAGraph, launches per replay); at most 8 entries
         self._graph_n = 0
         self.p = params
-        if prec != PREC_F32 and params.W_packed is None:
+        if prec in (PREC_BF16, PREC_BF16_STEPWISE) and params.W_packed is None:
             params.pack()
+        if prec == PREC_BF16X3 and params.W_packed_x3 is None:
+            params.pack_x3()
         self.cfg = _lib.ForecastCfg(S, N, T, P, K, r2, inv_2sigma2, int(relational), prec, seed, agent_offset)
         He = params.W2.shape[0] if (relational and params.W2 is not None) else 0
         nbytes = self.lib.mmt_forecast_workspace_bytes(C.byref(self.cfg), params.U, He)
@@ -375,6 +402,14 @@ class Forecaster:
 
     def _launch(self, pos, vis, valid, eps=None):
         _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis"); _chk(valid, torch.uint8, "valid")
+        c = self.cfg
+        want = {"pos": (pos, (c.S, c.N, c.T + c.P, 2)), "vis": (vis, (c.S, c.N, c.T, 2)), "valid": (valid, (c.S, c.N))}
+        if eps is not None:
+            _chk(eps, torch.float32, "eps")
+            want["eps"] = (eps, (c.S, c.N, c.K, c.P, 2))
+        for name, (t, shape) in want.items():        # the kernels index by these strides: a [S,N,F,2] vislet tensor
+            if tuple(t.shape) != shape:               # (scene_batch's) passed unsliced would be read with the wrong one
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
         o = self.out
         ew = C.byref(self._ew) if self._ew is not None else None
         _lib.check(self.lib.mmt_forecast_f32(_p(pos), _p(vis), _p(valid), C.byref(self._cw), ew, C.byref(self.cfg),

@@ -402,12 +402,12 @@ class Trainer:
         g = unflatten_bucket(flat / counts[1], g)
         g["W"] = g["W"] + self.lam * self.p.W
         rmsprop_update_(self._tensors(), g, self.ms, self.lr, self.decay, clip=self.clip)
-        self.p.W_packed = None                                         # the bf16 operand image is stale now
+        self.p.repack()                                                # the bf16 operand images are stale now: refreshed in place
         return counts[0] / counts[1] + 0.5 * self.lam * (self.p.W * self.p.W).sum()
 
 
 def _param_names(params):
-    return [k for k in params.__dataclass_fields__ if isinstance(getattr(params, k), torch.Tensor) and k != "W_packed"]
+    return [k for k in params.__dataclass_fields__ if isinstance(getattr(params, k), torch.Tensor) and k not in ("W_packed", "W_packed_x3")]
 
 
 def save_checkpoint(path, params: ops.CellParams, trainer: "Trainer" = None, global_step=None):

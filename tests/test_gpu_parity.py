@@ -142,12 +142,13 @@ def _cell_inputs(R, seed=0):
 
 
 @pytest.mark.parametrize("R", [64, 200, 1000])
-def test_gsk_cell_fp32(cuda, R):
-    """fp32 parity mode: 1e-4 relative (north_star tolerance) against the fp32 oracle."""
+@pytest.mark.parametrize("prec", [ops.PREC_F32, ops.PREC_BF16X3], ids=["f32", "bf16x3"])
+def test_gsk_cell_fp32(cuda, R, prec):
+    """fp32 parity mode and the split-bf16 tensor-core mode: 1e-4 relative (north_star tolerance) against the fp32 oracle."""
     p = synth.init_params(seed=1)
     x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R)
     P = ops.CellParams.from_numpy(p, cuda)
-    ho, co, mf, par, nxt = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, ops.PREC_F32,
+    ho, co, mf, par, nxt = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, prec,
                                         cur_pos=dev(cur, cuda), want_head=True)
     oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
     for got, want in ((ho, oh), (co, oc), (mf, of)):
@@ -327,16 +328,18 @@ def test_scene_batch_matches_oracle_and_reference_loader(cuda):
 
 
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", [ops.PREC_F32, ops.PREC_BF16X3], ids=["f32", "bf16x3"])
 @pytest.mark.parametrize("relational", [False, True])
-@pytest.mark.parametrize("S,N", [(6, 64), (3, 16)])
-def test_forecast_fp32_matches_oracle(cuda, S, N, relational):
-    """Whole path, fp32 mode: predicted positions within 1e-4 relative, ADE/FDE within 1e-3, best-of-K exact
-    when the GPU's own parameters are scored (noise supplied)."""
+@pytest.mark.parametrize("S,N", [(6, 64), (3, 16), (5, 12)])
+def test_forecast_fp32_matches_oracle(cuda, S, N, relational, prec):
+    """Whole path at the north_star's tolerance: predicted positions within 1e-4 relative, ADE/FDE within 1e-3, best-of-K
+    exact when the GPU's own parameters are scored (noise supplied) -- in fp32 mode (CUDA-core FMA) AND in the split-bf16
+    tensor-core mode (MMT_PREC_BF16X3: gate GEMM as a_hi w_hi + a_lo w_hi + a_hi w_lo on tcgen05, tanhf / expf)."""
     T, P, K = 8, 12, 20
     pos, vis, valid = synth.make_crowd(S, N, seed=77, half_extent=4.0, ragged=True)
     p = synth.init_params(seed=3)
     eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
-    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=relational, prec=ops.PREC_F32,
+    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=relational, prec=prec,
                         device=cuda, want_all=True)
     o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
     torch.cuda.synchronize()
