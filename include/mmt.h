@@ -308,6 +308,30 @@ int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, c
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);
 
+/* ---- the one collective of the path: gradient all-reduce of data-parallel training -----------
+ * The reference has no parallelism (train.py:28-41 is a serial loop over datasets and batches); the north_star asks
+ * for "an NCCL-over-NVLink gradient allreduce".  In-place SUM (MAX for timings) of n floats over the ranks of `comm`
+ * (an ncclComm_t owned by the caller, e.g. torch.distributed's ProcessGroupNCCL._comm_ptr()) on `stream`.  libmmt does
+ * not link NCCL: the calls are resolved from the NCCL instance already loaded in the process, the only one in which
+ * the caller's communicator is valid.  Returns MMT_ENCCL (text via mmt_last_error) on any NCCL failure. */
+int mmt_allreduce_f32(void* comm, float* buf, size_t n, void* stream);
+int mmt_allreduce_max_f32(void* comm, float* buf, size_t n, void* stream);
+
+/* ---- generic workspace / packed-image size query ---------------------------------------------------------------- */
+typedef struct mmt_shape {
+  int S, N, T, P, K;     /* scenes, agents per scene, observed / predicted frames, samples */
+  int U, E, He, D;       /* hidden units, embedding, edge-MLP width, static-context grid   */
+  int relational, prec;  /* MMT_PREC_*                                                     */
+  int img_h;             /* MMT_OP_STATIC_CONTEXT: image height                            */
+} mmt_shape;
+#define MMT_OP_FORECAST 0            /* mmt_forecast_f32 workspace                          */
+#define MMT_OP_EDGE_MLP 1            /* mmt_edge_mlp_{f32,bf16} work                        */
+#define MMT_OP_STATIC_CONTEXT 2      /* mmt_static_context_f32 workspace                    */
+#define MMT_OP_GATE_WEIGHTS_BF16 3   /* mmt_pack_gate_weights_bf16 image                    */
+#define MMT_OP_GATE_WEIGHTS_BF16X3 4 /* mmt_pack_gate_weights_bf16x3 image                  */
+#define MMT_OP_EDGE_WEIGHTS_BF16 5   /* mmt_pack_edge_weights_bf16 image                    */
+int mmt_workspace_bytes(int op, const mmt_shape* shape, size_t* out);
+
 #ifdef __cplusplus
 }
 #endif

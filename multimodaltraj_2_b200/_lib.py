@@ -31,6 +31,10 @@ class EdgeWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("W1", "b1", "W2", "b2", "w_out", "b_out")] + [("He", C.c_int)]
 
 
+class Shape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("S", "N", "T", "P", "K", "U", "E", "He", "D", "relational", "prec", "img_h")]
+
+
 class ForecastCfg(C.Structure):
     _fields_ = [("S", C.c_int), ("N", C.c_int), ("T", C.c_int), ("P", C.c_int), ("K", C.c_int),
                 ("r2", C.c_float), ("inv_2sigma2", C.c_float), ("relational", C.c_int), ("prec", C.c_int),
@@ -86,6 +90,9 @@ SIGNATURES = {
     "mmt_gsk_gates_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "mmt_gsk_cell_backward_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp,
                                             vp]),
+    "mmt_allreduce_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "mmt_allreduce_max_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "mmt_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(Shape), C.POINTER(C.c_size_t)]),
     "mmt_rollout_bf16": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_float, vp, vp, vp]),
 }
@@ -105,10 +112,10 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not path.exists():
-        if not build_if_missing:
-            raise RuntimeError(f"{path} is missing; run `python -m multimodaltraj_2_b200.build`")
-        _build.build()
+    if path == _build.LIB and build_if_missing:
+        _build.build()                   # no-op when the library matches the sources (content hash); else nvcc runs
+    elif not path.exists():
+        raise RuntimeError(f"{path} is missing; run `python -m multimodaltraj_2_b200.build`")
     lib = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported

@@ -19,6 +19,11 @@ int launch_cell_tc(const float* x, const float* h, const float* c, const float* 
                    int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos, int x3,
                    cudaStream_t stream);
 
+int launch_decode(const float* params, const float* eps, uint64_t seed, uint64_t agent_offset, const float* last_obs,
+                  int lo_stride, const float* gt, int gt_stride, const uint8_t* valid, int A, int P, int K, float* ade,
+                  float* fde, int32_t* best_k, float* best_ade, float* best_fde, float* best_traj, float* eps_out,
+                  cudaStream_t stream);
+
 int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
                         const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
                         const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
@@ -59,18 +64,9 @@ __global__ void __launch_bounds__(256) prep_step_kernel(const float* __restrict_
   reinterpret_cast<float4*>(x)[r] = make_float4(d.x, d.y, v.x, v.y);
 }
 
-__global__ void __launch_bounds__(256) gather_frames_kernel(const float* __restrict__ pos, int R, int F, int T, int P,
-                                                            float* __restrict__ last_obs, float* __restrict__ gt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * (P + 1)) return;
-  const int r = i / (P + 1), k = i - r * (P + 1);
-  const float2 v = __ldg(reinterpret_cast<const float2*>(pos) + (size_t)r * F + (T - 1 + k));
-  if (k == 0) reinterpret_cast<float2*>(last_obs)[r] = v;
-  else reinterpret_cast<float2*>(gt)[(size_t)r * P + (k - 1)] = v;
-}
 
 struct Workspace {
-  float *pbuf[3], *x, *hc[2], *mhc, *mf, *kern, *score, *ework, *params, *last_obs, *gt;
+  float *pbuf[3], *x, *hc[2], *mhc, *mf, *kern, *score, *ework, *params;
   void* epacked;        // bf16 operand images of the edge-MLP weights (relational bf16 modes)
   uint8_t* adj;
   // bf16-state fast path (non-relational bf16 mode): h, mh, mc bf16 [R,U]; c fp32 [R,U]
@@ -121,8 +117,6 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   w.ework = (float*)take(cfg->relational ? 2 * R * He * 4 : 0);
   w.epacked = take(cfg->relational && cfg->prec != MMT_PREC_F32 && cfg->prec != MMT_PREC_BF16X3 && U == 128 && He == 128 ? 96 * 1024 : 0);
   w.params = (float*)take(R * cfg->P * 5 * 4);
-  w.last_obs = (float*)take(R * 2 * 4);
-  w.gt = (float*)take(R * cfg->P * 2 * 4);
   w.bytes = off;
   return w;
 }
@@ -267,11 +261,10 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       ic = old_p;
     }
   }
-  gather_frames_kernel<<<(R * (P + 1) + 255) / 256, 256, 0, stream>>>(pos, R, F, T, P, w.last_obs, w.gt);
-  count_launch();
-  if ((rc = check_launch("gather_frames_kernel"))) return rc;
-  return mmt_decode_score_f32(par, eps, cfg->seed, cfg->agent_offset, w.last_obs, w.gt, valid, S, N, P, cfg->K, ade,
-                              fde, best_k, best_ade, best_fde, best_traj, stream);
+  // the fused epilogue reads the last observed point and the ground truth straight out of pos[S,N,F,2]
+  MMT_ALIGNED(eps);
+  return launch_decode(par, eps, cfg->seed, cfg->agent_offset, pos + (size_t)(T - 1) * 2, 2 * F, pos + (size_t)T * 2, 2 * F,
+                       valid, R, P, cfg->K, ade, fde, best_k, best_ade, best_fde, best_traj, nullptr, stream);
 }
 
 extern "C" int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,

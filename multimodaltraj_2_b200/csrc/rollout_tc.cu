@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   // then a link-time constant and every barrier address / UMMA descriptor derived from it is uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* const smem = smem_dyn;
-  require_smem_alignment(smem, a.trap, 1);
-  if (DIAG && (a.flags & 1024) && blockIdx.x == 1 && threadIdx.x == 33) trap_report(a.trap, 0x1EE, 0xABCD, 1);   // self-test of the trap record
+  uint32_t* const trap = DIAG ? a.trap : nullptr;   // production: bare traps (see tc_common.cuh: trap_report)
+  require_smem_alignment(smem, trap, 1);
+  if (DIAG && (a.flags & 1024) && blockIdx.x == 1 && threadIdx.x == 33) trap_report(trap, 0x1EE, 0xABCD, 1);   // self-test of the trap record
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + RS_BAR;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
       const uint32_t total = (DIAG && (a.flags & 1)) ? 0u : (uint32_t)my_tiles * nsteps * RO_NCH;
       for (uint32_t it = warp - RO_WWARPS; it < total; it += RO_NPROD) {
         const uint32_t s = it % RO_NSTAGE, ph = (it / RO_NSTAGE) & 1u, j = it % RO_NCH;
-        if (DIAG && (a.flags & 64)) mbar_wait_spin(W_EMPTY + 8 * s, ph ^ 1u, a.trap, RT_W_EMPTY); else mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, a.trap, RT_W_EMPTY);
+        if (DIAG && (a.flags & 64)) mbar_wait_spin(W_EMPTY + 8 * s, ph ^ 1u, trap, RT_W_EMPTY); else mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, trap, RT_W_EMPTY);
         if (DIAG && (a.flags & 512) && j == 6 && ((it / RO_NCH) % 5u) == 2u) {   // fault injection: a late weight chunk (tests/test_gpu_parity.py)
           const long long t0 = clock64();
           while (clock64() - t0 < 6000) {}
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               const long long w0 = timed ? clock64() : 0;
               // no tcgen05.fence here: the stage was written by the async proxy (bulk copy -> mbarrier), not by another
               // thread's tcgen05 operation; a fence per chunk drained the MMA pipeline (pass 2650 -> see profiles/)
-              if (!(DIAG && (a.flags & 128))) mbar_wait_warp(W_FULL + 8 * s, (sc + (j / RO_NSTAGE)) & 1u, a.trap, RT_W_FULL);   // 128: timing experiment
+              if (!(DIAG && (a.flags & 128))) mbar_wait_warp(W_FULL + 8 * s, (sc + (j / RO_NSTAGE)) & 1u, trap, RT_W_FULL);   // 128: timing experiment
               if (timed) wwait += clock64() - w0;
             }
             const uint64_t db = d_w + (uint64_t)((s * RO_STAGE_BYTES) >> 4);
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             constexpr int p = decltype(p_tag)::value;
             const uint32_t pc = pc0 + p;       // global pass counter: accumulator p & 1, use number pc >> 1
             constexpr uint32_t b = p & 1u;
-            mbar_wait_warp(ACC_EMPTY + 8 * b, ((pc >> 1) & 1u) ^ 1u, a.trap, RT_ACC_EMPTY);
+            mbar_wait_warp(ACC_EMPTY + 8 * b, ((pc >> 1) & 1u) ^ 1u, trap, RT_ACC_EMPTY);
             // The weight ring is ONE ring shared by the two issuers, and an mbarrier parity wait is only meaningful for a
             // waiter at most one phase ahead: chunk j of this pass re-uses the stage of chunk j - 4 of the previous pass,
             // which the OTHER issuer consumes.  Were that chunk still in flight when this issuer reached its wait, the
@@ -298,8 +299,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             // the extra W_EMPTY arrival would derail the producers (seen as an expired bounded wait = CUDA 719 once the
             // weight stream ran > ~1000 clk late).  So a pass starts only after the previous pass has been issued whole.
 #ifndef RO_NO_PASS_ORDER   // (defined only by scratch/ro_race.py's build of the pre-fix protocol)
-            if constexpr (p == 2) mbar_wait_warp(P1_ISSUED, par, a.trap, RT_P1_ISSUED);
-            if constexpr (p == 3) mbar_wait_warp(P2_ISSUED, par, a.trap, RT_P2_ISSUED);
+            if constexpr (p == 2) mbar_wait_warp(P1_ISSUED, par, trap, RT_P1_ISSUED);
+            if constexpr (p == 3) mbar_wait_warp(P2_ISSUED, par, trap, RT_P2_ISSUED);
 #endif
             tc_fence_after();
             const uint32_t d_tmem = tmem_u + (b ? RT_ACC1 : RT_ACC0);
@@ -322,15 +323,15 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             //      have released accumulator 1 after its last pass (on a tile's first step: once E_READY has published
             //      the zeroed state).
             const uint32_t d0 = tmem_u + RT_ACC0;
-            mbar_wait_warp(ACC_EMPTY, ((pc0 >> 1) & 1u) ^ 1u, a.trap, RT_ACC_EMPTY_P0);
+            mbar_wait_warp(ACC_EMPTY, ((pc0 >> 1) & 1u) ^ 1u, trap, RT_ACC_EMPTY_P0);
             if (t > 0) {
-              mbar_wait_warp(ACC_EMPTY + 8, (((pc0 + 1) >> 1) & 1u) ^ 1u, a.trap, RT_ACC1_EMPTY_P0);
+              mbar_wait_warp(ACC_EMPTY + 8, (((pc0 + 1) >> 1) & 1u) ^ 1u, trap, RT_ACC1_EMPTY_P0);
               tc_fence_after();
               if (DIAG && dbg) dbg[3] = clock64();
               gate_chunk(d0, std::integral_constant<int, 0>{});
               gate_chunk(d0, std::integral_constant<int, 1>{});
             }
-            mbar_wait_warp(ATT_READY, par, a.trap, RT_ATT_READY);
+            mbar_wait_warp(ATT_READY, par, trap, RT_ATT_READY);
             tc_fence_after();
             if (DIAG && dbg) dbg[0] = clock64();
 #if RO_AGG256
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                         kIdescAggMN, ks ? 1u : 0u);
 #endif
             if (DIAG && dbg) dbg[1] = clock64();
-            mbar_wait_warp(E_READY, par, a.trap, RT_E_READY);
+            mbar_wait_warp(E_READY, par, trap, RT_E_READY);
             tc_fence_after();
             if (DIAG && dbg) dbg[2] = clock64();
             if (t == 0) {
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               gate_chunk(d0, std::integral_constant<int, 1>{});
             }
             gate_chunk(d0, std::integral_constant<int, 2>{});
-            mbar_wait_warp(MH_READY, par, a.trap, RT_MH_READY_I0);   // the mh chunks wait for the conversion
+            mbar_wait_warp(MH_READY, par, trap, RT_MH_READY_I0);   // the mh chunks wait for the conversion
             tc_fence_after();
             if (DIAG && dbg) dbg[12] = clock64();
             gate_chunk(d0, std::integral_constant<int, 3>{});
@@ -377,8 +378,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             __syncwarp();
             gate_pass(std::integral_constant<int, 2>{});
           } else {
-            mbar_wait_warp(MH_READY, par, a.trap, RT_MH_READY_I1);   // accumulator 1 aliases the mh accumulator: wait for its conversion
-            mbar_wait_warp(P0_ISSUED, par, a.trap, RT_P0_ISSUED);
+            mbar_wait_warp(MH_READY, par, trap, RT_MH_READY_I1);   // accumulator 1 aliases the mh accumulator: wait for its conversion
+            mbar_wait_warp(P0_ISSUED, par, trap, RT_P0_ISSUED);
             tc_fence_after();
             gate_pass(std::integral_constant<int, 1>{});
             gate_pass(std::integral_constant<int, 3>{});
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
         mbar_arrive_warp(E_READY);
         if (DIAG && dbg) dbg[2] = clock64();
         // ---- (d) mh: accumulator -> normalise -> bf16 -> A-operand columns (this thread: row r, units 32 cs .. +31)
-        mbar_wait(AGG_FULL, par, a.trap, RT_AGG_FULL);
+        mbar_wait(AGG_FULL, par, trap, RT_AGG_FULL);
         tc_fence_after();
         if (DIAG && dbg) dbg[3] = clock64();
 #pragma unroll
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           for (int p = 0; p < RO_NP; ++p) {
             const uint32_t pc = sc * RO_NP + p;
             const uint32_t b = p & 1u, bph = (pc >> 1) & 1u;
-            mbar_wait(ACC_FULL + 8 * b, bph, a.trap, RT_ACC_FULL);
+            mbar_wait(ACC_FULL + 8 * b, bph, trap, RT_ACC_FULL);
             tc_fence_after();
             if (DIAG && dbg) dbg[5 + 2 * p] = clock64();
             const uint32_t t_acc = t_row + (b ? RT_ACC1 : RT_ACC0) + cs * 8;

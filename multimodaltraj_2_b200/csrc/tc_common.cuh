@@ -30,10 +30,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// A trap names itself first: the kernel's trap record is a 16-word block of host-mapped pinned memory (capi.cu:
+// A trap names itself first: the trap record is a 16-word block of host-mapped pinned memory (capi.cu:
 // trap_record(); reported by mmt_last_trap and appended to the error text of the next failing launch check), written
 // with a system-scope fence before __trap() kills the context.  word 0 = site code (kernel << 8 | wait), 1 = CTA,
 // 2 = thread, 3 = barrier shared address, 4 = awaited parity, 5 = extra.
+// rec == nullptr (a compile-time constant in rollout_tc_kernel's production instantiation) reduces this to a bare trap:
+// measured on a B200 (profiles/r02_trap_styles.txt), carrying the record pointer into that kernel's wait loops costs
+// 5 % (2.058 vs 1.957 ms; a pointer in a __device__ global 2-8 %: the kernel sits at its 96-register cap), so there only
+// the diagnostics instantiation (MMT_RO_FLAGS != 0) names its site.
 static __device__ __forceinline__ void trap_report(uint32_t* rec, uint32_t site, uint32_t bar, uint32_t parity, uint32_t extra = 0) {
   if (rec) {
     volatile uint32_t* r = rec;

@@ -513,3 +513,38 @@ def rowsoftmax(x):
     _lib.check(lib.mmt_rowsoftmax_f32(_p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], _stream()),
                "mmt_rowsoftmax_f32")
     return y
+
+
+# --------------------------------------------------------------------------------------------
+_comm_cache = {}
+
+
+def nccl_comm_ptr(group=None):
+    """ncclComm_t of the process group's NCCL backend on the current device, as an integer (None if the group is not
+    NCCL-backed): what mmt_allreduce_f32 takes.  The communicator stays owned by torch.distributed."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    pg = group if group is not None else dist.distributed_c10d._get_default_group()
+    key = (id(pg), torch.cuda.current_device())
+    if key not in _comm_cache:
+        try:
+            be = pg._get_backend(torch.device("cuda", torch.cuda.current_device()))
+            ptr = be._comm_ptr() if hasattr(be, "_comm_ptr") else None
+        except Exception:            # noqa: BLE001 -- gloo group, or a torch without _comm_ptr
+            ptr = None
+        _comm_cache[key] = ptr if ptr else None
+    return _comm_cache[key]
+
+
+def allreduce_(t, op="sum", group=None):
+    """In-place all-reduce of a contiguous fp32 CUDA tensor over the ranks of ``group`` through the C-ABI
+    (mmt_allreduce_f32 / _max_f32: NCCL over NVLink on the current stream).  Raises if the group has no NCCL communicator."""
+    lib = _lib.load()
+    _chk(t, torch.float32, "t")
+    comm = nccl_comm_ptr(group)
+    if comm is None:
+        raise RuntimeError("allreduce_: the process group has no NCCL communicator on this device")
+    fn = lib.mmt_allreduce_f32 if op == "sum" else lib.mmt_allreduce_max_f32
+    _lib.check(fn(C.c_void_p(comm), _p(t), t.numel(), _stream()), "mmt_allreduce_f32")
+    return t

@@ -68,7 +68,7 @@ def main(argv=None, params=None, device=None, results_path=None):
             continue
         true_traj = pos[s][v]
         pred_traj = np.concatenate([true_traj[:, :T], best[s][v]], 1)
-        a, f, c = get_mean_error(pred_traj, true_traj, T, args.maxNumPeds)
+        a, f, c = get_mean_error(pred_traj, true_traj, T, min(args.maxNumPeds, len(true_traj)))
         tot_a, tot_f, cnt = tot_a + a, tot_f + f, cnt + 1
         results.append((true_traj[:, :T], pred_traj))
     out = dict(realdata.public(res), mean_error_ade=tot_a / max(cnt, 1), mean_error_fde=tot_f / max(cnt, 1), scenes_scored=cnt)

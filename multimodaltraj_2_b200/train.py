@@ -215,9 +215,16 @@ def allreduce_mean_(flat, counts=None):
     agent-steps turns the reduced sum into the gradient of the global mean loss, whatever the sharding."""
     dist = torch.distributed
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat)
-        if counts is not None:
-            dist.all_reduce(counts)
+        if flat.is_cuda and ops.nccl_comm_ptr() is not None:
+            # the C-ABI collective (mmt_allreduce_f32): NCCL on the CURRENT stream, right behind the kernels that produced
+            # the bucket -- no hop to the process group's internal stream, no extra event pair per step
+            ops.allreduce_(flat)
+            if counts is not None:
+                ops.allreduce_(counts)
+        else:                                    # gloo (the CPU tests of the host logic)
+            dist.all_reduce(flat)
+            if counts is not None:
+                dist.all_reduce(counts)
     return flat
 
 

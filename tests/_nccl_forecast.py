@@ -37,6 +37,14 @@ def main():
         tot = torch.stack([ref["best_ade"].sum(), ref["best_fde"].sum()]) if world == 1 else None
         if tot is not None:
             assert torch.allclose(t, tot, rtol=1e-5)
+    # the C-ABI collective (mmt_allreduce_f32 over the process group's own communicator) == torch's all_reduce
+    g = torch.arange(131072, device=dev, dtype=torch.float32) * (rank + 1)
+    want = g.clone()
+    dist.all_reduce(want)
+    got = ops.allreduce_(g.clone())
+    assert torch.equal(got, want), (rank, "sum")
+    m = torch.tensor([float(rank), -float(rank)], device=dev)
+    assert torch.equal(ops.allreduce_(m, op="max"), torch.tensor([float(world - 1), 0.0], device=dev))
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
