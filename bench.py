@@ -733,7 +733,8 @@ def run_train(args, rank, world, local_rank):
                           "value": int(valid_h.sum()) * world / (ms_step * 1e-3), "unit": "agent-trajectories/s", "n_gpus": world,
                           "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32" if args.train_gemm == "fp32" else "f32 kernels, tf32 tensor-core GEMMs in the backward (fp32 accumulation)",
+                          "dtype": "f32" if args.train_gemm == "fp32" else "f32 kernels, tf32 tensor-core contractions (fp32 accumulation)"
+                                   + (": mmt_gemm_tf32 (TMA + tcgen05)" if args.train_gemm == "tc" else ": library GEMMs"),
                           "data": "synthetic",
                           "config": {"workload": f"{S} scenes x {N} agents per GPU, obs {T_OBS} / pred {P_PRED}, g2k_lstm_{'mcr' if relational else 'mc'} training step",
                                      "backward_gemm": args.train_gemm, "lr": 1e-3,
@@ -760,7 +761,8 @@ def main():
     ap.add_argument("--config", default="c3", choices=["c3", "c1", "c5"],
                     help="c3 (default): synthetic crowds, the headline; c1 / c5: the real-data configs on data/ (extra)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
-    ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32"], help="--mode train: arithmetic of the backward GEMMs")
+    ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32", "tc"],
+                    help="--mode train: contractions of the step: fp32 / tf32 library GEMMs, tc = mmt_gemm_tf32 (TMA + tcgen05) and mmt_aggregate_transpose_f32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -76,6 +76,11 @@ int mmt_neighbor_index_i32(const uint8_t* adj, int S, int N, int max_nbr, int32_
 int mmt_aggregate_f32(const float* logits, const uint8_t* adj, const float* feat, int S, int N,
                       int C, float* attn, float* out, void* stream);
 
+/* Adjoint of the aggregation (backward pass of the training step): out[S,N,C] = attn^T d per scene,
+ * out_j = sum_i attn_ij d_i, attn[S,N,N] as written by mmt_aggregate_f32 (zero off the edges), d[S,N,C].
+ * Deterministic (a gather in ascending i, no atomics). */
+int mmt_aggregate_transpose_f32(const float* attn, const float* d, int S, int N, int C, float* out, void* stream);
+
 /* ---- relational edge MLP (g2k_lstm_mcr only) ------------------------------------------------
  * Replaces relational_inf_models/nri_learned.py:5-28 (infer_rlns sigmoid gate) with the fNRI
  * node2edge -> 2-layer ELU MLP -> score it stubs out.
@@ -307,6 +312,17 @@ int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, c
 
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);
+
+/* ---- tensor-core GEMM of the training step (TMA tensor maps -> tcgen05.mma.kind::tf32 -> TMEM) -------------------
+ * The reference has no backward pass (the flags of argParser.py:40-47 are never read); the training step
+ * defined for it contracts  dW += [e|h|mh]^T dz  (K = all agent rows),  dA = dz W^T  and their
+ * smaller relatives.  C[M,N] = alpha * op(A) op(B) (+ C if accumulate), fp32 in memory, operands rounded to tf32 by
+ * the tensor core, fp32 accumulation.  op(A) is [M,K]: transA = 0 -> A is [M,K] row-major (lda >= K), transA = 1 -> A
+ * is [K,M] row-major (lda >= M); op(B) is [K,N]: transB = 0 -> B is [K,N] row-major (ldb >= N), transB = 1 -> B is
+ * [N,K] row-major (ldb >= K).  lda, ldb multiples of 4; A, B 16-byte aligned.  Small outputs are split over K and
+ * accumulated with red.global.add (summation order not fixed). */
+int mmt_gemm_tf32(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C, int ldc, int M,
+                  int N, int K, float alpha, int accumulate, void* stream);
 
 /* ---- the one collective of the path: gradient all-reduce of data-parallel training -----------
  * The reference has no parallelism (train.py:28-41 is a serial loop over datasets and batches); the north_star asks

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mmt_pairwise_adj_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),
     "mmt_neighbor_index_i32": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "mmt_aggregate_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "mmt_aggregate_transpose_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "mmt_edge_mlp_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                    C.c_size_t, vp]),
     "mmt_edge_weights_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),
@@ -90,6 +91,8 @@ SIGNATURES = {
     "mmt_gsk_gates_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "mmt_gsk_cell_backward_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp,
                                             vp]),
+    "mmt_gemm_tf32": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_float, C.c_int, vp]),
     "mmt_allreduce_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "mmt_allreduce_max_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "mmt_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(Shape), C.POINTER(C.c_size_t)]),

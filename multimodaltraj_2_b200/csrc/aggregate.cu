@@ -84,6 +84,51 @@ __global__ void __launch_bounds__(kAggWarps * 32) aggregate_kernel(
   }
 }
 
+// Transposed aggregation of the backward pass: out_j = sum_i a_ij d_i (the adjoint of out_i = sum_j a_ij feat_j),
+// i.e. att^T x d per scene.  One warp per output row j: the (sparse) column j of the attention matrix is compacted
+// with ballots, then the warp streams the rows d_i of its in-neighbours as float4 -- a gather in a fixed order
+// (ascending i), so the result is deterministic (no atomics).
+__global__ void __launch_bounds__(kAggWarps * 32) aggregate_transpose_kernel(
+    const float* __restrict__ att, const float* __restrict__ d, int rows, int N, int C, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* nb_idx = reinterpret_cast<int*>(smem_raw) + warp * N;
+  float* nb_w = reinterpret_cast<float*>(smem_raw) + kAggWarps * N + warp * N;
+  for (int r = blockIdx.x * kAggWarps + warp; r < rows; r += gridDim.x * kAggWarps) {
+    const int s = r / N, j = r - s * N;
+    const float* acol = att + (size_t)s * N * N + j;
+    int n = 0;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+      const int i = i0 + lane;
+      const float w = i < N ? __ldg(acol + (size_t)i * N) : 0.0f;
+      const bool a = w != 0.0f;
+      const unsigned m = __ballot_sync(0xffffffffu, a);
+      if (a) {
+        const int p = n + __popc(m & ((1u << lane) - 1u));
+        nb_idx[p] = i;
+        nb_w[p] = w;
+      }
+      n += __popc(m);
+    }
+    __syncwarp();
+    const float* dbase = d + (size_t)s * N * C;
+    float* orow = out + (size_t)r * C;
+    for (int c0 = lane * 4; c0 < C; c0 += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < n; ++k) {
+        const float w = nb_w[k];
+        const float4 f = __ldg(reinterpret_cast<const float4*>(dbase + (size_t)nb_idx[k] * C + c0));
+        acc.x = fmaf(w, f.x, acc.x);
+        acc.y = fmaf(w, f.y, acc.y);
+        acc.z = fmaf(w, f.z, acc.z);
+        acc.w = fmaf(w, f.w, acc.w);
+      }
+      *reinterpret_cast<float4*>(orow + c0) = acc;
+    }
+    __syncwarp();
+  }
+}
+
 int launch_aggregate(const float* logits, const float* logits2, const uint8_t* adj, const float* feat, int S, int N,
                      int C, int ld_feat, float* attn, float* out, int ld_out, cudaStream_t stream) {
   const long rows = (long)S * N;
@@ -112,4 +157,25 @@ extern "C" int mmt_aggregate_f32(const float* logits, const uint8_t* adj, const 
   MMT_ALIGNED(out);
   if (S == 0) return MMT_OK;
   return launch_aggregate(logits, nullptr, adj, feat, S, N, C, C, attn, out, C, (cudaStream_t)stream);
+}
+
+extern "C" int mmt_aggregate_transpose_f32(const float* attn, const float* d, int S, int N, int C, float* out,
+                                           void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(S >= 0 && N > 0 && N <= 1024 && C > 0 && C % 4 == 0, "need 0 < N <= 1024, C % 4 == 0");
+  if (S == 0) return MMT_OK;
+  MMT_REQUIRE(attn && d && out, "attn/d/out must not be NULL");
+  MMT_ALIGNED(d);
+  MMT_ALIGNED(out);
+  const long rows = (long)S * N;
+  const long blocks = (rows + kAggWarps - 1) / kAggWarps;
+  const int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
+  const size_t smem = (size_t)kAggWarps * N * 8;
+  if (smem > 48 * 1024) {
+    static unsigned long long smem_opted[1] = {};
+    if (int rc = opt_in_smem(reinterpret_cast<const void*>(&aggregate_transpose_kernel), kAggWarps * 1024 * 8, &smem_opted[0])) return rc;
+  }
+  aggregate_transpose_kernel<<<grid, kAggWarps * 32, smem, (cudaStream_t)stream>>>(attn, d, (int)rows, N, C, out);
+  count_launch();
+  return check_launch("aggregate_transpose_kernel");
 }

@@ -43,15 +43,15 @@ uint32_t* trap_record() {
 }
 
 // "<kernel>/<wait>" of a trap site code (tc_common.cuh: trap_report).  Kernel ids: 1 rollout_tc, 2 gsk_cell_tc,
-// 3 graph_aggregate_mma, 4 node_proj_tc, 5 edge_mlp_tc; wait 0xFF = shared-memory base not 1024-byte aligned.
+// 3 graph_aggregate_mma, 4 node_proj_tc, 5 edge_mlp_tc, 6 gemm_tf32; wait 0xFF = shared-memory base not 1024-byte aligned.
 static void describe_trap(char* out, size_t n) {
   const uint32_t* r = g_trap.load(std::memory_order_acquire);
   if (!r || r[0] == 0) { out[0] = 0; return; }
   static const char* kern[] = {"?", "rollout_tc_kernel", "gsk_cell_tc_kernel", "graph_aggregate_mma_kernel",
-                               "node_proj_tc_kernel", "edge_mlp_tc_kernel"};
+                               "node_proj_tc_kernel", "edge_mlp_tc_kernel", "gemm_tf32_kernel"};
   const uint32_t k = r[0] >> 8, w = r[0] & 0xFFu;
   snprintf(out, n, " [device trap: %s site 0x%02x%s, CTA %u thread %u, barrier smem 0x%x parity %u]",
-           k < 6 ? kern[k] : "?", w, w == 0xFF ? " (smem base misaligned)" : " (bounded mbarrier wait expired)", r[1], r[2],
+           k < 7 ? kern[k] : "?", w, w == 0xFF ? " (smem base misaligned)" : " (bounded mbarrier wait expired)", r[1], r[2],
            r[3], r[4]);
 }
 

@@ -78,6 +78,16 @@ def aggregate(logits, adj, feat, want_attn=True):
     return attn, out
 
 
+def aggregate_transpose(attn, d):
+    """out[S,N,C] = attn^T @ d per scene (mmt_aggregate_transpose_f32): the adjoint of ``aggregate``."""
+    lib = _lib.load()
+    _chk(attn, torch.float32, "attn"); _chk(d, torch.float32, "d")
+    S, N, Cc = d.shape
+    out = torch.empty_like(d)
+    _lib.check(lib.mmt_aggregate_transpose_f32(_p(attn), _p(d), S, N, Cc, _p(out), _stream()), "mmt_aggregate_transpose_f32")
+    return out
+
+
 def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out, prec=PREC_F32):
     """score[S,N,N] of the relational edge MLP on the edges of adj (0 elsewhere).  prec = PREC_BF16 runs the
     tcgen05 version (U = He = 128)."""
@@ -513,6 +523,29 @@ def rowsoftmax(x):
     _lib.check(lib.mmt_rowsoftmax_f32(_p(x), _p(y), x.numel() // x.shape[-1], x.shape[-1], _stream()),
                "mmt_rowsoftmax_f32")
     return y
+
+
+# --------------------------------------------------------------------------------------------
+def gemm_tf32(A, B, transA=False, transB=False, out=None, alpha=1.0, accumulate=False):
+    """C = alpha * op(A) @ op(B) (+ C) on the tensor cores (mmt_gemm_tf32: TMA tensor maps -> tcgen05 kind::tf32, fp32
+    accumulation in TMEM).  A, B: 2-D fp32 CUDA tensors whose last dimension is contiguous (row stride a multiple of 4)."""
+    lib = _lib.load()
+    for n, t in (("A", A), ("B", B)):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+            raise ValueError(f"gemm_tf32: {n} must be a 2-D fp32 CUDA tensor with a contiguous last dimension")
+    M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
+    K2, N = (B.shape[1], B.shape[0]) if transB else (B.shape[0], B.shape[1])
+    if K != K2:
+        raise ValueError(f"gemm_tf32: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm_tf32: accumulate needs out")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    if tuple(out.shape) != (M, N) or out.stride(1) != 1:
+        raise ValueError(f"gemm_tf32: out must be [{M}, {N}] with a contiguous last dimension")
+    _lib.check(lib.mmt_gemm_tf32(_p(A), A.stride(0), int(transA), _p(B), B.stride(0), int(transB), _p(out), out.stride(0),
+                                 M, N, K, float(alpha), int(accumulate), _stream()), "mmt_gemm_tf32")
+    return out
 
 
 # --------------------------------------------------------------------------------------------

@@ -256,8 +256,12 @@ class Trainer:
         #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2); the
         #          forward gate GEMM then is a library tensor-core GEMM + mmt_gsk_gates_f32 as well (z kept, not recomputed)
         #          instead of the fused fp32 CUDA-core cell kernel.
-        if gemm not in ("fp32", "tf32"):
-            raise ValueError("gemm must be 'fp32' or 'tf32'")
+        #   "tc"   this library's own contractions: mmt_gemm_tf32 (TMA tensor maps -> tcgen05.mma.kind::tf32 -> TMEM; split-K
+        #          with red.add for the weight gradients) for the gate GEMM forward, A^T dz and dz W^T -- 97 % of the step's
+        #          FLOPs -- and mmt_aggregate_transpose_f32 for att^T [d mh | d mc]; same tolerance as "tf32".  Only the 5-wide
+        #          head and the 4-wide embedding products (1 % of the FLOPs) stay library calls.
+        if gemm not in ("fp32", "tf32", "tc"):
+            raise ValueError("gemm must be 'fp32', 'tf32' or 'tc'")
         self.gemm = gemm
         # relational: g2k_lstm_mcr -- the attention logits are kern + the edge-MLP score (mmt_edge_mlp_f32); its backward
         # (softmax -> per-edge two-layer ELU MLP -> node projections) runs on the compacted edge list with library ops
@@ -304,7 +308,14 @@ class Trainer:
             rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc)
             if self.relational:
                 rec["adj"] = adj
-            if self.gemm == "tf32":
+            if self.gemm == "tc":
+                # gate GEMM on this library's tcgen05 tf32 GEMM + mmt_gsk_gates_f32; A, z are kept for the backward
+                e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
+                A = torch.cat([e, rec["h"], mh], -1)
+                z = ops.gemm_tf32(A, p.W).add_(p.b)
+                hn, cn, mf = ops.gsk_gates(z, rec["c"], mc, vflat, p)
+                rec["e"], rec["z"], rec["A"] = e, z, A
+            elif self.gemm == "tf32":
                 # gate GEMM on the tensor cores (library GEMM) + mmt_gsk_gates_f32; z and e are kept for the backward
                 e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
                 z = torch.addmm(p.b, torch.cat([e, rec["h"], mh], -1), p.W)
@@ -340,19 +351,29 @@ class Trainer:
                 Gh = Gh + dhm[:, :U]
                 d_mf = dhm[:, U:].contiguous()
             e = r["e"] if "e" in r else torch.relu(r["x"] @ p.W_e + p.b_e)
-            A = torch.cat([e, r["h"], r["mh"]], -1)
+            A = r.pop("A") if "A" in r else torch.cat([e, r["h"], r["mh"]], -1)
             z = r.pop("z") if "z" in r else torch.addmm(p.b, A, p.W)
             dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep)
-            g["W"] += A.t() @ dz
+            tc = self.gemm == "tc"
+            if tc:
+                ops.gemm_tf32(A, dz, transA=True, out=g["W"], accumulate=True)      # dW += A^T dz  (K = all agent rows)
+                dA = ops.gemm_tf32(dz, p.W, transB=True)                           # dA  = dz W^T
+            else:
+                g["W"] += A.t() @ dz
+                dA = dz @ p.W.t()
             g["b"] += dz.sum(0)
-            dA = dz @ p.W.t()
             dpre = dA[:, :E] * (e > 0)
             g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
-            attT = r["att"].transpose(1, 2)
             d_mh = dA[:, E + U:].reshape(S, N, U)
-            Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
-            Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
+            if tc:
+                back = ops.aggregate_transpose(r["att"], torch.cat([d_mh, dmc.view(S, N, U)], -1).contiguous()).reshape(R, 2 * U)
+                Gh = dA[:, E:E + U] + back[:, :U]
+                Gc = (dc + back[:, U:]).contiguous()
+            else:
+                attT = r["att"].transpose(1, 2)
+                Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
+                Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
             if self.relational:
                 Gh = Gh + self._edge_backward(r, d_mh, dmc.view(S, N, U), g, S, N)
         g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]

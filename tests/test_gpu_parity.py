@@ -509,15 +509,18 @@ def test_train_gradients_match_autograd_oracle(cuda):
         assert rel_err(npy(g[k]).astype(np.float64), want[k]) < 2e-3, k
 
 
-def test_train_gradients_tf32_gemm_mode(cuda):
-    """Stated separately from the fp32 parity mode: tensor-core (tf32) backward GEMMs, 2e-2 of the largest entry."""
+@pytest.mark.parametrize("gemm", ["tf32", "tc"])
+def test_train_gradients_tf32_gemm_mode(cuda, gemm):
+    """Stated separately from the fp32 parity mode: tensor-core (tf32) contractions, 2e-2 of the largest entry -- as library
+    GEMMs ("tf32") and as this library's own kernels ("tc": mmt_gemm_tf32 = TMA + tcgen05 kind::tf32 for the gate GEMM,
+    A^T dz and dz W^T; mmt_aggregate_transpose_f32 for att^T d)."""
     import train_b as o_t
     from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS
     S, N = 3, 16
     pos, vis, valid = synth.make_crowd(S, N, seed=5, half_extent=3.0, ragged=True)
     p = synth.init_params(seed=1)
     want_loss, want = o_t.loss_and_grads(pos, vis, valid, p)
-    tr = Trainer(ops.CellParams.from_numpy(p, cuda), gemm="tf32")
+    tr = Trainer(ops.CellParams.from_numpy(p, cuda), gemm=gemm)
     was = torch.backends.cuda.matmul.allow_tf32
     loss, g = tr.loss_and_grads(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
     assert torch.backends.cuda.matmul.allow_tf32 == was        # the global flag is restored
