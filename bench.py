@@ -486,7 +486,7 @@ def run_ours(args, rank, world, local_rank):
         h, c, mh, mc = (torch.randn((R, HIDDEN), device=dev) * 0.5 for _ in range(4))
         vflat = valid.reshape(-1).contiguous()
         cur = torch.randn((R, 2), device=dev)
-        cprec = ops.PREC_F32 if prec == ops.PREC_F32 else ops.PREC_BF16
+        cprec = prec if prec in (ops.PREC_F32, getattr(ops, "PREC_BF16X3", -1)) else ops.PREC_BF16
         for _ in range(3):
             ops.gsk_cell(x, h, c, mh, mc, vflat, params, cprec, cur_pos=cur, want_head=True)
         torch.cuda.synchronize()
@@ -499,10 +499,13 @@ def run_ours(args, rank, world, local_rank):
         flops = 2.0 * R * (EMBED + 2 * HIDDEN) * 3 * HIDDEN
         achieved = flops / (cell_ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"]
-        roof = {"kernel": "gsk_cell_tc_kernel" if prec != ops.PREC_F32 else "gsk_cell_f32_kernel", "bound": "tensor",
+        x3 = cprec == getattr(ops, "PREC_BF16X3", -1)
+        roof = {"kernel": ("gsk_cell_tc_kernel<x3>" if x3 else "gsk_cell_tc_kernel") if prec != ops.PREC_F32 else "gsk_cell_f32_kernel", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{pk['src']} (sustained bf16 cuBLAS)", "ms_per_launch": cell_ms,
-                "algorithmic_flops_per_launch": flops, "launches_per_step": nsteps}
+                "algorithmic_flops_per_launch": flops, "launches_per_step": nsteps,
+                **({"note": "split bf16: three tensor-core MMAs per algorithmic product; the per-step kernel moves the fp32 state "
+                            "through HBM (3.6 KB per agent-step) and is bound by its epilogue, not by the tensor pipe"} if x3 else {})}
     # decode + ADE/FDE epilogue kernel alone (Philox mode): 500 algorithmic bytes per agent
     o_dec = fc.out
     lo = pos[:, :, T_OBS - 1].contiguous()

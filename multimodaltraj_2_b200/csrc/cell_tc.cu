@@ -33,7 +33,9 @@ constexpr int TC_N = 3 * TC_UN;                               // 96 accumulator 
 constexpr int TC_KC = 64;                                     // k-chunk (one 128-byte swizzle row)
 constexpr int TC_NKC = TC_K / TC_KC;                          // 5
 constexpr int TC_STAGE_BYTES = TC_N * TC_KC * 2;              // 12288
-constexpr int TC_NSTAGE = 2;
+constexpr int TC_NSTAGE = 2;                                  // weight stages of the bf16 kernel (two CTAs per SM)
+constexpr int TC_NSTAGE_X3 = 4;                               // split-bf16 kernel (one CTA per SM): stages 2, 3 live behind A_lo
+constexpr int TC_NSTAGE_MAX = 4;                              // barrier slots
 constexpr int TC_A_BLOCK = TC_M * TC_KC * 2;                  // 16384 bytes per k-chunk block
 constexpr int TC_A_BYTES = TC_NKC * TC_A_BLOCK;               // 81920
 constexpr int TC_WORKERS = 256;
@@ -59,9 +61,24 @@ constexpr uint32_t kIdesc = make_idesc_bf16(TC_M, TC_N);
 // term is 2^-16 of a product that is itself rounded to 2^-24): the gate GEMM at fp32-grade accuracy on the bf16 tensor
 // pipe, at three MMAs per k-step.  To the kernel it is the same GEMM with K' = 3 K: the k-chunks of a pass run
 // [A_hi | A_lo | A_hi] against the packed stream [W_hi ; W_hi ; W_lo].  The epilogue then uses tanhf / expf.
-constexpr int TC_X3_NKC = 3 * TC_NKC;                         // 15 weight chunks per pass
+// Chunk order of a pass: W_hi[kc] (kc = 0..4), each used for TWO groups of MMAs (x A_hi[kc], then x A_lo[kc]) while it
+// sits in its stage, then W_lo[kc] (x A_hi[kc]): 10 streamed chunks per pass instead of 15.
+constexpr int TC_X3_NKC = 2 * TC_NKC;                         // 10 weight chunks per pass
 constexpr int SM_ALO = ((SM_TOTAL + 1023) / 1024) * 1024;     // A_lo blocks (x3 only), after the common map
-constexpr int SM_TOTAL_X3 = SM_ALO + TC_A_BYTES;
+constexpr int SM_W23 = SM_ALO + TC_A_BYTES;                   // weight stages 2 and 3 (x3 only)
+constexpr int SM_TOTAL_X3 = SM_W23 + 2 * TC_STAGE_BYTES;
+__device__ __forceinline__ uint32_t tc_stage_off(uint32_t s) {   // byte offset of weight stage s
+  return s < 2 ? (uint32_t)(SM_W + s * TC_STAGE_BYTES) : (uint32_t)(SM_W23 + (s - 2) * TC_STAGE_BYTES);
+}
+// tanh for the split-bf16 mode: 1 - 2 / (exp(2x) + 1) with ex2.approx / rcp.approx (two MUFU + three FMA-pipe
+// instructions; absolute error < 4e-7 -- the 1e-4 tolerance of the mode is relative to O(1) states) instead of the
+// ~25-instruction tanhf; saturates correctly for |x| large (exp -> inf -> 1, exp -> 0 -> -1).
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float e = ex2_fast(x * 2.885390081777927f);           // exp(2x)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
 static_assert(SM_TOTAL_X3 + 1024 <= 227 * 1024, "x3 mode: one CTA per SM");
 __device__ __forceinline__ uint32_t pack_bf16x2_lo(float a, float b, uint32_t hi) {   // residuals of a pair
   return pack_bf16x2(a - bf16_lo(hi), b - bf16_hi(hi));
@@ -96,6 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
   constexpr bool BF = LAY != 0;
   static_assert(!X3 || LAY == 0, "split-bf16 mode takes the fp32 state layout");
   constexpr int NKC = X3 ? TC_X3_NKC : TC_NKC;
+  constexpr int NSTAGE = X3 ? TC_NSTAGE_X3 : TC_NSTAGE;
   // SWIZZLE_128B atoms need a 1024-byte aligned base: requested from the toolchain, so that the base is a link-time
   // constant and the barrier addresses / descriptors derived from it are uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -105,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR;
   // barrier indices
-  const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * TC_NSTAGE, ACC_FULL = bar0 + 8 * 2 * TC_NSTAGE,
+  const uint32_t W_FULL = bar0, W_EMPTY = bar0 + 8 * TC_NSTAGE_MAX, ACC_FULL = bar0 + 8 * 2 * TC_NSTAGE_MAX,
                  ACC_EMPTY = ACC_FULL + 16, A_READY = ACC_EMPTY + 16;
   float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
   float* s_we = reinterpret_cast<float*>(smem + SM_WE);
@@ -113,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
 
   if (tid == 0) {
-    for (int s = 0; s < TC_NSTAGE; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(W_FULL + 8 * s, 1);
       mbar_init(W_EMPTY + 8 * s, 1);
     }
@@ -148,10 +166,10 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         for (int p = 0; p < TC_NP; ++p)
           for (int kc = 0; kc < NKC; ++kc, ++it) {
-            const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
+            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
             mbar_wait(W_EMPTY + 8 * s, ph ^ 1u, a.trap, 0x201);
             mbar_arrive_expect_tx(W_FULL + 8 * s, TC_STAGE_BYTES);
-            bulk_g2s(sbase + SM_W + s * TC_STAGE_BYTES, a.Wp + (size_t)(p * NKC + kc) * TC_STAGE_BYTES,
+            bulk_g2s(sbase + tc_stage_off(s), a.Wp + (size_t)(p * NKC + kc) * TC_STAGE_BYTES,
                      TC_STAGE_BYTES, W_FULL + 8 * s);
           }
       }
@@ -169,17 +187,28 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + b * TC_ACC_STRIDE;
           for (int kc = 0; kc < NKC; ++kc, ++it) {
-            const uint32_t s = it % TC_NSTAGE, ph = (it / TC_NSTAGE) & 1u;
+            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
             mbar_wait(W_FULL + 8 * s, ph, a.trap, 0x204);   // written by the async proxy: no tcgen05 fence needed
-            // x3: chunks 0-4 A_hi (x W_hi), 5-9 A_lo (x W_hi), 10-14 A_hi (x W_lo)
-            const uint32_t a_off = !X3 ? (uint32_t)(SM_A + kc * TC_A_BLOCK)
-                                       : (kc >= TC_NKC && kc < 2 * TC_NKC) ? (uint32_t)(SM_ALO + (kc - TC_NKC) * TC_A_BLOCK)
-                                                                           : (uint32_t)(SM_A + (kc % TC_NKC) * TC_A_BLOCK);
-            const uint64_t da = make_desc_sw128(sbase + a_off);
-            const uint64_t db = make_desc_sw128(sbase + SM_W + s * TC_STAGE_BYTES);
+            const uint64_t db = make_desc_sw128(sbase + tc_stage_off(s));
+            if constexpr (X3) {
+              // chunks 0-4: W_hi[kc] against A_hi[kc] and A_lo[kc]; chunks 5-9: W_lo[kc] against A_hi[kc]
+              const int kk = kc % TC_NKC;
+              const uint64_t da_hi = make_desc_sw128(sbase + SM_A + kk * TC_A_BLOCK);
 #pragma unroll
-            for (int ks = 0; ks < TC_KC / 16; ++ks)  // advance 32 B (16 bf16) inside the swizzle row
-              umma_bf16(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdesc, (kc | ks) ? 1u : 0u);
+              for (int ks = 0; ks < TC_KC / 16; ++ks)
+                umma_bf16(d_tmem, da_hi + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdesc, (kc | ks) ? 1u : 0u);
+              if (kc < TC_NKC) {
+                const uint64_t da_lo = make_desc_sw128(sbase + SM_ALO + kk * TC_A_BLOCK);
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 16; ++ks)
+                  umma_bf16(d_tmem, da_lo + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdesc, 1u);
+              }
+            } else {
+              const uint64_t da = make_desc_sw128(sbase + SM_A + kc * TC_A_BLOCK);
+#pragma unroll
+              for (int ks = 0; ks < TC_KC / 16; ++ks)  // advance 32 B (16 bf16) inside the swizzle row
+                umma_bf16(d_tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), kIdesc, (kc | ks) ? 1u : 0u);
+            }
             umma_commit(W_EMPTY + 8 * s);  // stage reusable once these MMAs have read it
           }
           umma_commit(ACC_FULL + 8 * b);  // accumulator (and, on the last pass, the A operand) done
@@ -298,25 +327,37 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
           }
         }
       } else {
-        // fp32 state: one warp per row, lane -> 4 consecutive k, converted to bf16 on the way
-        for (int rr = warp; rr < TC_M; rr += 8) {
-          const int g2 = row0 + rr;
-          float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), mv = hv;
-          if (g2 < a.R) {
-            hv = *reinterpret_cast<const float4*>(a.h + (size_t)g2 * a.ld + lane * 4);
-            mv = *reinterpret_cast<const float4*>(a.mh + (size_t)g2 * a.ld + lane * 4);
+        // fp32 state: one warp per row, lane -> 4 consecutive k, converted to bf16 on the way.  Eight rows (16 independent
+        // 512-byte loads) are in flight per warp: one row at a time left the build phase latency-bound (with the
+        // split-bf16 kernel's one CTA per SM nothing else hides it: 24 k of its 77 k clk per tile)
+        constexpr int RB = X3 ? 8 : 4;   // rows in flight per warp (the two-CTA kernel has 96 registers per thread)
+#pragma unroll 1
+        for (int r8 = warp; r8 < TC_M; r8 += 8 * RB) {
+          float4 hv[RB], mv[RB];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int g2 = row0 + r8 + 8 * i;
+            hv[i] = mv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g2 < a.R) {
+              hv[i] = *reinterpret_cast<const float4*>(a.h + (size_t)g2 * a.ld + lane * 4);
+              mv[i] = *reinterpret_cast<const float4*>(a.mh + (size_t)g2 * a.ld + lane * 4);
+            }
           }
-          const int k = lane * 4;  // 0..124 within the 128-wide part
-          const int blk = k >> 6, kk = k & 63;
-          const uint2 hh = make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
-          const uint2 mm = make_uint2(pack_bf16x2(mv.x, mv.y), pack_bf16x2(mv.z, mv.w));
-          *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = hh;
-          *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = mm;
-          if constexpr (X3) {
-            *reinterpret_cast<uint2*>(smem + SM_ALO + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-                make_uint2(pack_bf16x2_lo(hv.x, hv.y, hh.x), pack_bf16x2_lo(hv.z, hv.w, hh.y));
-            *reinterpret_cast<uint2*>(smem + SM_ALO + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
-                make_uint2(pack_bf16x2_lo(mv.x, mv.y, mm.x), pack_bf16x2_lo(mv.z, mv.w, mm.y));
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int rr = r8 + 8 * i;
+            const int k = lane * 4;  // 0..124 within the 128-wide part
+            const int blk = k >> 6, kk = k & 63;
+            const uint2 hh = make_uint2(pack_bf16x2(hv[i].x, hv[i].y), pack_bf16x2(hv[i].z, hv[i].w));
+            const uint2 mm = make_uint2(pack_bf16x2(mv[i].x, mv[i].y), pack_bf16x2(mv[i].z, mv[i].w));
+            *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = hh;
+            *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = mm;
+            if constexpr (X3) {
+              *reinterpret_cast<uint2*>(smem + SM_ALO + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+                  make_uint2(pack_bf16x2_lo(hv[i].x, hv[i].y, hh.x), pack_bf16x2_lo(hv[i].z, hv[i].w, hh.y));
+              *reinterpret_cast<uint2*>(smem + SM_ALO + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) =
+                  make_uint2(pack_bf16x2_lo(mv[i].x, mv[i].y, mm.x), pack_bf16x2_lo(mv[i].z, mv[i].w, mm.y));
+            }
           }
         }
       }
@@ -352,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
         if (v) {
           const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
           auto tanh2 = [](float2 t) {   // x3: accurate tanhf; bf16: tanh.approx (error below the operand rounding)
-            if constexpr (X3) return make_float2(tanhf(t.x), tanhf(t.y));
+            if constexpr (X3) return make_float2(tanh_acc(t.x), tanh_acc(t.y));
             else return mmt::tanh2(t);
           };
 #pragma unroll
@@ -460,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
             for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + __ldg(a.b_h + z);
             o[2] = X3 ? expf(o[2]) : __expf(o[2]);
             o[3] = X3 ? expf(o[3]) : __expf(o[3]);
-            o[4] = X3 ? tanhf(o[4]) : tanh_fast(o[4]);
+            o[4] = X3 ? tanh_acc(o[4]) : tanh_fast(o[4]);
           }
           float* po = a.params_out + (size_t)gr * a.params_stride;
 #pragma unroll
@@ -494,7 +535,7 @@ __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* _
   *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(g == 1 ? W[idx] : 0.5f * W[idx]);
 }
 
-// split-bf16 image: [pass][15 chunks][96 rows][64 k]: chunks 0-4 and 5-9 hold W_hi (against A_hi, A_lo), 10-14 W_lo
+// split-bf16 image: [pass][10 chunks][96 rows][64 k]: chunks 0-4 hold W_hi (against A_hi and A_lo), 5-9 W_lo (against A_hi)
 __global__ void pack_gate_weights_x3_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TC_K * 3 * TC_U) return;
@@ -508,8 +549,7 @@ __global__ void pack_gate_weights_x3_kernel(const float* __restrict__ W, uint8_t
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
   const size_t base = (size_t)(p * TC_X3_NKC) * TC_STAGE_BYTES + sw128_off(n, kk);
   *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)kc * TC_STAGE_BYTES) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)(TC_NKC + kc) * TC_STAGE_BYTES) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)(2 * TC_NKC + kc) * TC_STAGE_BYTES) = lo;
+  *reinterpret_cast<__nv_bfloat16*>(out + base + (size_t)(TC_NKC + kc) * TC_STAGE_BYTES) = lo;
 }
 
 static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
