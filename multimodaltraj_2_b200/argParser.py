@@ -31,6 +31,8 @@ class ArgsParser():
     parser.add_argument('--K', type=int, default=20, help='samples per agent for best-of-K')
     parser.add_argument('--precision', type=str, default='bf16', choices=['fp32', 'bf16'])
     parser.add_argument('--world_size', type=int, default=1)
+    parser.add_argument('--variant', type=str, default='mcr', choices=['mc', 'mcr'],
+                        help='model of the batched path: g2k_lstm_mcr (the reference driver\'s, relational) or g2k_lstm_mc')
     parser.add_argument('--data_root', type=str, default=None, help='directory holding eth/ and ucy/')
     parser.add_argument('--save_dir', type=str, default=None,
                         help='directory for TensorFlow-bundle checkpoints (train.py:330-343); resumed from if it holds one')

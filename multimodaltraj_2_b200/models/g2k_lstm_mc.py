@@ -10,6 +10,7 @@ from .g2k_lstm_mcr import g2k_lstm_mcr
 
 class g2k_lstm_mc(g2k_lstm_mcr):
     variant = 1
+    relational = False         # no edge MLP: ``forecast_batched`` reaches the fused persistent rollout kernel in bf16 mode
 
     def __init__(self, in_features, out_size, obs_len, num_nodes, lambda_reg, pred_len=12, device="cuda"):
         # reference signature: (in_features, out_size, obs_len, num_nodes, lambda_reg); out_size is the

@@ -67,3 +67,24 @@ class g2k_lstm_mcr():
         (train.py:240-254).  X[S,T,n] V[S,2,n] C[S,D,D] Hs[S,D,H] -> dict(attn, cost, band, pred, Hs, adj, vemb)."""
         return ops.mcr_step(X, V, C, Hs, self._w(dict(W_i=weight_i, W_ii=weight_ii)), self.lambda_reg,
                             self.pred_len, self.variant, vemb_prev)
+
+    # ------------------------------------------------------------------------------------------
+    relational = True          # g2k_lstm_mcr: edge-MLP scores join the attention logits (nri_learned.py:5-28)
+
+    def forecast_batched(self, pos, vis, valid, params, K=20, r2=4.0, inv_2sigma2=0.5, prec=ops.PREC_BF16, seed=0,
+                         agent_offset=0, eps=None, use_graph=False):
+        """The north_star path behind the drop-in class: all scenes of a batch through pairwise kernel -> [edge MLP]
+        -> aggregation -> gate update for obs_len + pred_len - 1 frames, then K-sample decode + ADE/FDE + best-of-K
+        (``mmt_forecast_f32``).  pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N]; ``params``: ops.CellParams.
+        g2k_lstm_mc in bf16 mode with 128 % N == 0 runs the fused persistent rollout kernel; g2k_lstm_mcr the
+        relational per-step tensor-core kernels.  The forecaster (workspace, CUDA graphs) is cached per shape."""
+        S, N = valid.shape
+        T = pos.shape[2] - self.pred_len
+        key = (S, N, T, K, prec, seed, agent_offset, use_graph, id(params))
+        cache = self.__dict__.setdefault("_forecasters", {})
+        if key not in cache:
+            cache[key] = ops.Forecaster(params, S, N, T, self.pred_len, K, r2, inv_2sigma2, relational=self.relational,
+                                        prec=prec, seed=seed, agent_offset=agent_offset, device=pos.device,
+                                        use_graph=use_graph)
+        return cache[key](pos, vis, valid, eps=eps)
+

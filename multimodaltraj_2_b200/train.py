@@ -52,8 +52,10 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
             pos, vis, valid = pos[lo:hi].contiguous(), vis[lo:hi, :, :T].contiguous(), valid[lo:hi].contiguous()
             sums = torch.zeros(3, device=device)
             if hi > lo:
-                fc = ops.Forecaster(p, hi - lo, N, T, P, K, relational=True, prec=prec, seed=d,
-                                    agent_offset=lo * N, device=device)
+                # the reference's driver builds g2k_lstm_mcr (train.py:6,161); --variant mc selects g2k_lstm_mc, whose bf16
+                # mode is the fused persistent rollout kernel
+                fc = ops.Forecaster(p, hi - lo, N, T, P, K, relational=getattr(args, "variant", "mcr") != "mc", prec=prec,
+                                    seed=d, agent_offset=lo * N, device=device)
                 o = fc(pos, vis, valid)
                 sums = torch.stack([o["best_ade"].sum(), o["best_fde"].sum(), valid.sum().float()])
             if dist is not None:

@@ -33,6 +33,19 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def within(err, tol, label):
+    """assert err < tol; with MMT_RECORD_ERRORS=<file> the measured error is appended to that file (the bf16 tolerances
+    below are 2x the largest error measured on a B200 over the parametrisations: profiles/r02_bf16_measured_errors.json)"""
+    import json
+    import os
+    err = float(err)
+    f = os.environ.get("MMT_RECORD_ERRORS")
+    if f:
+        with open(f, "a") as fh:
+            fh.write(json.dumps({"label": label, "err": err, "tol": tol}) + "\n")
+    assert err < tol, (label, err, tol)
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("S,N,ragged", [(7, 64, False), (5, 16, True), (3, 256, True), (2, 4, False), (3, 12, True),
                                         (1, 160, False)])
@@ -127,7 +140,7 @@ def test_edge_mlp_bf16_tensor_core(cuda, S, N):
     osc = o_b.edge_mlp(h, adj, p)
     assert adj.sum() > 0
     assert np.array_equal(sc != 0, adj != 0)
-    assert np.abs(sc - osc).max() < 2e-2
+    within(np.abs(sc - osc).max(), 2e-2, "edge_mlp_bf16.score")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -172,7 +185,7 @@ def test_gsk_cell_bf16_tensor_core(cuda, R):
     torch.cuda.synchronize()
     oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
     for got, want in ((ho, oh), (co, oc), (mf, of)):
-        assert np.abs(npy(got) - want[0]).max() < 2e-2
+        within(np.abs(npy(got) - want[0]).max(), 2e-2, "cell_bf16.state_vs_fp32_oracle")
 
     def bf(a):
         return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
@@ -187,10 +200,10 @@ def test_gsk_cell_bf16_tensor_core(cuda, R):
     c_f = (1 - g) * mc + g * tj
     q = o_b.sigmoid(z[:, 2 * U:] + p["w_Of"] * c_f + p["w_Ot"] * c_t)
     m_t = q * np.tanh(c_t) * valid[:, None]
-    assert np.abs(npy(ho) - m_t).max() < 5e-3
-    assert np.abs(npy(co) - c_t * valid[:, None]).max() < 5e-3
+    within(np.abs(npy(ho) - m_t).max(), 5e-3, "cell_bf16.h_vs_bf16_operand_oracle")
+    within(np.abs(npy(co) - c_t * valid[:, None]).max(), 5e-3, "cell_bf16.c_vs_bf16_operand_oracle")
     oy = o_b.head(oh, of, p)[0] * valid[:, None]
-    assert np.abs(npy(par) - oy).max() < 2e-2
+    within(np.abs(npy(par) - oy).max(), 2e-2, "cell_bf16.head")
 
 
 def test_gridlstm_reference_instantiation(cuda):
@@ -366,8 +379,9 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
     torch.cuda.synchronize()
     want = o_b.forecast(pos, vis, valid, p, eps, T, P)
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
-    assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
-    assert np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max() < 5e-2
+    within(np.abs(got_mean - want["pred_mean"]).max(), 5e-2, "forecast_bf16.pred_mean")
+    within(np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max(),
+           5e-2, "forecast_bf16.best_ade")
 
 
 @pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
@@ -384,7 +398,7 @@ def test_forecast_bf16_relational(cuda, S, N):
     torch.cuda.synchronize()
     want = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=True)
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
-    assert np.abs(got_mean - want["pred_mean"]).max() < 5e-2
+    within(np.abs(got_mean - want["pred_mean"]).max(), 5e-2, "forecast_bf16_relational.pred_mean")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -407,12 +421,12 @@ def test_rollout_bf16_matches_oracle_and_stepwise(cuda, S, N):
         eps = np.zeros((S, N, 1, P, 2), np.float32)
         want = o_b.forecast(pos, vis, valid, p, eps, T, P)
         m = valid.astype(bool)
-        assert np.abs(got_mean - want["pred_mean"])[m].max() < 5e-2
-        assert np.abs(par[..., 2:] - want["params"][..., 2:])[m].max() < 5e-2
+        within(np.abs(got_mean - want["pred_mean"])[m].max(), 5e-2, "rollout_bf16.pred_mean")
+        within(np.abs(par[..., 2:] - want["params"][..., 2:])[m].max(), 5e-2, "rollout_bf16.sigma_rho")
     fs = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)
     step = npy(fs(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"])
     step_mean = np.cumsum(step[..., :2], 2) + pos[:, :, T - 1:T]
-    assert np.abs(got_mean - step_mean).max() < 2.5e-2
+    within(np.abs(got_mean - step_mean).max(), 2.5e-2, "rollout_bf16.fused_vs_stepwise")
     # the forecaster's default bf16 mode runs the fused kernel: identical parameters
     ff = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16, device=cuda)
     assert np.array_equal(npy(ff(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"]), par)
@@ -442,7 +456,7 @@ def test_rollout_bf16_empty_batch_and_other_horizons(cuda):
     p = synth.init_params(seed=2)
     par = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), ops.CellParams.from_numpy(p, cuda), T, P))
     want = o_b.forecast(pos, vis, valid, p, np.zeros((S, N, 1, P, 2), np.float32), T, P)
-    assert np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max() < 5e-2
+    within(np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max(), 5e-2, "rollout_bf16.scene_local.pred_mean")
 
 
 def test_rollout_full_size_properties(cuda):
@@ -461,7 +475,7 @@ def test_rollout_full_size_properties(cuda):
     assert torch.equal(torch.cat([lo, hi]), ref)
     assert bool(torch.isfinite(ref).all()) and bool((ref[d[2] == 0] == 0).all())
     step = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)(*d)["params"]
-    assert float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()) < 2.5e-2
+    within(float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()), 2.5e-2, "rollout_bf16.full_size.fused_vs_stepwise")
 
 
 @pytest.mark.parametrize("prec,relational", [("bf16", False), ("bf16-stepwise", False), ("bf16", True), ("f32", False),

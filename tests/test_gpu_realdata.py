@@ -140,3 +140,30 @@ def test_sample_main_mirror(cuda, tmp_path, capsys):
     import pickle
     res = pickle.load(open(tmp_path / "results.pkl", "rb"))
     assert len(res) == out["scenes_scored"] and res[0][1].shape[1] == 20
+
+
+def test_drop_in_model_classes_reach_the_batched_path(cuda):
+    """models.g2k_lstm_mc / g2k_lstm_mcr.forecast_batched == ops.Forecaster (mc in bf16 mode: the fused rollout kernel)."""
+    from multimodaltraj_2_b200.models import g2k_lstm_mc as mc
+    from multimodaltraj_2_b200.models import g2k_lstm_mcr as mcr
+    S, N = 6, 64
+    pos, vis, valid = (torch.as_tensor(a).to(cuda) for a in synth.make_crowd(S, N, seed=4, half_extent=4.0, ragged=True))
+    p = ops.CellParams.from_numpy(synth.init_params(seed=0), cuda)
+    m = mc.g2k_lstm_mc(in_features=torch.zeros((16, 16)), out_size=128, obs_len=8, num_nodes=N, lambda_reg=0.0005)
+    got = m.forecast_batched(pos, vis, valid, p, seed=3)
+    want = ops.rollout_bf16(pos, vis, valid, p)
+    assert torch.equal(got["params"], want)                              # the fused kernel, bit for bit
+    r = mcr.g2k_lstm_mcr(in_features=torch.zeros((16, 16)), hidden_size=128, obs_len=8, num_nodes=N, lambda_reg=0.0005)
+    got_r = r.forecast_batched(pos, vis, valid, p, seed=3)
+    ref = ops.Forecaster(p, S, N, 8, 12, 20, relational=True, prec=ops.PREC_BF16, seed=3, device=cuda)(pos, vis, valid)
+    assert torch.equal(got_r["best_k"], ref["best_k"]) and not torch.equal(got_r["params"], got["params"])
+
+
+def test_train_driver_on_the_shipped_tables(cuda):
+    """train.train (train.py:23-366 outer loop) over the real UCY tables under data/: leave-one-out, both variants."""
+    a = _args(leaveDataset=2, max_agents=64, precision="bf16", save_dir=None)
+    res = train.train(a, datasets=(2, 3), rank=0, world=1, device=cuda)
+    assert set(res) == {3} and res[3]["n_agents"] > 1000 and np.isfinite(res[3]["ade"])
+    a.variant = "mc"
+    res_mc = train.train(a, datasets=(2, 3), rank=0, world=1, device=cuda)
+    assert res_mc[3]["n_agents"] == res[3]["n_agents"] and res_mc[3]["ade"] != res[3]["ade"]
