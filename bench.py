@@ -684,6 +684,78 @@ def run_config(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_c2(args, rank, world, local_rank):
+    """--config c2 (BASELINE configs[1]): g2k_lstm_mcr training steps, UCY zara1 leave-one-out.  The reference's loop
+    (train.py:28-41) trains on datasets {2,3,4,5} minus the left-out one; 5 (town_center.csv) is absent upstream, so zara02
+    and ucy/univ train and zara01 is the held-out split.  Every step is one data-parallel step of the Trainer on ALL obs+pred
+    windows of one training table's first 70 % of the columns (load_traj.py:125-134), scenes sharded over the ranks, ONE
+    gradient all-reduce; the held-out best-of-20 ADE / FDE is evaluated before and after (the only accuracy datum this repo can
+    produce: the reference ships no trained model)."""
+    import types
+
+    import torch
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from multimodaltraj_2_b200 import ops, realdata, synth
+    from multimodaltraj_2_b200.train import Trainer
+    a = types.SimpleNamespace(batch_size=16, seq_length=12, pred_len=P_PRED, obs_len=T_OBS, K=K_SAMPLES, data_root=None)
+    relational = args.variant != "mc"            # configs[1] names g2k_lstm_mcr: the default of this config
+    params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
+    leave, train_sets = 2, [3, 4]
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational)
+    shards = {}
+    for d in train_sets:
+        sc = realdata.scene_windows(a, d, "train", dev)
+        lo, hi = realdata.shard_range(sc["pos"].shape[0], rank, world)
+        shards[d] = tuple(sc[k][lo:hi].contiguous() for k in ("pos", "vis", "valid")) + (int(sc["valid"].sum()), sc["N"], sc["pos"].shape[0])
+    held = realdata.scene_windows(a, leave, "all", dev)
+
+    def evaluate():
+        r = realdata.evaluate_split(a, leave, params, part="all", prec=ops.PREC_BF16, relational=relational, rank=rank,
+                                    world=world, device=dev, scenes=held, seed=11)
+        return realdata.public(r)
+    before = evaluate()
+    losses, ms = [], {d: [] for d in train_sets}
+    steps = max(1, args.steps)
+    for it in range(args.warmup + steps):
+        for d in train_sets:
+            pos, vis, valid, n_valid, N, S = shards[d]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = tr.step(pos, vis, valid)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= args.warmup:
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms[d].append(float(t.item()))
+            losses.append(float(loss))
+    after = evaluate()
+    if rank == 0:
+        per = {realdata.DATASET_NAMES[d]: {"scenes": shards[d][5], "agents_per_scene": shards[d][4], "valid_agents": shards[d][3],
+                                           "ms_per_step": float(np.mean(ms[d])),
+                                           "agent_trajectories_per_s": shards[d][3] / (float(np.mean(ms[d])) * 1e-3)} for d in train_sets}
+        tot_agents = sum(shards[d][3] for d in train_sets)
+        tot_ms = sum(float(np.mean(ms[d])) for d in train_sets)
+        emit({"mode": "train", "metric": "agent-trajectories/sec (training step: teacher-forced NLL + BPTT + gradient all-reduce + RMSProp)",
+              "value": tot_agents / (tot_ms * 1e-3), "unit": "agent-trajectories/s", "n_gpus": world, "steps": steps,
+              "warmup": args.warmup, "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f32 state; contractions " + args.train_gemm, "data": "ETH/UCY tables under data/ (real)",
+              "config": {"workload": "C2: g2k_lstm_%s training step, UCY zara1 leave-one-out (train: zara02 + ucy/univ, all obs+pred windows "
+                                     "of the training columns per step; held out: zara01)" % ("mcr" if relational else "mc"),
+                         "contractions": args.train_gemm, "lr": 1e-3, "collective": "one all-reduce (SUM) of the gradient bucket per step" if world > 1 else "none (1 GPU)"},
+              "per_table": per, "loss_first": losses[0], "loss_last": losses[-1],
+              "held_out_zara01_best_of_20": {"before": before, "after": after,
+                                             "note": "normalised (z-scored) units; random init -> after %d steps per table" % (args.warmup + steps)}})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_train(args, rank, world, local_rank):
     """--mode train: data-parallel training steps (teacher-forced NLL, BPTT through the fp32 kernels, ONE NCCL
     all-reduce of the flat gradient bucket, RMSProp) on this rank's scene shard.  Extra mode: the headline metric of
@@ -755,18 +827,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--prec", default="bf16", choices=["bf16", "f32", "bf16-stepwise", "bf16x3"])
-    ap.add_argument("--variant", default="mc", choices=["mc", "mcr"])
+    ap.add_argument("--variant", default=None, choices=["mc", "mcr"], help="default: mc (mcr for --config c2)")
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly (no CUDA graph)")
     ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the short runs of the other precision modes")
     ap.add_argument("--parity-scenes", type=int, default=256, help="scenes of the batch compared with the CPU oracle")
-    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c5"],
-                    help="c3 (default): synthetic crowds, the headline; c1 / c5: the real-data configs on data/ (extra)")
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c5"],
+                    help="c3 (default): synthetic crowds, the headline; c1 / c5: real-data evaluation on data/; c2: g2k_lstm_mcr "
+                         "training steps on the real zara1 leave-one-out tables (extras)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
     ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32", "tc"],
                     help="--mode train: contractions of the step: fp32 / tf32 library GEMMs, tc = mmt_gemm_tf32 (TMA + tcgen05) and mmt_aggregate_transpose_f32")
     args = ap.parse_args()
+    if args.variant is None:
+        args.variant = "mcr" if args.config == "c2" else "mc"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -778,6 +853,8 @@ def main():
             run_reference(args, rank, world)
         elif args.config in ("c1", "c5"):
             run_config(args, rank, world, local_rank)
+        elif args.config == "c2":
+            run_c2(args, rank, world, local_rank)
         elif args.mode == "train":
             run_train(args, rank, world, local_rank)
         else:
