@@ -92,10 +92,11 @@ def test_pairwise_full_size_properties(cuda):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("S,N,C", [(5, 64, 256), (3, 16, 128), (2, 256, 256), (4, 12, 32)])
+@pytest.mark.parametrize("S,N,C", [(5, 64, 256), (3, 16, 128), (2, 256, 256), (4, 12, 32), (1, 1024, 64), (2, 800, 32)])
 def test_aggregate(cuda, S, N, C):
+    """N = 800, 1024: more than 48 KB of dynamic shared memory (the kernel opts in per device: ADVICE r01)."""
     rng = np.random.default_rng(5)
-    pos, _, valid = synth.make_crowd(S, N, seed=21, half_extent=4.0 if N < 100 else 8.0, ragged=True)
+    pos, _, valid = synth.make_crowd(S, N, seed=21, half_extent=4.0 if N < 100 else (8.0 if N < 500 else 24.0), ragged=True)
     kern, adj, _ = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
     feat = rng.standard_normal((S, N, C)).astype(np.float32)
     a, out = ops.aggregate(dev(kern, cuda), dev(adj, cuda), dev(feat, cuda))
