@@ -24,7 +24,8 @@
 namespace mmt {
 
 constexpr int GB_M = 128, GB_N = 128, GB_K = 32;         // CTA tile; one k-block = 32 fp32 = 128 B
-constexpr int GB_STAGES = 4;
+constexpr int GB_STAGES = 3;                             // 96 KB of stages: TWO CTAs per SM, so that one CTA's prologue / epilogue
+                                                         // (latency-bound: these GEMMs have 10-12 k-blocks per tile) hides behind the other's main loop
 constexpr int GB_TILE_BYTES = GB_M * GB_K * 4;           // 16 KB per operand per stage
 constexpr int GB_SM_A = 0;
 constexpr int GB_SM_B = GB_SM_A + GB_STAGES * GB_TILE_BYTES;
@@ -65,16 +66,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, float v[16]) {
-  uint32_t r[16];
+// 32 consecutive accumulator columns of this thread's row: 128 bytes = one full line of C per thread and store
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float v[32]) {
+  uint32_t r[32];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(addr)
       : "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 struct GemmArgs {
@@ -87,7 +92,7 @@ struct GemmArgs {
   uint32_t* trap;
 };
 
-__global__ void __launch_bounds__(GB_THREADS, 1)
+__global__ void __launch_bounds__(GB_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* const smem = smem_dyn;
@@ -173,24 +178,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < GB_N; c0 += 16) {
-      float v[16];
+    for (int c0 = 0; c0 < GB_N; c0 += 32) {
+      if (n0 + c0 >= a.N) break;                  // columns beyond N (ragged last tile): nothing to store
+      float v[32];
       if (nkb > 0) {
-        tmem_ld16(t_row + c0, v);
+        tmem_ld32(t_row + c0, v);
         tmem_wait_ld();
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       if (row < a.M) {
         float* cp = a.C + (size_t)row * a.ldc + n0 + c0;
+        const bool full = n0 + c0 + 32 <= a.N && ((reinterpret_cast<uintptr_t>(cp) & 15u) == 0);
+        if (full && a.mode == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (n0 + c0 + j < a.N) {
-            const float x = a.alpha * v[j];
-            if (a.mode == 0) cp[j] = x;
-            else if (a.mode == 1) cp[j] += x;
-            else atomicAdd(cp + j, x);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(cp + j) = make_float4(a.alpha * v[j], a.alpha * v[j + 1], a.alpha * v[j + 2], a.alpha * v[j + 3]);
+        } else if (full && a.mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = *reinterpret_cast<const float4*>(cp + j);
+            o.x = fmaf(a.alpha, v[j], o.x); o.y = fmaf(a.alpha, v[j + 1], o.y);
+            o.z = fmaf(a.alpha, v[j + 2], o.z); o.w = fmaf(a.alpha, v[j + 3], o.w);
+            *reinterpret_cast<float4*>(cp + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + c0 + j < a.N) {
+              const float x = a.alpha * v[j];
+              if (a.mode == 0) cp[j] = x;
+              else if (a.mode == 1) cp[j] += x;
+              else atomicAdd(cp + j, x);
+            }
           }
         }
       }
