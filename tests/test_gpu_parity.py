@@ -125,7 +125,7 @@ def test_edge_mlp(cuda):
 @pytest.mark.parametrize("S,N", [(4, 32), (9, 64), (2, 256), (3, 12), (700, 16), (640, 32)])
 def test_edge_mlp_bf16_tensor_core(cuda, S, N):
     """tcgen05 edge MLP (bf16 operands, fp32 accumulation, ex2-based elu): tolerance stated separately from fp32.
-    Edges exactly where the mask has them (bit-exact zero pattern), scores within 2e-2 of the fp32 oracle.
+    Edges exactly where the mask has them (bit-exact zero pattern), scores within 3.5e-3 of the fp32 oracle (2x measured).
     S = 700, 640: more scenes than CTAs, so partial edge tiles are carried from scene to scene (ragged crowds: across
     scenes without any edge too)."""
     U = 128
@@ -141,7 +141,7 @@ def test_edge_mlp_bf16_tensor_core(cuda, S, N):
     osc = o_b.edge_mlp(h, adj, p)
     assert adj.sum() > 0
     assert np.array_equal(sc != 0, adj != 0)
-    within(np.abs(sc - osc).max(), 2e-2, "edge_mlp_bf16.score")
+    within(np.abs(sc - osc).max(), 3.5e-3, "edge_mlp_bf16.score")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,8 +176,8 @@ def test_gsk_cell_fp32(cuda, R, prec):
 @pytest.mark.parametrize("R", [128, 200, 1000, 128 * 300 + 17])
 def test_gsk_cell_bf16_tensor_core(cuda, R):
     """tcgen05 path: bf16 operands, fp32 accumulate, approx tanh -- tolerance stated separately
-    (north_star): |err| <= 2e-2 absolute on O(1) states, and it must agree with an oracle that
-    rounds the GEMM operands to bf16 to 5e-3."""
+    (north_star): |err| <= 9e-3 absolute on O(1) states (2x the measured 4.3e-3), and it must agree with an oracle that
+    rounds the GEMM operands to bf16 to 4e-4 / 6e-4 (measured 1.7e-4 / 3.0e-4)."""
     p = synth.init_params(seed=1)
     x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R + 1)
     P = ops.CellParams.from_numpy(p, cuda)
@@ -186,7 +186,7 @@ def test_gsk_cell_bf16_tensor_core(cuda, R):
     torch.cuda.synchronize()
     oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
     for got, want in ((ho, oh), (co, oc), (mf, of)):
-        within(np.abs(npy(got) - want[0]).max(), 2e-2, "cell_bf16.state_vs_fp32_oracle")
+        within(np.abs(npy(got) - want[0]).max(), 9e-3, "cell_bf16.state_vs_fp32_oracle")
 
     def bf(a):
         return torch.as_tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
@@ -201,10 +201,10 @@ def test_gsk_cell_bf16_tensor_core(cuda, R):
     c_f = (1 - g) * mc + g * tj
     q = o_b.sigmoid(z[:, 2 * U:] + p["w_Of"] * c_f + p["w_Ot"] * c_t)
     m_t = q * np.tanh(c_t) * valid[:, None]
-    within(np.abs(npy(ho) - m_t).max(), 5e-3, "cell_bf16.h_vs_bf16_operand_oracle")
-    within(np.abs(npy(co) - c_t * valid[:, None]).max(), 5e-3, "cell_bf16.c_vs_bf16_operand_oracle")
+    within(np.abs(npy(ho) - m_t).max(), 4e-4, "cell_bf16.h_vs_bf16_operand_oracle")
+    within(np.abs(npy(co) - c_t * valid[:, None]).max(), 6e-4, "cell_bf16.c_vs_bf16_operand_oracle")
     oy = o_b.head(oh, of, p)[0] * valid[:, None]
-    within(np.abs(npy(par) - oy).max(), 2e-2, "cell_bf16.head")
+    within(np.abs(npy(par) - oy).max(), 3e-4, "cell_bf16.head")
 
 
 def test_gridlstm_reference_instantiation(cuda):
@@ -380,9 +380,9 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
     torch.cuda.synchronize()
     want = o_b.forecast(pos, vis, valid, p, eps, T, P)
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
-    within(np.abs(got_mean - want["pred_mean"]).max(), 5e-2, "forecast_bf16.pred_mean")
+    within(np.abs(got_mean - want["pred_mean"]).max(), 1.3e-3, "forecast_bf16.pred_mean")
     within(np.abs(npy(o["best_ade"]) - np.take_along_axis(want["ade"], np.maximum(want["best_k"], 0)[..., None], -1)[..., 0]).max(),
-           5e-2, "forecast_bf16.best_ade")
+           7e-4, "forecast_bf16.best_ade")
 
 
 @pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
@@ -399,7 +399,7 @@ def test_forecast_bf16_relational(cuda, S, N):
     torch.cuda.synchronize()
     want = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=True)
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
-    within(np.abs(got_mean - want["pred_mean"]).max(), 5e-2, "forecast_bf16_relational.pred_mean")
+    within(np.abs(got_mean - want["pred_mean"]).max(), 1.4e-3, "forecast_bf16_relational.pred_mean")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -407,7 +407,7 @@ def test_forecast_bf16_relational(cuda, S, N):
 @pytest.mark.parametrize("S,N", [(8, 64), (21, 16), (2, 128), (40, 8), (9, 32), (300, 64)])
 def test_rollout_bf16_matches_oracle_and_stepwise(cuda, S, N):
     """bf16/tcgen05 mode, tolerance stated separately from fp32: the fused kernel's predicted mean trajectory is
-    within 5e-2 of the fp32 oracle and within 2.5e-2 of the per-step bf16 kernels (which keep c in fp32 HBM and
+    within 1.1e-3 of the fp32 oracle and within 4e-4 of the per-step bf16 kernels (2x the measured 5.3e-4 / 1.6e-4) (which keep c in fp32 HBM and
     round mc to bf16; the fused kernel keeps c in fp32 on chip and mc in fp32).  S*N % 128 != 0 exercises the
     tail tile; ragged validity masks exercise empty rows; S = 300 makes a CTA walk several tiles."""
     T, P = 8, 12
@@ -422,12 +422,12 @@ def test_rollout_bf16_matches_oracle_and_stepwise(cuda, S, N):
         eps = np.zeros((S, N, 1, P, 2), np.float32)
         want = o_b.forecast(pos, vis, valid, p, eps, T, P)
         m = valid.astype(bool)
-        within(np.abs(got_mean - want["pred_mean"])[m].max(), 5e-2, "rollout_bf16.pred_mean")
-        within(np.abs(par[..., 2:] - want["params"][..., 2:])[m].max(), 5e-2, "rollout_bf16.sigma_rho")
+        within(np.abs(got_mean - want["pred_mean"])[m].max(), 1.1e-3, "rollout_bf16.pred_mean")
+        within(np.abs(par[..., 2:] - want["params"][..., 2:])[m].max(), 1.6e-4, "rollout_bf16.sigma_rho")
     fs = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)
     step = npy(fs(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"])
     step_mean = np.cumsum(step[..., :2], 2) + pos[:, :, T - 1:T]
-    within(np.abs(got_mean - step_mean).max(), 2.5e-2, "rollout_bf16.fused_vs_stepwise")
+    within(np.abs(got_mean - step_mean).max(), 4e-4, "rollout_bf16.fused_vs_stepwise")
     # the forecaster's default bf16 mode runs the fused kernel: identical parameters
     ff = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16, device=cuda)
     assert np.array_equal(npy(ff(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))["params"]), par)
@@ -457,7 +457,7 @@ def test_rollout_bf16_empty_batch_and_other_horizons(cuda):
     p = synth.init_params(seed=2)
     par = npy(ops.rollout_bf16(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), ops.CellParams.from_numpy(p, cuda), T, P))
     want = o_b.forecast(pos, vis, valid, p, np.zeros((S, N, 1, P, 2), np.float32), T, P)
-    within(np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max(), 5e-2, "rollout_bf16.scene_local.pred_mean")
+    within(np.abs(np.cumsum(par[..., :2], 2) + pos[:, :, T - 1:T] - want["pred_mean"]).max(), 3.5e-4, "rollout_bf16.scene_local.pred_mean")
 
 
 def test_rollout_full_size_properties(cuda):
@@ -476,7 +476,7 @@ def test_rollout_full_size_properties(cuda):
     assert torch.equal(torch.cat([lo, hi]), ref)
     assert bool(torch.isfinite(ref).all()) and bool((ref[d[2] == 0] == 0).all())
     step = ops.Forecaster(cp, S, N, T, P, 1, prec=ops.PREC_BF16_STEPWISE, device=cuda)(*d)["params"]
-    within(float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()), 2.5e-2, "rollout_bf16.full_size.fused_vs_stepwise")
+    within(float((ref[..., :2].cumsum(2) - step[..., :2].cumsum(2)).abs().max()), 4e-4, "rollout_bf16.full_size.fused_vs_stepwise")
 
 
 @pytest.mark.parametrize("prec,relational", [("bf16", False), ("bf16-stepwise", False), ("bf16", True), ("f32", False),

@@ -56,7 +56,7 @@ def test_scene_windows_match_oracle_batching(cuda, d):
     assert int(sc["valid"].sum(1).max()) <= sc["N"]
 
 
-@pytest.mark.parametrize("d,prec,tol", [(1, ops.PREC_F32, 1e-3), (2, ops.PREC_F32, 1e-3), (1, ops.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("d,prec,tol", [(1, ops.PREC_F32, 1e-3), (2, ops.PREC_F32, 1e-3), (1, ops.PREC_BF16, 1e-3)])
 def test_best_of_k_on_real_split_matches_oracle(cuda, d, prec, tol):
     """C1: forward + best-of-20 ADE/FDE on a real split against the oracle with the same fed noise (fp32 mode: the
     north_star's 1e-3; bf16 stated separately), in the table's units and -- ETH -- in metres."""
