@@ -666,6 +666,8 @@ def run_config(args, rank, world, local_rank):
                              "ours_ade": float(g_ade.mean()), "ours_fde": float(g_fde.mean()),
                              "max_abs_d_ade": float(np.abs(g_ade - w_ade).max()), "max_abs_d_fde": float(np.abs(g_fde - w_fde).max()),
                              "best_k_equal_frac": float((got["_out"]["best_k"].cpu().numpy()[v] == want["best_k"][v]).mean())}
+            same = got["_out"]["best_k"].cpu().numpy()[v] == want["best_k"][v]       # a flipped near-tie compares two different samples' FDE
+            row["oracle"]["max_abs_d_fde_same_best_k"] = float(np.abs(g_fde - w_fde)[same].max()) if same.any() else None
         rows[realdata.DATASET_NAMES[d]] = row
         total_agents += row["n_agents"]
         total_ms += row["ms_forecast"]
