@@ -34,12 +34,20 @@ constexpr int TC_KC = 64;                                     // k-chunk (one 12
 constexpr int TC_NKC = TC_K / TC_KC;                          // 5
 constexpr int TC_STAGE_BYTES = TC_N * TC_KC * 2;              // 12288
 constexpr int TC_NSTAGE = 2;                                  // weight stages of the bf16 kernel (two CTAs per SM)
-constexpr int TC_NSTAGE_X3 = 4;                               // split-bf16 kernel (one CTA per SM): stages 2, 3 live behind A_lo
+#ifndef TC_X3_STAGING
+#define TC_X3_STAGING 1   // 1: c / mc / h' / c' of the epilogue staged through 33 KB of shared memory (coalesced global access), which
+#endif                    //    leaves room for only two weight stages; 0: four weight stages, per-lane global access.
+// Measured on a B200 at C3 (scratch/timeline_x3.py): staging + 2 stages 0.407 ms per step (a pass = 7.0 k clk, paced by the weight
+// stream: 24 KB in flight; the epilogue alone needs 4.3-6 k), no staging + 4 stages 0.527 ms (per-lane 32-byte global pieces: epilogue
+// 10-12 k clk per pass).  Both at once do not fit in 227 KB next to the two 80 KB operand images.
+constexpr int TC_NSTAGE_X3 = TC_X3_STAGING ? 2 : 4;
 constexpr int TC_NSTAGE_MAX = 4;                              // barrier slots
 constexpr int TC_A_BLOCK = TC_M * TC_KC * 2;                  // 16384 bytes per k-chunk block
 constexpr int TC_A_BYTES = TC_NKC * TC_A_BLOCK;               // 81920
-constexpr int TC_WORKERS = 256;
+constexpr int TC_WORKERS = 256;                               // worker threads of the bf16 kernel (two CTAs per SM)
 constexpr int TC_THREADS = TC_WORKERS + 64;                   // + producer warp + MMA warp
+constexpr int TC_WORKERS_X3 = 512;                            // split-bf16 kernel: one CTA per SM, so 16 worker warps (the 8-warp
+constexpr int TC_THREADS_X3 = TC_WORKERS_X3 + 64;             // version was latency-bound: 2 warps per scheduler, 57 k clk per tile)
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_ACC_STRIDE = 128;                            // TMEM column stride between the two accumulators
 
@@ -65,8 +73,15 @@ constexpr uint32_t kIdesc = make_idesc_bf16(TC_M, TC_N);
 // sits in its stage, then W_lo[kc] (x A_hi[kc]): 10 streamed chunks per pass instead of 15.
 constexpr int TC_X3_NKC = 2 * TC_NKC;                         // 10 weight chunks per pass
 constexpr int SM_ALO = ((SM_TOTAL + 1023) / 1024) * 1024;     // A_lo blocks (x3 only), after the common map
-constexpr int SM_W23 = SM_ALO + TC_A_BYTES;                   // weight stages 2 and 3 (x3 only)
-constexpr int SM_TOTAL_X3 = SM_W23 + 2 * TC_STAGE_BYTES;
+constexpr int SM_W23 = SM_ALO + TC_A_BYTES;                   // (weight stages 2 and 3 when TC_NSTAGE_X3 == 4)
+// Epilogue staging of the split-bf16 kernel: c and mc of a pass (128 rows x 32 units, fp32) come in, c' and h' go out,
+// through shared memory, so that every global access of the epilogue is a coalesced 128-byte row piece instead of one
+// 32-byte piece per lane (row-major fp32 state: the per-lane pieces were 36 k of the kernel's 57 k clk per tile).
+// [8 unit quads][129 rows (128 + 1 pad: the transposing accesses fall on different banks)][4 units], two arrays.
+constexpr int TC_STG_Q = 129;
+constexpr int TC_STG_BYTES = 8 * TC_STG_Q * 16;               // 16512 per array
+constexpr int SM_STG = SM_W23 + (TC_NSTAGE_X3 > 2 ? 2 * TC_STAGE_BYTES : 0);
+constexpr int SM_TOTAL_X3 = SM_STG + (TC_X3_STAGING ? 2 * TC_STG_BYTES : 0);
 __device__ __forceinline__ uint32_t tc_stage_off(uint32_t s) {   // byte offset of weight stage s
   return s < 2 ? (uint32_t)(SM_W + s * TC_STAGE_BYTES) : (uint32_t)(SM_W23 + (s - 2) * TC_STAGE_BYTES);
 }
@@ -109,11 +124,18 @@ __host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  //
 }
 
 template <int LAY, bool X3 = false>
-__global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
   constexpr bool BF = LAY != 0;
   static_assert(!X3 || LAY == 0, "split-bf16 mode takes the fp32 state layout");
   constexpr int NKC = X3 ? TC_X3_NKC : TC_NKC;
   constexpr int NSTAGE = X3 ? TC_NSTAGE_X3 : TC_NSTAGE;
+  constexpr bool STG = X3 && TC_X3_STAGING;
+  constexpr int NWT = X3 ? TC_WORKERS_X3 : TC_WORKERS;   // worker threads
+  constexpr int NW = NWT / 32;                            // worker warps: 8 or 16; producer = warp NW, MMA issuer = warp NW + 1
+  constexpr int NTHR = NWT + 64;
+  constexpr int NH = NW / 4;                              // column slices of a pass (one per group of four warps)
+  constexpr int UPT = TC_UN / NH;                         // units per thread per pass: 16 or 8
+  constexpr int NSUB = UPT / 8;                           // 8-unit sub-chunks per pass: 2 or 1
   // SWIZZLE_128B atoms need a 1024-byte aligned base: requested from the toolchain, so that the base is a link-time
   // constant and the barrier addresses / descriptors derived from it are uniform
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -137,29 +159,29 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(ACC_FULL + 8 * b, 1);
-      mbar_init(ACC_EMPTY + 8 * b, TC_WORKERS);
+      mbar_init(ACC_EMPTY + 8 * b, NW);     // one arrival per worker WARP (per-thread arrivals serialise in the smem atomic unit)
     }
-    mbar_init(A_READY, TC_WORKERS);
+    mbar_init(A_READY, NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(sbase + SM_TMEM, TC_TMEM_COLS);
+  if (warp == NW) tmem_alloc(sbase + SM_TMEM, TC_TMEM_COLS);
   // sigmoid(z) = 0.5 tanh(z/2) + 0.5: the 1/2 is folded into everything that feeds the i and o gates
   // (their packed weight columns, biases and peephole diagonals), so a gate is one MUFU.TANH + one FMA
-  for (int i = tid; i < 384; i += TC_THREADS) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
-  for (int i = tid; i < 128; i += TC_THREADS) {
+  for (int i = tid; i < 384; i += NTHR) s_bias[i] = (i >= 128 && i < 256) ? a.b[i] : 0.5f * a.b[i];
+  for (int i = tid; i < 128; i += NTHR) {
     s_bias[384 + i] = 0.5f * a.w_If[i];
     s_bias[512 + i] = 0.5f * a.w_It[i];
     s_bias[640 + i] = 0.5f * a.w_Of[i];
     s_bias[768 + i] = 0.5f * a.w_Ot[i];
   }
-  for (int i = tid; i < 256; i += TC_THREADS) s_we[i] = a.W_e[i];
-  for (int i = tid; i < 64; i += TC_THREADS) s_we[256 + i] = a.b_e[i];
+  for (int i = tid; i < 256; i += NTHR) s_we[i] = a.W_e[i];
+  for (int i = tid; i < 64; i += NTHR) s_we[256 + i] = a.b_e[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 8) {
+  if (warp == NW) {
     // =============================== weight-stage producer ===============================
     if (lane == 0) {
       uint32_t it = 0;
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
           }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == NW + 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       uint32_t it = 0, pc = 0, tc = 0;
@@ -218,6 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
   } else {
     // =============================== workers: operand build + epilogue ===============================
     const int q = warp & 3, hsel = warp >> 2;
+    auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(NWT) : "memory"); };
     uint32_t pc = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int row0 = tile * TC_M;
@@ -225,13 +248,14 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
       if (dbg) dbg[0] = clock64();
       // ---- e = relu(x W_e + b_e) -> block 0.  thread -> (row tid/2, 32 k's)
       {
-        const int r = tid >> 1, k0 = (tid & 1) * 32;
+        constexpr int EPT = 64 * TC_M / NWT;   // k's of e per thread: 32 or 16
+        const int r = tid / (64 / EPT), k0 = (tid % (64 / EPT)) * EPT;
         const int gr = row0 + r;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool ok = gr < a.R;
         if (ok) xv = __ldg(reinterpret_cast<const float4*>(a.x) + gr);
 #pragma unroll
-        for (int kk = 0; kk < 32; kk += 8) {
+        for (int kk = 0; kk < EPT; kk += 8) {
           uint32_t pk[4];
           [[maybe_unused]] uint32_t pl[4];
 #pragma unroll
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
         o.m = make_uint4(0u, 0u, 0u, 0u);
         if constexpr (!BF) o.mf0 = o.mf1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (v) {
-          const int u = (idx >> 1) * TC_UN + hsel * 16 + (idx & 1) * 8;
+          const int u = (idx / NSUB) * TC_UN + hsel * UPT + (idx % NSUB) * 8;
           const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
           const float4* cp = reinterpret_cast<const float4*>(a.c + so);
           o.c0 = cp[0];
@@ -330,13 +354,13 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
         // fp32 state: one warp per row, lane -> 4 consecutive k, converted to bf16 on the way.  Eight rows (16 independent
         // 512-byte loads) are in flight per warp: one row at a time left the build phase latency-bound (with the
         // split-bf16 kernel's one CTA per SM nothing else hides it: 24 k of its 77 k clk per tile)
-        constexpr int RB = X3 ? 8 : 4;   // rows in flight per warp (the two-CTA kernel has 96 registers per thread)
+        constexpr int RB = 4;   // rows in flight per warp (96 / 112 registers per thread)
 #pragma unroll 1
-        for (int r8 = warp; r8 < TC_M; r8 += 8 * RB) {
+        for (int r8 = warp; r8 < TC_M; r8 += NW * RB) {
           float4 hv[RB], mv[RB];
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
-            const int g2 = row0 + r8 + 8 * i;
+            const int g2 = row0 + r8 + NW * i;
             hv[i] = mv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (g2 < a.R) {
               hv[i] = *reinterpret_cast<const float4*>(a.h + (size_t)g2 * a.ld + lane * 4);
@@ -345,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
           }
 #pragma unroll
           for (int i = 0; i < RB; ++i) {
-            const int rr = r8 + 8 * i;
+            const int rr = r8 + NW * i;
             const int k = lane * 4;  // 0..124 within the 128-wide part
             const int blk = k >> 6, kk = k & 63;
             const uint2 hh = make_uint2(pack_bf16x2(hv[i].x, hv[i].y), pack_bf16x2(hv[i].z, hv[i].w));
@@ -362,16 +386,55 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
         }
       }
       if (dbg) dbg[1] = clock64();
-      CM pre = load_cm(0), pre2 = load_cm(1);  // two sub-chunks in flight while the MMAs of pass 0 run
+      CM pre = {}, pre2 = {};
+      if constexpr (!STG) {
+        pre = load_cm(0);
+        pre2 = load_cm(1);   // two sub-chunks in flight while the MMAs of pass 0 run
+      }
+      // split-bf16 kernel: operands of the epilogue staged through shared memory, pass by pass (see TC_STG_Q)
+      constexpr int NSTG = TC_M * TC_UN / 4 / NWT;   // float4 per thread and array in the staging copies: 4 or 2
+      float4* const s_c4 = reinterpret_cast<float4*>(smem + SM_STG);
+      float4* const s_m4 = reinterpret_cast<float4*>(smem + SM_STG + TC_STG_BYTES);
+      [[maybe_unused]] auto stage_load = [&](int pass, float4 (&cin)[NSTG], float4 (&min)[NSTG]) {   // global -> registers (coalesced)
+#pragma unroll
+        for (int k = 0; k < NSTG; ++k) {
+          const int i = tid + NWT * k, row = i >> 3, chunk = i & 7;
+          const int g2 = row0 + row;
+          cin[k] = min[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g2 < a.R) {
+            cin[k] = *reinterpret_cast<const float4*>(a.c + (size_t)g2 * a.ld + pass * TC_UN + chunk * 4);
+            min[k] = *reinterpret_cast<const float4*>(a.mc + (size_t)g2 * a.ld + pass * TC_UN + chunk * 4);
+          }
+        }
+      };
+      [[maybe_unused]] auto stage_put = [&](const float4 (&cin)[NSTG], const float4 (&min)[NSTG]) {   // registers -> staging
+#pragma unroll
+        for (int k = 0; k < NSTG; ++k) {
+          const int i = tid + NWT * k, row = i >> 3, chunk = i & 7;
+          s_c4[chunk * TC_STG_Q + row] = cin[k];
+          s_m4[chunk * TC_STG_Q + row] = min[k];
+        }
+      };
+      if constexpr (STG) {
+        float4 cin[NSTG], min[NSTG];
+        stage_load(0, cin, min);
+        stage_put(cin, min);   // visible to the epilogue threads after the bar.sync that follows the fence below
+      }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      mbar_arrive(A_READY);
+      __syncwarp();         // every lane has fenced its own writes; lane 0's arrive releases them
+      if (lane == 0) mbar_arrive(A_READY);
+      if constexpr (STG) worker_bar();   // pass 0's c / mc staged
 
       // ---- epilogue: 8 sub-chunks (4 passes x 2 halves), operands prefetched one sub-chunk ahead
       float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      [[maybe_unused]] float4 nxt_c[NSTG], nxt_m[NSTG];   // split-bf16 kernel: next pass's c / mc, in flight during this pass's epilogue
 #pragma unroll 1
-      for (int idx = 0; idx < 2 * TC_NP; ++idx) {
-        const int p = idx >> 1, sub = idx & 1;
+      for (int idx = 0; idx < NSUB * TC_NP; ++idx) {
+        const int p = idx / NSUB, sub = idx % NSUB;
         const uint32_t b = pc & 1u, bph = (pc >> 1) & 1u;
+        if constexpr (STG) {
+          if (sub == 0 && p + 1 < TC_NP) stage_load(p + 1, nxt_c, nxt_m);
+        }
         if (sub == 0) {
           if (dbg) dbg[2 + 3 * p] = clock64();
           mbar_wait(ACC_FULL + 8 * b, bph, a.trap, 0x205);
@@ -379,20 +442,33 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
           tc_fence_after();
         }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + b * TC_ACC_STRIDE;
-        const int ul = hsel * 16 + sub * 8;  // unit within pass
+        const int ul = hsel * UPT + sub * 8;  // unit within pass
         const int u = p * TC_UN + ul;        // global unit
         float zi[8], zj[8], zo[8];
         tmem_ld8(t_row + ul, zi);
         tmem_ld8(t_row + TC_UN + ul, zj);
         tmem_ld8(t_row + 2 * TC_UN + ul, zo);
-        const CM cur = pre;
-        pre = pre2;
-        if (idx + 2 < 2 * TC_NP) pre2 = load_cm(idx + 2);
+        CM cur;
+        if constexpr (STG) {
+          const int qd = ul >> 2;   // unit quad within the pass
+          cur.c0 = s_c4[qd * TC_STG_Q + r];
+          cur.c1 = s_c4[(qd + 1) * TC_STG_Q + r];
+          cur.mf0 = s_m4[qd * TC_STG_Q + r];
+          cur.mf1 = s_m4[(qd + 1) * TC_STG_Q + r];
+          cur.m = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          cur = pre;
+          pre = pre2;
+          if (idx + 2 < NSUB * TC_NP) pre2 = load_cm(idx + 2);
+        }
         tmem_wait_ld();
         float ho[8], co[8], fo[8];
         if (v) {
           const float2 kHalf = make_float2(0.5f, 0.5f), kNeg = make_float2(-1.f, -1.f);
           auto tanh2 = [](float2 t) {   // x3: accurate tanhf; bf16: tanh.approx (error below the operand rounding)
+#ifdef TC_X3_EXP_FAST_TANH   // timing experiment only (scratch/timeline_x3.py): what the accurate tanh costs
+            if constexpr (X3) return mmt::tanh2(t);
+#endif
             if constexpr (X3) return make_float2(tanh_acc(t.x), tanh_acc(t.y));
             else return mmt::tanh2(t);
           };
@@ -441,7 +517,19 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
 #pragma unroll
           for (int i = 0; i < 8; ++i) ho[i] = co[i] = fo[i] = 0.f;
         }
-        if (rok || LAY == 2) {
+        if constexpr (STG) {
+          // c' and h' take the staging slots their inputs came from (this thread's own); stored coalesced after the pass
+          const int qd = ul >> 2;
+          s_c4[qd * TC_STG_Q + r] = make_float4(co[0], co[1], co[2], co[3]);
+          s_c4[(qd + 1) * TC_STG_Q + r] = make_float4(co[4], co[5], co[6], co[7]);
+          s_m4[qd * TC_STG_Q + r] = make_float4(ho[0], ho[1], ho[2], ho[3]);
+          s_m4[(qd + 1) * TC_STG_Q + r] = make_float4(ho[4], ho[5], ho[6], ho[7]);
+          if (a.mf_out && rok) {
+            float4* fp = reinterpret_cast<float4*>(a.mf_out + (size_t)gr * a.ld_mf + u);
+            fp[0] = make_float4(fo[0], fo[1], fo[2], fo[3]);
+            fp[1] = make_float4(fo[4], fo[5], fo[6], fo[7]);
+          }
+        } else if (rok || LAY == 2) {
           const size_t so = LAY == 2 ? blk_off(tile, r, u) : (size_t)gr * a.ld + u;
           float4* cp = reinterpret_cast<float4*>(a.c_out + so);
           cp[0] = make_float4(co[0], co[1], co[2], co[3]);
@@ -461,7 +549,11 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
             }
           }
         }
+#ifdef TC_X3_EXP_NO_HEAD      // timing experiment only
+        if (false) {
+#else
         if (a.params_out) {
+#endif
           // head partial sums: W_h rows u..u+7 are 40 contiguous floats (160 B, 16-byte aligned): 10 uniform
           // 128-bit loads per half instead of 40 scalar ones (the scalar version saturated L1TEX)
           float wv[40];
@@ -479,9 +571,32 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
               for (int z = 0; z < 5; ++z) y[z] = fmaf(hsrc ? fo[i] : ho[i], wv[i * 5 + z], y[z]);
           }
         }
-        if (sub == 1) {
+        if (sub == NSUB - 1) {
           tc_fence_before();
-          mbar_arrive(ACC_EMPTY + 8 * b);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ACC_EMPTY + 8 * b);
+          if constexpr (STG) {
+            worker_bar();           // every h', c' of the pass is in the staging slots
+            float4 cout[NSTG], hout[NSTG];
+#pragma unroll
+            for (int k = 0; k < NSTG; ++k) {
+              const int i = tid + NWT * k, row = i >> 3, chunk = i & 7;
+              cout[k] = s_c4[chunk * TC_STG_Q + row];
+              hout[k] = s_m4[chunk * TC_STG_Q + row];
+            }
+            worker_bar();           // all staging slots have been read (also guards the next tile)
+            if (p + 1 < TC_NP) stage_put(nxt_c, nxt_m);               // next pass's operands (loaded during this pass's epilogue)
+#pragma unroll
+            for (int k = 0; k < NSTG; ++k) {
+              const int i = tid + NWT * k, row = i >> 3, chunk = i & 7;
+              const int g2 = row0 + row;
+              if (g2 < a.R) {
+                *reinterpret_cast<float4*>(a.c_out + (size_t)g2 * a.ld + p * TC_UN + chunk * 4) = cout[k];
+                *reinterpret_cast<float4*>(a.h_out + (size_t)g2 * a.ld + p * TC_UN + chunk * 4) = hout[k];
+              }
+            }
+            if (p + 1 < TC_NP) worker_bar();         // staged for pass p + 1
+          }
           if (dbg) dbg[4 + 3 * p] = clock64();
           ++pc;
         }
@@ -489,16 +604,24 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
       if (dbg) dbg[14] = clock64();
       // ---- head: combine the two column halves of each row
       if (a.params_out) {
-        if (hsel == 1) {
+        // slices 1 .. NH-1 hand their partial sums to slice 0.  The split-bf16 kernel has three of them: they go through the
+        // A_lo operand region, free once the last pass has completed (every worker has seen its ACC_FULL) until the next build
+        float* const s_part = X3 ? reinterpret_cast<float*>(smem + SM_ALO) : s_head;
+        if (hsel >= 1) {
 #pragma unroll
-          for (int z = 0; z < 5; ++z) s_head[r * 5 + z] = y[z];
+          for (int z = 0; z < 5; ++z) s_part[((hsel - 1) * TC_M + r) * 5 + z] = y[z];
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        worker_bar();
         if (hsel == 0 && rok) {
           float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
           if (v) {
 #pragma unroll
-            for (int z = 0; z < 5; ++z) o[z] = y[z] + s_head[r * 5 + z] + __ldg(a.b_h + z);
+            for (int z = 0; z < 5; ++z) {
+              float acc = y[z];
+#pragma unroll
+              for (int hh = 0; hh < NH - 1; ++hh) acc += s_part[(hh * TC_M + r) * 5 + z];
+              o[z] = acc + __ldg(a.b_h + z);
+            }
             o[2] = X3 ? expf(o[2]) : __expf(o[2]);
             o[3] = X3 ? expf(o[3]) : __expf(o[3]);
             o[4] = X3 ? tanh_acc(o[4]) : tanh_fast(o[4]);
@@ -511,13 +634,13 @@ __global__ void __launch_bounds__(TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcA
             *reinterpret_cast<float2*>(a.next_pos + (size_t)gr * 2) = make_float2(cp.x + o[0], cp.y + o[1]);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        worker_bar();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  if (warp == NW) tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
 // W[E+2U, 3U] fp32 row-major -> bf16 operand image [pass][k-chunk][96 rows][64 k], SWIZZLE_128B.
@@ -565,7 +688,7 @@ static int tc_launch(TcArgs& a, cudaStream_t stream) {
   static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3>), kSmem, &smem_opted[0])) return rc;
   const int grid = a.num_tiles < kPerSM * num_sms() ? a.num_tiles : kPerSM * num_sms();
-  gsk_cell_tc_kernel<LAY, X3><<<grid, TC_THREADS, kSmem, stream>>>(a);
+  gsk_cell_tc_kernel<LAY, X3><<<grid, X3 ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);
   count_launch();
   return check_launch(X3 ? "gsk_cell_tc_kernel<x3>" : "gsk_cell_tc_kernel");
 }
@@ -650,4 +773,19 @@ extern "C" int mmt_debug_cell_tc_timeline(const float* x, const void* hb, const 
   a.c_out = c_out; a.cur_pos = cur_pos; a.params_out = params_out; a.next_pos = next_pos;
   a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = 5; a.dbg = dbg;
   return tc_launch<2>(a, (cudaStream_t)stream);
+}
+
+// diagnostics: the fp32-state kernel (bf16 or split-bf16 gate GEMM) once with per-tile phase timestamps
+extern "C" int mmt_debug_cell_tc_f32state_timeline(const float* x, const float* h, const float* c, const float* mh,
+                                                   const float* mc, const uint8_t* valid, const mmt_cell_weights* w, int R,
+                                                   float* h_out, float* c_out, const float* cur_pos, float* params_out,
+                                                   float* next_pos, int x3, long long* dbg, void* stream) {
+  using namespace mmt;
+  TcArgs a = {};
+  a.x = x; a.h = h; a.c = c; a.mh = mh; a.mc = mc; a.valid = valid;
+  tc_fill_weights(a, w);
+  if (x3) a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16x3);
+  a.h_out = h_out; a.c_out = c_out; a.mf_out = nullptr; a.cur_pos = cur_pos; a.params_out = params_out;
+  a.next_pos = next_pos; a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = 5; a.dbg = dbg;
+  return x3 ? tc_launch<0, true>(a, (cudaStream_t)stream) : tc_launch<0>(a, (cudaStream_t)stream);
 }
