@@ -280,7 +280,7 @@ def _decode_inputs(S, N, P, K, seed):
     return par.astype(np.float32), eps, last, gt, valid
 
 
-@pytest.mark.parametrize("S,N,P,K", [(9, 64, 12, 20), (3, 16, 12, 1), (5, 20, 8, 32), (2, 7, 12, 20)])
+@pytest.mark.parametrize("S,N,P,K", [(9, 64, 12, 20), (3, 16, 12, 1), (5, 20, 8, 32), (2, 7, 12, 20), (4, 9, 31, 3), (600, 64, 12, 20)])
 def test_decode_score_bit_exact(cuda, S, N, P, K):
     par, eps, last, gt, valid = _decode_inputs(S, N, P, K, seed=S * 7 + K)
     o = ops.decode_score(dev(par, cuda), dev(last, cuda), dev(gt, cuda), dev(valid, cuda), K, eps=dev(eps, cuda))
