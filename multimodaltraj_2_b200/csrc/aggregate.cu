@@ -136,7 +136,7 @@ int launch_aggregate(const float* logits, const float* logits2, const uint8_t* a
   int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   const size_t smem = (size_t)kAggWarps * N * 8;
   if (smem > 48 * 1024) {   // N > 768: beyond the default dynamic shared-memory limit (N <= 1024 -> 64 KB)
-    static unsigned long long smem_opted[1] = {};
+    static DeviceMask smem_opted[1];
     if (int rc = opt_in_smem(reinterpret_cast<const void*>(&aggregate_kernel), kAggWarps * 1024 * 8, &smem_opted[0])) return rc;
   }
   aggregate_kernel<<<grid, kAggWarps * 32, smem, stream>>>(logits, logits2, adj, feat, (int)rows, N, C, ld_feat, attn,
@@ -172,7 +172,7 @@ extern "C" int mmt_aggregate_transpose_f32(const float* attn, const float* d, in
   const int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   const size_t smem = (size_t)kAggWarps * N * 8;
   if (smem > 48 * 1024) {
-    static unsigned long long smem_opted[1] = {};
+    static DeviceMask smem_opted[1];
     if (int rc = opt_in_smem(reinterpret_cast<const void*>(&aggregate_transpose_kernel), kAggWarps * 1024 * 8, &smem_opted[0])) return rc;
   }
   aggregate_transpose_kernel<<<grid, kAggWarps * 32, smem, (cudaStream_t)stream>>>(attn, d, (int)rows, N, C, out);

@@ -77,11 +77,10 @@ int num_sms() {
   return n;
 }
 
-int opt_in_smem(const void* func, int bytes, unsigned long long* done) {
+int opt_in_smem(const void* func, int bytes, DeviceMask* mask) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
   const unsigned long long bit = 1ull << (dev & 63);
-  auto* mask = reinterpret_cast<std::atomic<unsigned long long>*>(done);
   if (mask->load(std::memory_order_acquire) & bit) return MMT_OK;
   const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
@@ -93,8 +92,7 @@ int opt_in_smem(const void* func, int bytes, unsigned long long* done) {
   return MMT_OK;
 }
 
-int env_int_once(const char* name, int* cache) {   // *cache: INT_MIN until read
-  auto* c = reinterpret_cast<std::atomic<int>*>(cache);
+int env_int_once(const char* name, std::atomic<int>* c) {
   int v = c->load(std::memory_order_relaxed);
   if (v != INT_MIN) return v;
   const char* s = getenv(name);

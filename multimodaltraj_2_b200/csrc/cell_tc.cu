@@ -685,7 +685,7 @@ static int tc_launch(TcArgs& a, cudaStream_t stream) {
   a.num_tiles = (a.R + TC_M - 1) / TC_M;
   a.trap = trap_record();
   constexpr int kSmem = (X3 ? SM_TOTAL_X3 : SM_TOTAL) + 1024, kPerSM = X3 ? 1 : 2;
-  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3>), kSmem, &smem_opted[0])) return rc;
   const int grid = a.num_tiles < kPerSM * num_sms() ? a.num_tiles : kPerSM * num_sms();
   gsk_cell_tc_kernel<LAY, X3><<<grid, X3 ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);

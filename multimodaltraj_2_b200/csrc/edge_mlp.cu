@@ -170,7 +170,7 @@ int launch_edge_mlp_f32(const float* h, int ld_h, const uint8_t* adj, const mmt_
   rc = launch_sgemm(h, ld_h, w->W1 + (size_t)U * He, He, nb, He, (int)R, He, U, stream);
   if (rc) return rc;
   const size_t smem = sizeof(float) * ((size_t)He * He + (size_t)ETILE * (He + 1)) + sizeof(int) * ECAP;
-  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&edge_mlp_kernel), 160 * 1024, &smem_opted[0])) return rc;
   int grid = S < num_sms() ? S : num_sms();
   edge_mlp_kernel<<<grid, 256, smem, stream>>>(na, nb, adj, w->b1, w->W2, w->b2, w->w_out, w->b_out, S, N, He, score);

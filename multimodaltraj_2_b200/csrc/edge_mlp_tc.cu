@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
 int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
                        int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
-  static unsigned long long smem_opted[3] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[3];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<false>), NP_SM_TOTAL + 1024, &smem_opted[0])) return rc;
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<true>), NP_SM_TOTAL + 1024, &smem_opted[1])) return rc;
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&edge_mlp_tc_kernel), EE_SM_TOTAL + 1024, &smem_opted[2])) return rc;

@@ -315,7 +315,7 @@ extern "C" int mmt_gemm_tf32(const float* A, int lda, int transA, const float* B
     const cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream);
     if (e != cudaSuccess) { set_error("mmt_gemm_tf32: memset: %s", cudaGetErrorString(e)); return MMT_ECUDA; }
   }
-  static unsigned long long smem_opted[1] = {};
+  static DeviceMask smem_opted[1];
   if ((rc = opt_in_smem(reinterpret_cast<const void*>(&gemm_tf32_kernel), GB_SM_TOTAL + 1024, &smem_opted[0]))) return rc;
   gemm_tf32_kernel<<<dim3(tm, tn, splits), GB_THREADS, GB_SM_TOTAL + 1024, stream>>>(tmA, tmB, a);
   count_launch();

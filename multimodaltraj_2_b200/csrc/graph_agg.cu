@@ -234,7 +234,7 @@ int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const
                                    float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   const size_t smem = 128 * GB_HROW * 2 + 128 * GB_CROW * 4 + 128 * 8 + (size_t)8 * N * 8 + 128 + 16;
-  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_blocked_kernel), 112 * 1024, &smem_opted[0])) return rc;
   const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   graph_aggregate_blocked_kernel<<<grid, GB_THREADS, smem, stream>>>(

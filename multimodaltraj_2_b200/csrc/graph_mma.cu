@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
                                int S, int N, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
-  static unsigned long long smem_opted[1] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_mma_kernel), GM_SM_TOTAL + 1024, &smem_opted[0])) return rc;
   const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
   graph_aggregate_mma_kernel<<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(

@@ -1,6 +1,8 @@
 // Shared helpers for libmmt (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -17,14 +19,15 @@ void count_launch(int n = 1);
 // Opt a kernel into `bytes` of dynamic shared memory on the current device.  The attribute is per device and per
 // function: `done` is the caller's bit mask of devices already opted in (one static mask per kernel).  Thread-safe;
 // returns MMT_OK / MMT_ECUDA.
-int opt_in_smem(const void* func, int bytes, unsigned long long* done);
+using DeviceMask = std::atomic<unsigned long long>;
+int opt_in_smem(const void* func, int bytes, DeviceMask* done);
 
 // 16 words of host-mapped pinned memory (same address on every device under UVA) that a trapping kernel fills in
 // before it dies (tc_common.cuh: trap_report); nullptr if the allocation failed.  Never freed (process lifetime).
 uint32_t* trap_record();
 
 // value of an integer environment variable read ONCE per process (diagnostic switches; never on the launch path)
-int env_int_once(const char* name, int* cache);
+int env_int_once(const char* name, std::atomic<int>* cache);   // *cache: INT_MIN until read
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -746,9 +746,9 @@ int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, 
   a.dbg = dbg;
   a.trap = trap_record();
   // diagnostic switches of scratch/ro_*.py (timing experiments, fault injection): read once per process
-  static int env_flags = INT_MIN, env_grid = INT_MIN;
+  static std::atomic<int> env_flags{INT_MIN}, env_grid{INT_MIN};
   a.flags = env_int_once("MMT_RO_FLAGS", &env_flags);
-  static unsigned long long smem_opted[2] = {};   // per kernel: devices already opted in
+  static DeviceMask smem_opted[2];   // per kernel: devices already opted in
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<false>), RS_TOTAL + 1024, &smem_opted[0])) return rc;
   if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<true>), RS_TOTAL + 1024, &smem_opted[1])) return rc;
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
