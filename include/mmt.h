@@ -302,13 +302,15 @@ int mmt_gsk_gates_f32(const float* z, const float* c, const float* mc, const uin
  * (0 for invalid rows).
  * mmt_gsk_cell_backward_f32: backward of mmt_gsk_cell given the pre-activations z[R,3U] = [e|h|mh] W + b, the
  * previous cell state c, mc, and the upstream gradients d_mt (w.r.t. h' = m_t), d_mf, d_ct (either may be NULL = 0):
- * dz[R,3U], dc[R,U] (w.r.t. the previous c), dmc[R,U]; dpeep[4,U] += gradients of (w_If, w_It, w_Of, w_Ot). */
+ * dz[R,3U], dc[R,U] (w.r.t. the previous c), dmc[R,U]; dpeep[4,U] += gradients of (w_If, w_It, w_Of, w_Ot);
+ * db[3U] += the gate-bias gradient (column sums of dz), fused so that no separate pass re-reads dz. */
 int mmt_head_nll_f32(const float* m_t, const float* m_f, const uint8_t* valid, const float* W_h, const float* b_h,
                      const float* target, int R, int U, float scale, float* loss_sum, float* dy, void* stream);
 int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, const uint8_t* valid,
                               const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot,
                               const float* d_mt, const float* d_mf, const float* d_ct, int R, int U, float* dz,
-                              float* dc, float* dmc, float* dpeep, void* stream);
+                              float* dc, float* dmc, float* dpeep, float* db /* [3U] += column sums of dz, or NULL */,
+                              void* stream);
 
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);

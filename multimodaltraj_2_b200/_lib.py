@@ -90,7 +90,7 @@ SIGNATURES = {
     "mmt_head_nll_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
     "mmt_gsk_gates_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "mmt_gsk_cell_backward_f32": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp,
-                                            vp]),
+                                            vp, vp]),
     "mmt_gemm_tf32": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_float, C.c_int, vp]),
     "mmt_allreduce_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),

@@ -104,11 +104,12 @@ __global__ void __launch_bounds__(128) gsk_cell_backward_kernel(
     const float* __restrict__ w_If, const float* __restrict__ w_It, const float* __restrict__ w_Of,
     const float* __restrict__ w_Ot, const float* __restrict__ d_mt, const float* __restrict__ d_mf,
     const float* __restrict__ d_ct, int R, int U, float* __restrict__ dz, float* __restrict__ dc,
-    float* __restrict__ dmc, float* __restrict__ dpeep) {
+    float* __restrict__ dmc, float* __restrict__ dpeep, float* __restrict__ db) {
   const int u = threadIdx.x;
   if (u >= U) return;
   const float pIf = w_If[u], pIt = w_It[u], pOf = w_Of[u], pOt = w_Ot[u];
   float aIf = 0.f, aIt = 0.f, aOf = 0.f, aOt = 0.f;
+  float bI = 0.f, bJ = 0.f, bO = 0.f;   // column sums of dz = the bias gradient (was a separate reduction pass over dz)
   for (int r = blockIdx.x; r < R; r += gridDim.x) {
     const size_t o = (size_t)r * U + u, oz = (size_t)r * 3 * U + u;
     float di = 0.f, dj = 0.f, dO = 0.f, dcp = 0.f, dm = 0.f;
@@ -143,6 +144,9 @@ __global__ void __launch_bounds__(128) gsk_cell_backward_kernel(
     dz[oz] = di;
     dz[oz + U] = dj;
     dz[oz + 2 * U] = dO;
+    bI += di;
+    bJ += dj;
+    bO += dO;
     dc[o] = dcp;
     dmc[o] = dm;
   }
@@ -150,6 +154,11 @@ __global__ void __launch_bounds__(128) gsk_cell_backward_kernel(
   atomicAdd(dpeep + U + u, aIt);
   atomicAdd(dpeep + 2 * U + u, aOf);
   atomicAdd(dpeep + 3 * U + u, aOt);
+  if (db) {
+    atomicAdd(db + u, bI);
+    atomicAdd(db + U + u, bJ);
+    atomicAdd(db + 2 * U + u, bO);
+  }
 }
 
 }  // namespace mmt
@@ -170,7 +179,7 @@ extern "C" int mmt_head_nll_f32(const float* m_t, const float* m_f, const uint8_
 extern "C" int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, const uint8_t* valid,
                                          const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot,
                                          const float* d_mt, const float* d_mf, const float* d_ct, int R, int U,
-                                         float* dz, float* dc, float* dmc, float* dpeep, void* stream) {
+                                         float* dz, float* dc, float* dmc, float* dpeep, float* db, void* stream) {
   using namespace mmt;
   MMT_REQUIRE(R >= 0 && U > 0 && U <= 128, "need R >= 0, 0 < U <= 128");
   if (R == 0) return MMT_OK;
@@ -178,7 +187,7 @@ extern "C" int mmt_gsk_cell_backward_f32(const float* z, const float* c, const f
               "z/c/mc/valid/peepholes/d_mt/outputs required");
   const int grid = R < num_sms() * 16 ? R : num_sms() * 16;
   gsk_cell_backward_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z, c, mc, valid, w_If, w_It, w_Of, w_Ot, d_mt, d_mf,
-                                                                   d_ct, R, U, dz, dc, dmc, dpeep);
+                                                                   d_ct, R, U, dz, dc, dmc, dpeep, db);
   count_launch();
   return check_launch("gsk_cell_backward_kernel");
 }

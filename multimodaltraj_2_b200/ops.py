@@ -243,9 +243,9 @@ def gsk_gates(z, c, mc, valid, params: "CellParams"):
     return h_out, c_out, mf
 
 
-def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, dpeep):
+def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, dpeep, db=None):
     """Backward of the gate update from the saved pre-activations (mmt_gsk_cell_backward_f32):
-    returns (dz[R,3U], dc[R,U], dmc[R,U]); dpeep[4,U] is accumulated in place."""
+    returns (dz[R,3U], dc[R,U], dmc[R,U]); dpeep[4,U] and (if given) db[3U], the gate-bias gradient, are accumulated in place."""
     lib = _lib.load()
     for n, t in dict(z=z, c=c, mc=mc, d_mt=d_mt, dpeep=dpeep).items():
         _chk(t, torch.float32, n)
@@ -254,7 +254,7 @@ def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, d
     dz, dc, dmc = torch.empty_like(z), torch.empty_like(c), torch.empty_like(c)
     _lib.check(lib.mmt_gsk_cell_backward_f32(_p(z), _p(c), _p(mc), _p(valid), _p(params.w_If), _p(params.w_It),
                                              _p(params.w_Of), _p(params.w_Ot), _p(d_mt), _p(d_mf), _p(d_ct), R, U,
-                                             _p(dz), _p(dc), _p(dmc), _p(dpeep), _stream()), "mmt_gsk_cell_backward_f32")
+                                             _p(dz), _p(dc), _p(dmc), _p(dpeep), _p(db), _stream()), "mmt_gsk_cell_backward_f32")
     return dz, dc, dmc
 
 

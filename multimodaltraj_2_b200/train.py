@@ -355,15 +355,18 @@ class Trainer:
             e = r["e"] if "e" in r else torch.relu(r["x"] @ p.W_e + p.b_e)
             A = r.pop("A") if "A" in r else torch.cat([e, r["h"], r["mh"]], -1)
             z = r.pop("z") if "z" in r else torch.addmm(p.b, A, p.W)
-            dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep)
             tc = self.gemm == "tc"
+            # "tc": the bias gradient (column sums of dz) comes out of the same kernel, no separate reduction over dz
+            dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep,
+                                                db=g["b"] if tc else None)
             if tc:
                 ops.gemm_tf32(A, dz, transA=True, out=g["W"], accumulate=True)      # dW += A^T dz  (K = all agent rows)
                 dA = ops.gemm_tf32(dz, p.W, transB=True)                           # dA  = dz W^T
             else:
                 g["W"] += A.t() @ dz
                 dA = dz @ p.W.t()
-            g["b"] += dz.sum(0)
+            if not tc:
+                g["b"] += dz.sum(0)
             dpre = dA[:, :E] * (e > 0)
             g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
