@@ -260,8 +260,10 @@ class Trainer:
         #          instead of the fused fp32 CUDA-core cell kernel.
         #   "tc"   this library's own contractions: mmt_gemm_tf32 (TMA tensor maps -> tcgen05.mma.kind::tf32 -> TMEM; split-K
         #          with red.add for the weight gradients) for the gate GEMM forward, A^T dz and dz W^T -- 97 % of the step's
-        #          FLOPs -- and mmt_aggregate_transpose_f32 for att^T [d mh | d mc]; same tolerance as "tf32".  Only the 5-wide
-        #          head and the 4-wide embedding products (1 % of the FLOPs) stay library calls.
+        #          FLOPs -- the head-weight and embedding-weight gradients ([hn|mf]^T dy, x^T dpre: K = all agent rows too),
+        #          mmt_aggregate_transpose_f32 for att^T [d mh | d mc], the bias gradient inside gsk_cell_backward_kernel; same
+        #          tolerance as "tf32".  Left as library calls: the two products with a 4- / 5-long inner dimension
+        #          (x W_e, dy W_h^T: 0.3 % of the FLOPs) and the elementwise glue.
         if gemm not in ("fp32", "tf32", "tc"):
             raise ValueError("gemm must be 'fp32', 'tf32' or 'tc'")
         self.gemm = gemm
@@ -342,12 +344,20 @@ class Trainer:
         dpeep = torch.zeros((4, U), device=dev)
         Gh = torch.zeros((R, U), device=dev)
         Gc = None
+        tc = self.gemm == "tc"
+        gWh8 = torch.zeros((2 * U, 8), device=dev) if tc else None     # head-weight gradient, 8-column rows (ld % 4 == 0)
         for t in reversed(range(T + P - 1)):
             r = saved[t]
             d_mf = None
             if "dy" in r:
                 dy = r["dy"]
-                g["W_h"] += torch.cat([r["hn"], r["mf"]], -1).t() @ dy
+                if tc:
+                    # [hn | mf]^T dy (K = all agent rows) on mmt_gemm_tf32, split over K; dy padded to 8 columns for the tensor map
+                    dy8 = torch.nn.functional.pad(dy, (0, 3))
+                    ops.gemm_tf32(r["hn"], dy8, transA=True, out=gWh8[:U], accumulate=True)
+                    ops.gemm_tf32(r["mf"], dy8, transA=True, out=gWh8[U:], accumulate=True)
+                else:
+                    g["W_h"] += torch.cat([r["hn"], r["mf"]], -1).t() @ dy
                 g["b_h"] += dy.sum(0)
                 dhm = dy @ p.W_h.t()
                 Gh = Gh + dhm[:, :U]
@@ -355,7 +365,6 @@ class Trainer:
             e = r["e"] if "e" in r else torch.relu(r["x"] @ p.W_e + p.b_e)
             A = r.pop("A") if "A" in r else torch.cat([e, r["h"], r["mh"]], -1)
             z = r.pop("z") if "z" in r else torch.addmm(p.b, A, p.W)
-            tc = self.gemm == "tc"
             # "tc": the bias gradient (column sums of dz) comes out of the same kernel, no separate reduction over dz
             dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep,
                                                 db=g["b"] if tc else None)
@@ -368,7 +377,10 @@ class Trainer:
             if not tc:
                 g["b"] += dz.sum(0)
             dpre = dA[:, :E] * (e > 0)
-            g["W_e"] += r["x"].t() @ dpre
+            if tc:
+                ops.gemm_tf32(r["x"], dpre.contiguous(), transA=True, out=g["W_e"], accumulate=True)
+            else:
+                g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
             d_mh = dA[:, E + U:].reshape(S, N, U)
             if tc:
@@ -381,6 +393,8 @@ class Trainer:
                 Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
             if self.relational:
                 Gh = Gh + self._edge_backward(r, d_mh, dmc.view(S, N, U), g, S, N)
+        if tc:
+            g["W_h"] += gWh8[:, :5]
         g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]
         return loss_sum, valid.sum().float() * P, g
 
