@@ -103,6 +103,31 @@ int mmt_edge_mlp_bf16(const float* h, const uint8_t* adj, const void* packed, co
                       const float* w_out, const float* b_out, int S, int N, int U, int He, float* score,
                       float* work, size_t work_bytes, void* stream);
 
+/* Backward pass of the relational scores (training of g2k_lstm_mcr, BASELINE configs[1]; the reference differentiates
+ * models/g2k_lstm_mcr.py:99-124 / relational_inf_models/nri_learned.py:5-28 through TF autodiff, train.py:240-254).
+ * Everything runs on the edges of adj, compacted on the device: no edge list goes to the host.
+ *
+ * mmt_attention_score_grad_f32: gradient of the loss w.r.t. the attention LOGITS through the aggregated state,
+ *   G_ij = dm_i . v_j,  dlogit_ij = attn_ij (G_ij - sum_k attn_ik G_ik) on the edges, 0 elsewhere;
+ *   attn[S,N,N] as written by mmt_aggregate_f32, dm[S*N,C] = d loss / d [mh | mc], v[S*N,C] = [h | c]; C % 128 == 0, C <= 512.
+ * mmt_edge_mlp_backward_f32 (fp32 CUDA cores, He in {64,128}) / _bf16 (tcgen05, bf16 operands, U = He = 128; tolerance
+ *   2e-2 of the largest gradient entry): from dlogit (the scores are added to the logits), per edge
+ *   du = dlogit s (1 - s), d pre2 = du w_out elu'(pre2), d pre1 = (d pre2 W2^T) elu'(pre1); outputs
+ *   dab[S*N, 2 He] = [sum_j d pre1_ij | sum_i d pre1_ij] (overwritten), and ACCUMULATED into: gW2[He,He] += e1^T d pre2,
+ *   gb2 += sum d pre2, gw_out += e2^T du, gb_out += sum du, gb1 += sum d pre1 (fp32 version only: the column sums of
+ *   dab[:, :He] give the same).  The node level (g W1 = h^T [da | db], d h = da W1a^T + db W1b^T) is two GEMMs of the
+ *   caller (mmt_gemm_tf32).  work: >= 2*S*N*He floats. */
+int mmt_attention_score_grad_f32(const float* attn, const uint8_t* adj, const float* dm, const float* v, int S, int N, int C,
+                                 float* dlogit, void* stream);
+int mmt_edge_mlp_backward_f32(const float* h, const uint8_t* adj, const float* dlogit, const float* W1, const float* b1,
+                              const float* W2, const float* b2, const float* w_out, const float* b_out, int S, int N, int U,
+                              int He, float* dab, float* gW2, float* gb1, float* gb2, float* gw_out, float* gb_out,
+                              float* work, size_t work_bytes, void* stream);
+int mmt_edge_mlp_backward_bf16(const float* h, const uint8_t* adj, const float* dlogit, const void* packed, const float* b1,
+                               const float* b2, const float* w_out, const float* b_out, int S, int N, int U, int He,
+                               float* dab, float* gW2, float* gb2, float* gw_out, float* gb_out, float* work,
+                               size_t work_bytes, void* stream);
+
 /* ---- gsk_lstm_cell: fused gate update ---------------------------------------------------------
  * Replaces models/gsk_lstm_cell.py:4-65 (dead Hadamard stub) with the GridLSTMCell gate
  * equations of helper.py:31-39 at U units over the graph neighbourhood:

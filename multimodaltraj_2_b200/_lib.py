@@ -58,6 +58,9 @@ SIGNATURES = {
     "mmt_pack_edge_weights_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     "mmt_edge_mlp_bf16": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t,
                                     vp]),
+    "mmt_attention_score_grad_f32": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "mmt_edge_mlp_backward_f32": (C.c_int, [vp] * 9 + [C.c_int] * 4 + [vp] * 7 + [C.c_size_t, vp]),
+    "mmt_edge_mlp_backward_bf16": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp] * 6 + [C.c_size_t, vp]),
     "mmt_gsk_cell": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                C.c_int, vp, vp]),
     "mmt_gate_weights_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libmmt.so"
 SOURCES = ["capi.cu", "pairwise.cu", "aggregate.cu", "cell_f32.cu", "cell_tc.cu", "edge_mlp.cu",
-           "decode_score.cu", "track_a.cu", "scene_batch.cu", "forecast.cu", "scores.cu", "graph_agg.cu", "graph_mma.cu", "rollout_tc.cu", "edge_mlp_tc.cu", "train_step.cu", "static_ctx.cu", "collective.cu", "gemm_tc.cu"]
+           "decode_score.cu", "track_a.cu", "scene_batch.cu", "forecast.cu", "scores.cu", "graph_agg.cu", "graph_mma.cu", "rollout_tc.cu", "edge_mlp_tc.cu", "train_step.cu", "static_ctx.cu", "collective.cu", "gemm_tc.cu", "edge_mlp_bwd.cu", "edge_mlp_bwd_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -48,10 +48,10 @@ static void describe_trap(char* out, size_t n) {
   const uint32_t* r = g_trap.load(std::memory_order_acquire);
   if (!r || r[0] == 0) { out[0] = 0; return; }
   static const char* kern[] = {"?", "rollout_tc_kernel", "gsk_cell_tc_kernel", "graph_aggregate_mma_kernel",
-                               "node_proj_tc_kernel", "edge_mlp_tc_kernel", "gemm_tf32_kernel"};
+                               "node_proj_tc_kernel", "edge_mlp_tc_kernel", "gemm_tf32_kernel", "edge_mlp_bwd_tc_kernel"};
   const uint32_t k = r[0] >> 8, w = r[0] & 0xFFu;
   snprintf(out, n, " [device trap: %s site 0x%02x%s, CTA %u thread %u, barrier smem 0x%x parity %u]",
-           k < 7 ? kern[k] : "?", w, w == 0xFF ? " (smem base misaligned)" : " (bounded mbarrier wait expired)", r[1], r[2],
+           k < 8 ? kern[k] : "?", w, w == 0xFF ? " (smem base misaligned)" : " (bounded mbarrier wait expired)", r[1], r[2],
            r[3], r[4]);
 }
 

@@ -380,6 +380,18 @@ int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void*
   return check_launch("edge_mlp_tc_kernel");
 }
 
+// node projections only (the backward kernel of edge_mlp_bwd_tc.cu gathers the same [a | b] rows)
+int launch_node_proj_tc(const float* h, int ld_h, const void* packed, int R, __nv_bfloat16* out, cudaStream_t stream) {
+  static DeviceMask smem_opted[1];
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<false>), NP_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  const int tiles = (R + 127) / 128;
+  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+  node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, reinterpret_cast<const uint8_t*>(packed), out,
+                                                                        tiles, trap_record());
+  count_launch();
+  return check_launch("node_proj_tc_kernel");
+}
+
 int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream) {
   const int n = 256 * 128 + 128 * 128;
   pack_edge_weights_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W1, W2, reinterpret_cast<uint8_t*>(packed));

@@ -88,9 +88,21 @@ def aggregate_transpose(attn, d):
     return out
 
 
-def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out, prec=PREC_F32):
+def pack_edge_weights(W1, W2):
+    """bf16 tensor-core operand images of the edge-MLP weights (mmt_pack_edge_weights_bf16; U = He = 128)."""
+    lib = _lib.load()
+    U, He = W1.shape[0] // 2, W2.shape[0]
+    nb = lib.mmt_edge_weights_packed_bytes(U, He)
+    if nb == 0:
+        raise ValueError("tensor-core edge MLP needs U = He = 128")
+    packed = torch.empty((nb,), dtype=torch.uint8, device=W1.device)
+    _lib.check(lib.mmt_pack_edge_weights_bf16(_p(W1), _p(W2), U, He, _p(packed), _stream()), "mmt_pack_edge_weights_bf16")
+    return packed
+
+
+def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out, prec=PREC_F32, packed=None):
     """score[S,N,N] of the relational edge MLP on the edges of adj (0 elsewhere).  prec = PREC_BF16 runs the
-    tcgen05 version (U = He = 128)."""
+    tcgen05 version (U = He = 128; ``packed``: the images of pack_edge_weights, built here when None)."""
     lib = _lib.load()
     for n, t in dict(h=h, W1=W1, b1=b1, W2=W2, b2=b2, w_out=w_out, b_out=b_out).items():
         _chk(t, torch.float32, n)
@@ -100,17 +112,54 @@ def edge_mlp(h, adj, W1, b1, W2, b2, w_out, b_out, prec=PREC_F32):
     score = torch.empty((S, N, N), dtype=torch.float32, device=h.device)
     work = torch.empty((2 * S * N * He,), dtype=torch.float32, device=h.device)
     if prec != PREC_F32:
-        nb = lib.mmt_edge_weights_packed_bytes(U, He)
-        if nb == 0:
-            raise ValueError("tensor-core edge MLP needs U = He = 128")
-        packed = torch.empty((nb,), dtype=torch.uint8, device=h.device)
-        _lib.check(lib.mmt_pack_edge_weights_bf16(_p(W1), _p(W2), U, He, _p(packed), _stream()), "mmt_pack_edge_weights_bf16")
+        if packed is None:
+            packed = pack_edge_weights(W1, W2)
         _lib.check(lib.mmt_edge_mlp_bf16(_p(h), _p(adj), _p(packed), _p(b1), _p(b2), _p(w_out), _p(b_out), S, N, U, He,
                                          _p(score), _p(work), work.numel() * 4, _stream()), "mmt_edge_mlp_bf16")
         return score
     _lib.check(lib.mmt_edge_mlp_f32(_p(h), _p(adj), _p(W1), _p(b1), _p(W2), _p(b2), _p(w_out), _p(b_out), S, N, U, He,
                                     _p(score), _p(work), work.numel() * 4, _stream()), "mmt_edge_mlp_f32")
     return score
+
+
+def attention_score_grad(attn, adj, dm, v):
+    """d loss / d attention logits [S,N,N] through the aggregated state (mmt_attention_score_grad_f32):
+    attn_ij (dm_i . v_j - sum_k attn_ik dm_i . v_k) on the edges.  dm, v: [S,N,C]."""
+    lib = _lib.load()
+    _chk(attn, torch.float32, "attn"); _chk(adj, torch.uint8, "adj"); _chk(dm, torch.float32, "dm"); _chk(v, torch.float32, "v")
+    S, N, Cc = v.shape
+    out = torch.empty((S, N, N), dtype=torch.float32, device=v.device)
+    _lib.check(lib.mmt_attention_score_grad_f32(_p(attn), _p(adj), _p(dm), _p(v), S, N, Cc, _p(out), _stream()),
+               "mmt_attention_score_grad_f32")
+    return out
+
+
+def edge_mlp_backward(h, adj, dlogit, p, g, prec=PREC_F32, packed=None):
+    """Backward of ``edge_mlp`` on the edges of adj (mmt_edge_mlp_backward_f32 / _bf16), no host synchronisation.
+    p: CellParams (edge weights); g: dict of gradient tensors, W2 / b1 / b2 / w_out / b_out accumulated in place.
+    Returns dab[S*N, 2 He] = [d loss / d a | d loss / d b] of the node projections a = h W1[:U], b = h W1[U:]."""
+    lib = _lib.load()
+    _chk(h, torch.float32, "h"); _chk(adj, torch.uint8, "adj"); _chk(dlogit, torch.float32, "dlogit")
+    S, N, U = h.shape
+    He = p.W2.shape[0]
+    for k in ("W2", "b1", "b2", "w_out", "b_out"):
+        _chk(g[k], torch.float32, "g." + k)
+    dab = torch.empty((S * N, 2 * He), dtype=torch.float32, device=h.device)
+    work = torch.empty((2 * S * N * He,), dtype=torch.float32, device=h.device)
+    if prec != PREC_F32:
+        if packed is None:
+            packed = pack_edge_weights(p.W1, p.W2)
+        _lib.check(lib.mmt_edge_mlp_backward_bf16(_p(h), _p(adj), _p(dlogit), _p(packed), _p(p.b1), _p(p.b2), _p(p.w_out),
+                                                  _p(p.b_out), S, N, U, He, _p(dab), _p(g["W2"]), _p(g["b2"]), _p(g["w_out"]),
+                                                  _p(g["b_out"]), _p(work), work.numel() * 4, _stream()),
+                   "mmt_edge_mlp_backward_bf16")
+        g["b1"] += dab[:, :He].sum(0)
+        return dab
+    _lib.check(lib.mmt_edge_mlp_backward_f32(_p(h), _p(adj), _p(dlogit), _p(p.W1), _p(p.b1), _p(p.W2), _p(p.b2), _p(p.w_out),
+                                             _p(p.b_out), S, N, U, He, _p(dab), _p(g["W2"]), _p(g["b1"]), _p(g["b2"]),
+                                             _p(g["w_out"]), _p(g["b_out"]), _p(work), work.numel() * 4, _stream()),
+               "mmt_edge_mlp_backward_f32")
+    return dab
 
 
 # --------------------------------------------------------------------------------------------

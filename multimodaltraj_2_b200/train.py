@@ -268,7 +268,8 @@ class Trainer:
             raise ValueError("gemm must be 'fp32', 'tf32' or 'tc'")
         self.gemm = gemm
         # relational: g2k_lstm_mcr -- the attention logits are kern + the edge-MLP score (mmt_edge_mlp_f32); its backward
-        # (softmax -> per-edge two-layer ELU MLP -> node projections) runs on the compacted edge list with library ops
+        # (softmax -> per-edge two-layer ELU MLP -> node projections) runs on the device-side edge list of
+        # mmt_attention_score_grad_f32 + mmt_edge_mlp_backward_f32 (gemm = "tc", U = He = 128: _bf16 on tcgen05), no host sync
         self.relational = bool(relational)
         if self.relational and params.W1 is None:
             raise ValueError("relational training needs the edge-MLP weights (W1 .. b_out)")
@@ -300,13 +301,18 @@ class Trainer:
         c = torch.zeros((S, N, U), device=dev)
         saved = []
         loss_sum = torch.zeros((1,), device=dev)
+        edge_packed = None
+        if self.relational and self.gemm == "tc" and U == 128 and p.W2.shape[0] == 128:
+            edge_packed = ops.pack_edge_weights(p.W1, p.W2)
         for t in range(T + P - 1):
             cur = pos[:, :, t].contiguous()
             disp = cur - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
             x = torch.cat([disp, vis[:, :, min(t, T - 1)]], -1).reshape(R, 4).contiguous()
             kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
             if self.relational:
-                kern = kern + ops.edge_mlp(h.contiguous(), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out)
+                # "tc" with U = He = 128: the tcgen05 edge MLP (bf16 operands); its backward recomputes the same values
+                kern = kern + ops.edge_mlp(h.contiguous(), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out,
+                                           ops.PREC_BF16 if edge_packed is not None else ops.PREC_F32, edge_packed)
             att, mhc = ops.aggregate(kern, adj, torch.cat([h, c], -1).contiguous())
             mh, mc = mhc[..., :U].reshape(R, U).contiguous(), mhc[..., U:].reshape(R, U).contiguous()
             rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc)
@@ -334,9 +340,9 @@ class Trainer:
             saved.append(rec)
             h, c = hn.view(S, N, U), cn.view(S, N, U)
         # ---- back-propagation through time
-        return self._backward(saved, loss_sum, valid, vflat, S, N)
+        return self._backward(saved, loss_sum, valid, vflat, S, N, edge_packed)
 
-    def _backward(self, saved, loss_sum, valid, vflat, S, N):
+    def _backward(self, saved, loss_sum, valid, vflat, S, N, edge_packed=None):
         p, T, P = self.p, self.T, self.P
         R, U, E = S * N, p.U, p.E
         dev = vflat.device
@@ -346,6 +352,11 @@ class Trainer:
         Gc = None
         tc = self.gemm == "tc"
         gWh8 = torch.zeros((2 * U, 8), device=dev) if tc else None     # head-weight gradient, 8-column rows (ld % 4 == 0)
+        node = None
+        if self.relational:                                            # node level of the edge MLP: [a | b] = h [W1a | W1b]
+            He = p.W2.shape[0]
+            node = dict(W1cat=torch.cat([p.W1[:U], p.W1[U:]], 1).contiguous(), gW1=torch.zeros((U, 2 * He), device=dev),
+                        packed=edge_packed)
         for t in reversed(range(T + P - 1)):
             r = saved[t]
             d_mf = None
@@ -383,8 +394,9 @@ class Trainer:
                 g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
             d_mh = dA[:, E + U:].reshape(S, N, U)
+            dmhc = torch.cat([d_mh, dmc.view(S, N, U)], -1).contiguous() if (tc or self.relational) else None
             if tc:
-                back = ops.aggregate_transpose(r["att"], torch.cat([d_mh, dmc.view(S, N, U)], -1).contiguous()).reshape(R, 2 * U)
+                back = ops.aggregate_transpose(r["att"], dmhc).reshape(R, 2 * U)
                 Gh = dA[:, E:E + U] + back[:, :U]
                 Gc = (dc + back[:, U:]).contiguous()
             else:
@@ -392,46 +404,36 @@ class Trainer:
                 Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
                 Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
             if self.relational:
-                Gh = Gh + self._edge_backward(r, d_mh, dmc.view(S, N, U), g, S, N)
+                Gh = Gh + self._edge_backward(r, dmhc, g, S, N, node)
         if tc:
             g["W_h"] += gWh8[:, :5]
+        if self.relational:
+            He = p.W2.shape[0]
+            g["W1"][:U] += node["gW1"][:, :He]
+            g["W1"][U:] += node["gW1"][:, He:]
         g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]
         return loss_sum, valid.sum().float() * P, g
 
-    def _edge_backward(self, r, d_mh, d_mc, g, S, N):
+    def _edge_backward(self, r, dmhc, g, S, N, node):
         """Back through the attention softmax and the relational edge MLP of one step (oracle: train_b.edge_scores):
-        accumulates the edge-weight gradients into ``g`` and returns d loss / d h[R,U] through the scores."""
+        accumulates the edge-weight gradients into ``g`` / ``node`` and returns d loss / d h[R,U] through the scores.
+        dmhc[S,N,2U] = d loss / d [mh | mc].  All of it on the device-side edge list of the kernels: no host sync.
+          mmt_attention_score_grad_f32   d logit_ij = att_ij (G_ij - sum_k att_ik G_ik), G_ij = d mh_i . h_j + d mc_i . c_j
+          mmt_edge_mlp_backward_f32/bf16 per edge: sigmoid -> ELU layer 2 -> ELU layer 1; g W2, g b*, g w_out; [d a | d b] rows
+          node level                     g W1 += h^T [d a | d b],  d h = [d a | d b] [W1a | W1b]^T   (two GEMMs)."""
         p = self.p
-        U = p.U
+        U, He = p.U, p.W2.shape[0]
         h = r["h"]
-        att = r["att"]
-        # G_ij = d mh_i . h_j + d mc_i . c_j ; d logit = att * (G - sum_k att_ik G_ik)
-        G = torch.bmm(d_mh, h.view(S, N, U).transpose(1, 2)) + torch.bmm(d_mc, r["c"].view(S, N, U).transpose(1, 2))
-        dlog = att * (G - (att * G).sum(-1, keepdim=True))
-        s_, i_, j_ = r["adj"].nonzero(as_tuple=True)               # compacted edge list (host sync: first version)
-        if s_.numel() == 0:
-            return torch.zeros_like(h)
-        ri, rj = s_ * N + i_, s_ * N + j_
-        W1a, W1b = p.W1[:U], p.W1[U:]
-        a, b = h @ W1a, h @ W1b                                    # node projections [R, He]
-        pre1 = a[ri] + b[rj] + p.b1
-        e1 = torch.nn.functional.elu(pre1)
-        pre2 = torch.addmm(p.b2, e1, p.W2)
-        e2 = torch.nn.functional.elu(pre2)
-        sc = torch.sigmoid(e2 @ p.w_out + p.b_out)
-        du = dlog[s_, i_, j_] * sc * (1 - sc)
-        g["w_out"] += e2.t() @ du
-        g["b_out"] += du.sum()
-        dpre2 = du[:, None] * p.w_out[None, :] * torch.where(pre2 > 0, torch.ones_like(pre2), e2 + 1)
-        g["W2"] += e1.t() @ dpre2
-        g["b2"] += dpre2.sum(0)
-        dpre1 = (dpre2 @ p.W2.t()) * torch.where(pre1 > 0, torch.ones_like(pre1), e1 + 1)
-        g["b1"] += dpre1.sum(0)
-        da = torch.zeros_like(a).index_add_(0, ri, dpre1)
-        db = torch.zeros_like(b).index_add_(0, rj, dpre1)
-        g["W1"][:U] += h.t() @ da
-        g["W1"][U:] += h.t() @ db
-        return da @ W1a.t() + db @ W1b.t()
+        hc = torch.cat([h, r["c"]], -1).view(S, N, 2 * U)
+        dlog = ops.attention_score_grad(r["att"], r["adj"], dmhc, hc)
+        packed = node["packed"]
+        dab = ops.edge_mlp_backward(h.view(S, N, U), r["adj"], dlog, p, g, ops.PREC_BF16 if packed is not None else ops.PREC_F32,
+                                    packed)
+        if self.gemm == "tc":
+            ops.gemm_tf32(h, dab, transA=True, out=node["gW1"], accumulate=True)
+            return ops.gemm_tf32(dab, node["W1cat"], transB=True)
+        node["gW1"] += h.t() @ dab
+        return dab @ node["W1cat"].t()
 
     def loss_and_grads(self, pos, vis, valid):
         """Single-process view: (mean loss incl. weight decay, {name: gradient of it})."""

@@ -144,6 +144,75 @@ def test_edge_mlp_bf16_tensor_core(cuda, S, N):
     within(np.abs(sc - osc).max(), 3.5e-3, "edge_mlp_bf16.score")
 
 
+def _edge_case(S, N, He, seed):
+    """A crowd, its adjacency / attention, random states and upstream gradients; everything the edge backward reads."""
+    U = 128
+    p = synth.init_params(seed=2, He=He)
+    rng = np.random.default_rng(seed)
+    pos, _, valid = synth.make_crowd(S, N, seed=seed + 17, half_extent=4.0 if N < 100 else 8.0, ragged=(N in (12, 16)))
+    if S > 600:
+        valid[5:9] = 0
+    kern, adj, _ = o_b.pairwise_adj(pos[:, :, 0], valid, 4.0, 0.5)
+    h = (rng.standard_normal((S, N, U)) * 0.5).astype(np.float32)
+    return p, adj, kern, h, rng
+
+
+@pytest.mark.parametrize("S,N", [(5, 32), (3, 64), (2, 256), (4, 12)])
+def test_attention_score_grad_matches_autograd(cuda, S, N):
+    """mmt_attention_score_grad_f32 == d/d logits of sum(dm * (softmax(logits) @ v)) (fp64 autograd), zero off the edges."""
+    U = 128
+    p, adj, kern, h, rng = _edge_case(S, N, 128, seed=40 + N)
+    c = (rng.standard_normal((S, N, U)) * 0.5).astype(np.float32)
+    dm = rng.standard_normal((S, N, 2 * U)).astype(np.float32)
+    v = np.concatenate([h, c], -1)
+    lg = torch.tensor(kern.astype(np.float64), requires_grad=True)
+    adj_t = torch.tensor(adj != 0)
+    att = torch.where(adj_t, torch.exp(torch.where(adj_t, lg, torch.zeros_like(lg))), torch.zeros_like(lg))
+    den = att.sum(-1, keepdim=True)
+    att = att / torch.where(den > 0, den, torch.ones_like(den))
+    (torch.tensor(dm.astype(np.float64)) * (att @ torch.tensor(v.astype(np.float64)))).sum().backward()
+    want = lg.grad.numpy() * (adj != 0)
+    got = npy(ops.attention_score_grad(dev(att.detach().numpy().astype(np.float32), cuda), dev(adj, cuda), dev(dm, cuda),
+                                       dev(v, cuda)))
+    assert adj.sum() > 0 and np.all(got[adj == 0] == 0)
+    assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("S,N,He,prec", [(4, 32, 64, "f32"), (9, 64, 128, "f32"), (2, 256, 128, "f32"), (3, 12, 64, "f32"),
+                                         (4, 32, 128, "bf16"), (9, 64, 128, "bf16"), (2, 256, 128, "bf16"), (3, 12, 128, "bf16"),
+                                         (700, 16, 128, "bf16"), (300, 16, 128, "f32")])
+def test_edge_mlp_backward_matches_autograd(cuda, S, N, He, prec):
+    """mmt_edge_mlp_backward_f32 / _bf16 against fp64 autograd of sum(dlogit * score) over the edges: the edge-weight
+    gradients, and [d a | d b] through what the caller makes of it (g W1 = h^T dab, d h = dab [W1a | W1b]^T).
+    fp32: 1e-4 of the largest entry of each gradient; tcgen05 bf16: stated separately (2x the measured error)."""
+    import train_b as o_t
+    U = 128
+    p, adj, _, h, rng = _edge_case(S, N, He, seed=50 + N + He)
+    dlog = (rng.standard_normal((S, N, N)) * (adj != 0)).astype(np.float32)
+    keys = ("W1", "b1", "W2", "b2", "w_out", "b_out")
+    pt = {k: torch.tensor(np.asarray(p[k], np.float64), requires_grad=True) for k in keys}
+    ht = torch.tensor(h.astype(np.float64), requires_grad=True)
+    (torch.tensor(dlog.astype(np.float64)) * o_t.edge_scores(ht, pt)).sum().backward()
+    cp = ops.CellParams.from_numpy(p, cuda)
+    g = {k: torch.zeros_like(getattr(cp, k)) for k in keys}
+    g["b2"] += 1.0                                           # the call accumulates
+    dab = ops.edge_mlp_backward(dev(h, cuda), dev(adj, cuda), dev(dlog, cuda), cp, g,
+                                ops.PREC_F32 if prec == "f32" else ops.PREC_BF16)
+    g["b2"] -= 1.0
+    dab = npy(dab).astype(np.float64)
+    h2 = h.reshape(S * N, U).astype(np.float64)
+    gW1 = h2.T @ dab
+    got = {k: npy(g[k]).astype(np.float64) for k in keys if k != "W1"}
+    got["W1"] = np.concatenate([gW1[:, :He], gW1[:, He:]], 0)
+    got["h"] = (dab @ np.concatenate([p["W1"][:U], p["W1"][U:]], 1).astype(np.float64).T).reshape(S, N, U)
+    want = {k: pt[k].grad.numpy() for k in keys}
+    want["h"] = ht.grad.numpy()
+    assert adj.sum() > 0 and np.abs(want["W2"]).max() > 1e-6
+    for k in (*keys, "h"):
+        err = np.abs(got[k].reshape(want[k].shape) - want[k]).max() / max(np.abs(want[k]).max(), 1e-30)
+        within(err, 1e-4 if prec == "f32" else 2e-2, f"edge_mlp_backward_{prec}.{k}")
+
+
 # ------------------------------------------------------------------------------------------------
 def _cell_inputs(R, seed=0):
     rng = np.random.default_rng(seed)
@@ -650,24 +719,27 @@ def test_gsk_gates_from_preactivations_matches_oracle_and_fused_cell(cuda):
 
 
 @pytest.mark.gpu
-def test_train_gradients_relational_match_autograd_oracle(cuda):
+@pytest.mark.parametrize("gemm,He", [("fp32", 64), ("fp32", 128), ("tc", 128)])
+def test_train_gradients_relational_match_autograd_oracle(cuda, gemm, He):
     """g2k_lstm_mcr training step (BASELINE configs[1]): gradients through the attention softmax and the relational
-    edge MLP, fp32 kernels + library ops vs the fp64 autograd oracle."""
+    edge MLP vs the fp64 autograd oracle.  fp32: CUDA-core kernels (mmt_edge_mlp_f32 / _backward_f32); tc: every
+    contraction on the tensor cores (mmt_gemm_tf32, mmt_edge_mlp_bf16 / _backward_bf16), tolerance stated separately."""
     import train_b as o_t
     from multimodaltraj_2_b200.train import Trainer, TRAIN_KEYS, EDGE_KEYS
     S, N = 3, 16
     pos, vis, valid = synth.make_crowd(S, N, seed=6, half_extent=1.5, ragged=False)    # dense: many neighbours per agent
-    p = synth.init_params(seed=1, He=64)
+    p = synth.init_params(seed=1, He=He)
     want_loss, want = o_t.loss_and_grads(pos, vis, valid, p, relational=True)
-    tr = Trainer(ops.CellParams.from_numpy(p, cuda), relational=True)
+    tr = Trainer(ops.CellParams.from_numpy(p, cuda), relational=True, gemm=gemm)
     loss, g = tr.loss_and_grads(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
-    assert abs(float(loss) - want_loss) < 1e-4 * max(1.0, abs(want_loss))
+    tc = gemm == "tc"
+    assert abs(float(loss) - want_loss) < (2e-3 if tc else 1e-4) * max(1.0, abs(want_loss))
     for k in TRAIN_KEYS:
-        assert rel_err(npy(g[k]).astype(np.float64), want[k]) < 2e-3, k
+        within(rel_err(npy(g[k]).astype(np.float64), want[k]), 2e-2 if tc else 2e-3, f"train_relational_{gemm}.{k}")
     scale = max(np.abs(want[k]).max() for k in EDGE_KEYS)
     assert scale > 1e-6                                     # the scores matter in this crowd
     for k in EDGE_KEYS:                                     # relative to the largest edge-weight gradient entry
-        assert np.abs(npy(g[k]).astype(np.float64) - want[k]).max() < 5e-3 * scale, k
+        within(np.abs(npy(g[k]).astype(np.float64) - want[k]).max() / scale, 3e-2 if tc else 5e-3, f"train_relational_{gemm}.{k}")
     # one data-parallel step runs and moves the edge weights
     w0 = tr.p.W2.clone()
     tr.step(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
