@@ -184,7 +184,8 @@ def test_attention_score_grad_matches_autograd(cuda, S, N):
 def test_edge_mlp_backward_matches_autograd(cuda, S, N, He, prec):
     """mmt_edge_mlp_backward_f32 / _bf16 against fp64 autograd of sum(dlogit * score) over the edges: the edge-weight
     gradients, and [d a | d b] through what the caller makes of it (g W1 = h^T dab, d h = dab [W1a | W1b]^T).
-    fp32: 1e-4 of the largest entry of each gradient; tcgen05 bf16: stated separately (2x the measured error)."""
+    fp32: 1e-5 of the largest entry of each gradient; tcgen05 bf16: stated separately, 1.2e-2 = 2x the measured error
+    (profiles/r02_edge_bwd_measured_errors.json)."""
     import train_b as o_t
     U = 128
     p, adj, _, h, rng = _edge_case(S, N, He, seed=50 + N + He)
@@ -210,7 +211,7 @@ def test_edge_mlp_backward_matches_autograd(cuda, S, N, He, prec):
     assert adj.sum() > 0 and np.abs(want["W2"]).max() > 1e-6
     for k in (*keys, "h"):
         err = np.abs(got[k].reshape(want[k].shape) - want[k]).max() / max(np.abs(want[k]).max(), 1e-30)
-        within(err, 1e-4 if prec == "f32" else 2e-2, f"edge_mlp_backward_{prec}.{k}")
+        within(err, 1e-5 if prec == "f32" else 1.2e-2, f"edge_mlp_backward_{prec}.{k}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -735,11 +736,11 @@ def test_train_gradients_relational_match_autograd_oracle(cuda, gemm, He):
     tc = gemm == "tc"
     assert abs(float(loss) - want_loss) < (2e-3 if tc else 1e-4) * max(1.0, abs(want_loss))
     for k in TRAIN_KEYS:
-        within(rel_err(npy(g[k]).astype(np.float64), want[k]), 2e-2 if tc else 2e-3, f"train_relational_{gemm}.{k}")
+        within(rel_err(npy(g[k]).astype(np.float64), want[k]), 4e-3 if tc else 2e-3, f"train_relational_{gemm}.{k}")
     scale = max(np.abs(want[k]).max() for k in EDGE_KEYS)
     assert scale > 1e-6                                     # the scores matter in this crowd
     for k in EDGE_KEYS:                                     # relative to the largest edge-weight gradient entry
-        within(np.abs(npy(g[k]).astype(np.float64) - want[k]).max() / scale, 3e-2 if tc else 5e-3, f"train_relational_{gemm}.{k}")
+        within(np.abs(npy(g[k]).astype(np.float64) - want[k]).max() / scale, 8e-3 if tc else 5e-3, f"train_relational_{gemm}.{k}")
     # one data-parallel step runs and moves the edge weights
     w0 = tr.p.W2.clone()
     tr.step(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda))
