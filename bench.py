@@ -775,7 +775,8 @@ def run_train(args, rank, world, local_rank):
     pos, vis, valid = (torch.from_numpy(a).to(dev) for a in (pos_h, vis_h, valid_h))
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
     relational = getattr(args, "variant", "mc") == "mcr"
-    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational)   # lr 0.005 (argParser.py:40) diverges on this synthetic set
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational,
+                 graph=args.train_graph)   # lr 0.005 (argParser.py:40) diverges on this synthetic set
 
     def barrier():
         if world > 1:
@@ -817,6 +818,7 @@ def run_train(args, rank, world, local_rank):
                                      "backward_gemm": args.train_gemm, "lr": 1e-3,
                                      "gradient_bucket_bytes": int(w.numel() * 4), "collective": "one NCCL all-reduce (SUM) per step" if world > 1 else "none (1 GPU)"},
                           "loss_first": losses[0], "loss_last": float(loss), "weights_identical_across_ranks": in_sync,
+                          "cuda_graph": bool(args.train_graph),
                           "gpu_launches": int(ops.launch_count() - l0)})
     if world > 1:
         dist.destroy_process_group()
@@ -839,6 +841,8 @@ def main():
                     help="c3 (default): synthetic crowds, the headline; c1 / c5: real-data evaluation on data/; c2: g2k_lstm_mcr "
                          "training steps on the real zara1 leave-one-out tables (extras)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: data-parallel training steps (extra)")
+    ap.add_argument("--train-graph", action="store_true",
+                    help="--mode train: replay forward + BPTT of the shard as one CUDA graph (all-reduce / RMSProp outside it)")
     ap.add_argument("--train-gemm", default="fp32", choices=["fp32", "tf32", "tc"],
                     help="--mode train: contractions of the step: fp32 / tf32 library GEMMs, tc = mmt_gemm_tf32 (TMA + tcgen05) and mmt_aggregate_transpose_f32")
     args = ap.parse_args()

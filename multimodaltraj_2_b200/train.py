@@ -252,7 +252,7 @@ class Trainer:
     """
 
     def __init__(self, params: ops.CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, lam=0.0005, lr=0.005, decay=0.95,
-                 clip=10.0, gemm="fp32", relational=False):
+                 clip=10.0, gemm="fp32", relational=False, graph=False):
         # gemm: arithmetic of the library contractions of the backward pass (A^T dz, dz W^T, att^T d mh, head):
         #   "fp32" CUDA-core SGEMM (parity mode: gradients within 2e-3 of the fp64 autograd oracle),
         #   "tf32" tensor cores, operands rounded to 10 mantissa bits, fp32 accumulation (stated separately: 2e-2); the
@@ -273,6 +273,10 @@ class Trainer:
         self.relational = bool(relational)
         if self.relational and params.W1 is None:
             raise ValueError("relational training needs the edge-MLP weights (W1 .. b_out)")
+        # graph: step() replays the forward + BPTT of one shard (~1000 launches, no host synchronisation, fixed shapes) as ONE
+        # CUDA graph, captured on the first step of each input shape; all-reduce, clipping and RMSProp stay outside it.
+        self.graph = bool(graph)
+        self._captured = None                                          # (key, CUDAGraph, static inputs, static outputs)
         self.keys = TRAIN_KEYS + (EDGE_KEYS if self.relational else ())
         self.p, self.T, self.P, self.r2, self.inv = params, T, P, r2, inv_2sigma2
         self.lam, self.lr, self.decay, self.clip = lam, lr, decay, clip
@@ -442,9 +446,36 @@ class Trainer:
         g["W"] = g["W"] + self.lam * self.p.W
         return loss_sum[0] / n + 0.5 * self.lam * (self.p.W * self.p.W).sum(), g
 
+    def _replay(self, pos, vis, valid):
+        """loss_and_grad_sums through a CUDA graph (captured once per input shape; the weights are updated in place, so a
+        replay reads the current ones).  The outputs are the graph's own buffers: consumed before the next replay."""
+        key = (tuple(pos.shape), tuple(vis.shape), tuple(valid.shape), pos.device)
+        if self._captured is None or self._captured[0] != key:
+            static = tuple(t.clone() for t in (pos, vis, valid))
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                              # warm-up off the capture: opt-ins, library handles
+                self.loss_and_grad_sums(*static)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                out = self.loss_and_grad_sums(*static)
+            self.graph_launches = ops.launch_count() - n0              # this library's kernels inside one replay
+            self._captured = (key, cg, static, out)
+        _, cg, static, out = self._captured
+        for dst, src in zip(static, (pos, vis, valid)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+        cg.replay()
+        ops._graph_launches += self.graph_launches                    # replayed launches, for ops.launch_count()
+        return out
+
     def step(self, pos, vis, valid):
         """One data-parallel training step on this rank's scene shard; returns the global mean loss."""
-        loss_sum, n, g = self.loss_and_grad_sums(pos, vis, valid)
+        loss_sum, n, g = self._replay(pos, vis, valid) if self.graph else self.loss_and_grad_sums(pos, vis, valid)
         flat = flatten_bucket(g)
         counts = torch.stack([loss_sum[0], n])
         allreduce_mean_(flat, counts)                                  # ONE all-reduce of the < 1 MB bucket (+ 2 floats)

@@ -634,6 +634,31 @@ def test_train_step_rmsprop_and_loss_decrease(cuda):
     assert losses[-1] < losses[0] - 0.05, losses
 
 
+@pytest.mark.parametrize("gemm,relational", [("fp32", False), ("tc", False), ("tc", True)])
+def test_train_step_cuda_graph_equals_eager(cuda, gemm, relational):
+    """Trainer(graph=True): forward + BPTT replayed as one CUDA graph.  Same launches in the same order, so after three
+    steps (the weights change in place between replays) the losses match the eager trainer; the weights match to the
+    reordering of the atomic accumulations of the split-K weight-gradient GEMMs / edge scatter (fp32 mode: exactly)."""
+    from multimodaltraj_2_b200.train import Trainer
+    S, N = 6, 16
+    pos, vis, valid = synth.make_crowd(S, N, seed=12, half_extent=2.0, ragged=True)
+    d = [dev(a, cuda) for a in (pos, vis, valid)]
+    out = []
+    for graph in (False, True):
+        cp = ops.CellParams.from_numpy(synth.init_params(seed=2), cuda)
+        tr = Trainer(cp, gemm=gemm, relational=relational, graph=graph, lr=1e-3)
+        n0 = ops.launch_count()
+        losses = [float(tr.step(*d)) for _ in range(3)]
+        out.append((losses, cp.W.clone(), ops.launch_count() - n0))
+    (l_e, w_e, n_e), (l_g, w_g, n_g) = out
+    assert n_g >= n_e > 0                                    # replayed launches are counted (+ the capture's warm-up)
+    if gemm == "fp32" and not relational:
+        assert l_e == l_g and torch.equal(w_e, w_g)
+    else:
+        assert np.allclose(l_e, l_g, rtol=0, atol=2e-4), (l_e, l_g)
+        assert (w_e - w_g).abs().max().item() < 2e-4
+
+
 # ------------------------------------------------------------------------------------------------
 # SURVEY 8f rank 3: static-context branch (train.py:93-110,154-158)
 @pytest.mark.gpu
