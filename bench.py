@@ -311,6 +311,7 @@ def run_ours(args, rank, world, local_rank):
     PRECS = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}
     if hasattr(ops, "PREC_BF16X3"):
         PRECS["bf16x3"] = ops.PREC_BF16X3
+    PRECS["f16"] = ops.PREC_F16
     prec = PRECS[args.prec]
     relational = args.variant == "mcr"
     pos_h, vis_h, valid_h = synth.make_crowd(S, N, seed=synth.SEED + rank)
@@ -374,8 +375,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- the other precision modes of the same workload, a few steps each, in the same line ("modes"):
     # f32 = the parity mode of the north_star tolerance (CUDA-core FMA); bf16x3 = split-bf16 tensor-core mode
     modes = {args.prec: {"value": value, "ms_per_step": ms_step}}
-    if args.modes and not relational and args.prec == "bf16":
-        for name in [m for m in ("bf16x3", "f32") if m in PRECS]:
+    if args.modes and not relational and args.prec in ("bf16", "f16"):
+        for name in [m for m in ("f16", "bf16", "bf16x3", "f32") if m in PRECS and m != args.prec]:
             stage(f"mode {name}")
             fm = ops.Forecaster(params, S, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, prec=PRECS[name], seed=0xB200,
                                 agent_offset=rank * S * N, device=dev, use_graph=not args.no_graph)
@@ -450,7 +451,8 @@ def run_ours(args, rank, world, local_rank):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
     nsteps = T_OBS + P_PRED - 1
-    fused = prec == ops.PREC_BF16 and args.variant == "mc" and 128 % N == 0 and N >= 8
+    fused = prec in (ops.PREC_BF16, ops.PREC_F16) and args.variant == "mc" and 128 % N == 0 and N >= 8
+    f16 = prec == ops.PREC_F16
     prof = {}
     for name in ("r02_traffic.json", "r01_traffic.json"):
         pf = ROOT / "profiles" / name
@@ -463,19 +465,19 @@ def run_ours(args, rank, world, local_rank):
         # of h and c over the scene 2*N*2U.
         par_out = torch.empty((S, N, P_PRED, 5), device=dev)
         for _ in range(3):
-            ops.rollout_bf16(pos, vis, valid, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out)
+            ops.rollout_bf16(pos, vis, valid, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out, f16=f16)
         torch.cuda.synchronize()
         k0.record()
         for i in range(reps):
             p_, v_, m_ = sets[i % NSETS]
-            ops.rollout_bf16(p_, v_, m_, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out)
+            ops.rollout_bf16(p_, v_, m_, params, T_OBS, P_PRED, R2, INV_2SIGMA2, out=par_out, f16=f16)
         k1.record()
         torch.cuda.synchronize()
         ro_ms = k0.elapsed_time(k1) / reps
         flops = float(R) * nsteps * (2.0 * (EMBED + 2 * HIDDEN) * 3 * HIDDEN + 2.0 * N * 2 * HIDDEN)
         achieved = flops / (ro_ms * 1e-3) / 1e12
         peak = pk["bf16"]
-        roof = {"kernel": "rollout_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roof = {"kernel": "rollout_tc_kernel" + ("<f16 operands>" if f16 else ""), "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": prof.get("rollout_tc_kernel_dram_bytes_per_launch"),
                 "peak_source": f"{pk['src']} (burst bf16 cuBLAS: kernel timed alone); sustained peak {pk['bf16_sustained']}",
                 "frac_of_sustained": achieved / pk["bf16_sustained"], "ms_per_launch": ro_ms,
@@ -579,7 +581,8 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": value, "unit": "agent-trajectories/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if prec == ops.PREC_F32 else "bf16", "data": "synthetic", "config": config(args, S),
+                "dtype": {"f32": "f32", "f16": "f16 (tensor-core operands; fp32 accumulation and state)"}.get(args.prec, "bf16"),
+                "data": "synthetic", "config": config(args, S),
                 "modes": modes,
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "agent-trajectories/s", "h2d_bytes_per_step": h2d,
@@ -619,7 +622,8 @@ def run_config(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     from multimodaltraj_2_b200 import ops, realdata, synth
     a = types.SimpleNamespace(batch_size=16, seq_length=12, pred_len=P_PRED, obs_len=T_OBS, K=K_SAMPLES, data_root=None)
-    prec = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE}[args.prec]
+    prec = {"bf16": ops.PREC_BF16, "f32": ops.PREC_F32, "bf16-stepwise": ops.PREC_BF16_STEPWISE, "f16": ops.PREC_F16,
+            "bf16x3": ops.PREC_BF16X3}[args.prec]
     relational = args.variant == "mcr"
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
     splits = [1] if args.config == "c1" else [0, 1, 2, 3, 4]
@@ -675,7 +679,7 @@ def run_config(args, rank, world, local_rank):
         emit({"metric": "agent-trajectories/sec (obs8->pred12, K=20)", "value": total_agents / (total_ms * 1e-3),
               "unit": "agent-trajectories/s", "n_gpus": world, "steps": 3, "warmup": 1, "ms_per_step": total_ms,
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-              "dtype": "f32" if prec == ops.PREC_F32 else "bf16", "data": "ETH/UCY tables under data/ (real), seed-0 random-init weights",
+              "dtype": {"f32": "f32", "f16": "f16"}.get(args.prec, "bf16"), "data": "ETH/UCY tables under data/ (real), seed-0 random-init weights",
               "config": {"workload": {"c1": "C1: g2k_lstm forward + best-of-20 ADE/FDE on the ETH-univ split",
                                       "c5": "C5: best-of-20 ADE/FDE over all five ETH/UCY splits, scene-sharded"}[args.config],
                          "variant": f"g2k_lstm_{args.variant}", "precision_mode": args.prec,
@@ -830,7 +834,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", default="bf16", choices=["bf16", "f32", "bf16-stepwise", "bf16x3"])
+    ap.add_argument("--prec", default="bf16", choices=["bf16", "f16", "f32", "bf16-stepwise", "bf16x3"])
     ap.add_argument("--variant", default=None, choices=["mc", "mcr"], help="default: mc (mcr for --config c2)")
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)

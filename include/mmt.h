@@ -41,6 +41,10 @@ extern "C" {
                              (a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 accumulate in TMEM: 16 operand mantissa bits),
                              tanhf / expf in the epilogue -- the north_star's 1e-4 / 1e-3 tolerance on tcgen05      */
 
+#define MMT_PREC_F16 4 /* the fused rollout of MMT_PREC_BF16 with fp16 operands (10 stored mantissa bits instead of 7; fp32
+                          accumulate in TMEM): same kernel and speed, ADE / FDE inside the 1e-3 bar that bf16 misses.
+                          g2k_lstm_mc, N in {8,16,32,64,128}; operands must stay inside the fp16 range (|x| < 65504)  */
+
 int mmt_version(void);
 const char* mmt_last_error(void);
 /* SM count of the current device (grids are sized from it; queried once per device). */
@@ -154,6 +158,7 @@ typedef struct mmt_cell_weights {
   int E;
   int U;
   const void* W_packed_bf16x3; /* split-bf16 image [W_hi ; W_hi ; W_lo] (mmt_pack_gate_weights_bf16x3) or NULL */
+  const void* W_packed_f16;    /* the W_packed_bf16 image with fp16 entries (mmt_pack_gate_weights_f16) or NULL */
 } mmt_cell_weights;
 
 int mmt_gsk_cell(const float* x, const float* h, const float* c, const float* mh, const float* mc,
@@ -167,6 +172,8 @@ size_t mmt_gate_weights_packed_bytes(int E, int U);
 size_t mmt_gate_weights_packed_x3_bytes(int E, int U);
 int mmt_pack_gate_weights_bf16x3(const float* W, int E, int U, void* packed, void* stream);
 int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* packed, void* stream);
+/* fp16 entries instead of bf16 (MMT_PREC_F16); mmt_gate_weights_packed_bytes bytes */
+int mmt_pack_gate_weights_f16(const float* W, int E, int U, void* packed, void* stream);
 
 /* ---- GridLSTMCell exactly as helper.py:31-39 / :131-139 instantiate it -------
  * inputs[B, in_stride] (first 4F columns used), state[B, st_stride] (first 2UF used),
@@ -308,6 +315,12 @@ int mmt_forecast_f32(const float* pos, const float* vis, const uint8_t* valid,
 int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
                      int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
                      int64_t* timeline, void* stream);
+/* The same kernel with fp16 instead of bf16 operands (MMT_PREC_F16; cw->W_packed_f16): 10 stored mantissa bits in the
+ * gate-GEMM operands, the state images and the attention numerators, fp32 accumulation; same speed, and inside the
+ * 1e-3 bar on ADE / FDE that bf16 misses (measured: profiles/, bench.py modes{}).  Values must stay below 65504. */
+int mmt_rollout_f16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
+                    int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
+                    int64_t* timeline, void* stream);
 
 /* Forward gate update from pre-activations z[R,3U] = [e|h|mh] W + b (columns i | j | o) computed by a library GEMM:
  * the gate equations of helper.py:31-39 -> h'[R,U], c'[R,U], m_f[R,U]; invalid rows give zeros.  Used by

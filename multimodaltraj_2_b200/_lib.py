@@ -20,7 +20,7 @@ vp = C.c_void_p
 class CellWeights(C.Structure):
     _fields_ = [("W_e", vp), ("b_e", vp), ("W", vp), ("b", vp), ("w_If", vp), ("w_It", vp), ("w_Of", vp),
                 ("w_Ot", vp), ("W_h", vp), ("b_h", vp), ("W_packed_bf16", vp), ("E", C.c_int), ("U", C.c_int),
-                ("W_packed_bf16x3", vp)]
+                ("W_packed_bf16x3", vp), ("W_packed_f16", vp)]
 
 
 class McrWeights(C.Structure):
@@ -67,6 +67,7 @@ SIGNATURES = {
     "mmt_pack_gate_weights_bf16": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "mmt_gate_weights_packed_x3_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mmt_pack_gate_weights_bf16x3": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    "mmt_pack_gate_weights_f16": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "mmt_gridlstm_step_f32": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                         C.c_int, vp, vp, vp]),
     "mmt_mcr_step_f32": (C.c_int, [vp, vp, vp, vp, vp, C.POINTER(McrWeights), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -100,6 +101,8 @@ SIGNATURES = {
     "mmt_allreduce_max_f32": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "mmt_workspace_bytes": (C.c_int, [C.c_int, C.POINTER(Shape), C.POINTER(C.c_size_t)]),
     "mmt_rollout_bf16": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_float, vp, vp, vp]),
+    "mmt_rollout_f16": (C.c_int, [vp, vp, vp, C.POINTER(CellWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_float, vp, vp, vp]),
 }
 

@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) g
 
 // W[E+2U, 3U] fp32 row-major -> bf16 operand image [pass][k-chunk][96 rows][64 k], SWIZZLE_128B.
 // Row n = g*32 + ul of a pass holds gate column g*U + pass*32 + ul.
+template <bool F16>
 __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TC_K * 3 * TC_U) return;
@@ -655,7 +656,9 @@ __global__ void pack_gate_weights_kernel(const float* __restrict__ W, uint8_t* _
   const int kc = k / TC_KC, kk = k - kc * TC_KC;
   const size_t off = (size_t)(p * TC_NKC + kc) * TC_STAGE_BYTES + sw128_off(n, kk);
   // gates i (g == 0) and o (g == 2) go through sigmoid(z) = 0.5 tanh(z/2) + 0.5: fold the 1/2 (exact in bf16)
-  *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(g == 1 ? W[idx] : 0.5f * W[idx]);
+  const float w = g == 1 ? W[idx] : 0.5f * W[idx];
+  if constexpr (F16) *reinterpret_cast<__half*>(out + off) = __float2half_rn(w);
+  else *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(w);
 }
 
 // split-bf16 image: [pass][10 chunks][96 rows][64 k]: chunks 0-4 hold W_hi (against A_hi and A_lo), 5-9 W_lo (against A_hi)
@@ -752,7 +755,19 @@ extern "C" int mmt_pack_gate_weights_bf16(const float* W, int E, int U, void* pa
   MMT_REQUIRE(E == TC_E && U == TC_U, "packing is built for E = 64, U = 128");
   MMT_ALIGNED(packed);
   const int n = TC_K * 3 * TC_U;
-  pack_gate_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
+  pack_gate_weights_kernel<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
+  count_launch();
+  return check_launch("pack_gate_weights_kernel");
+}
+
+// the same image with fp16 entries (MMT_PREC_F16: fused rollout with fp16 operands); same size
+extern "C" int mmt_pack_gate_weights_f16(const float* W, int E, int U, void* packed, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(W && packed, "W/packed must not be NULL");
+  MMT_REQUIRE(E == TC_E && U == TC_U, "packing is built for E = 64, U = 128");
+  MMT_ALIGNED(packed);
+  const int n = TC_K * 3 * TC_U;
+  pack_gate_weights_kernel<true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, reinterpret_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_gate_weights_kernel");
 }

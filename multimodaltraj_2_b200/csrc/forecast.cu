@@ -35,7 +35,7 @@ int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void*
                        int N, float* score, float* nab, int zero_fill, cudaStream_t stream);
 int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream);
 int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
-                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, cudaStream_t stream);
+                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, int f16, cudaStream_t stream);
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
                                    float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
 int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
@@ -95,7 +95,13 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
   w.blocked = w.fast && tileable;
-  if (w.fast) {
+  if (cfg->prec == MMT_PREC_F16) {
+    // fused rollout only: the state never leaves the chip, no per-step buffers
+    for (int i = 0; i < 2; ++i) { w.hb[i] = nullptr; w.cf[i] = nullptr; w.hc[i] = nullptr; }
+    w.mhb = w.mcb = nullptr;
+    w.mhc = w.mf = w.kern = nullptr;
+    w.adj = nullptr;
+  } else if (w.fast) {
     const size_t Rp = (R + 127) / 128 * 128;   // state rows padded to whole 128-row tiles
     for (int i = 0; i < 2; ++i) {
       w.hb[i] = take(Rp * U * 2);
@@ -140,9 +146,12 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   MMT_REQUIRE(cw->W_h && cw->b_h, "head weights required");
   MMT_REQUIRE(!cfg->relational || (ew && ew->He > 0), "relational mode needs edge weights");
   MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE ||
-                  cfg->prec == MMT_PREC_BF16X3,
+                  cfg->prec == MMT_PREC_BF16X3 || cfg->prec == MMT_PREC_F16,
               "unknown precision mode");
-  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16X3 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
+  const bool f16 = cfg->prec == MMT_PREC_F16;
+  MMT_REQUIRE(!f16 || (cw->W_packed_f16 && !cfg->relational && cfg->N >= 8 && cfg->N <= 128 && 128 % cfg->N == 0),
+              "MMT_PREC_F16 is the fused rollout with fp16 operands: needs W_packed_f16, g2k_lstm_mc, N in {8,16,32,64,128}");
+  MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16X3 || f16 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
   MMT_REQUIRE(cfg->prec != MMT_PREC_BF16X3 || cw->W_packed_bf16x3, "bf16x3 mode needs W_packed_bf16x3");
   MMT_ALIGNED(pos);
   MMT_ALIGNED(vis);
@@ -162,9 +171,9 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
 
   // bf16, non-relational, whole scenes per 128-row tile: the entire recurrence is one persistent kernel with the
   // state on chip (rollout_tc.cu).  MMT_PREC_BF16_STEPWISE keeps the per-step kernels (A/B checks, other N).
-  const bool fused = w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16 && !cfg->relational;
+  const bool fused = f16 || (w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16 && !cfg->relational);
   if (fused) {
-    if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, stream)))
+    if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, f16, stream)))
       return rc0;
   } else if (w.fast) {
     const size_t Rp = ((size_t)R + 127) / 128 * 128;
@@ -282,5 +291,22 @@ extern "C" int mmt_rollout_bf16(const float* pos, const float* vis, const uint8_
   MMT_ALIGNED(params);
   if (S == 0) return MMT_OK;
   return launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, r2, inv_2sigma2, params,
-                           reinterpret_cast<long long*>(timeline), (cudaStream_t)stream);
+                           reinterpret_cast<long long*>(timeline), 0, (cudaStream_t)stream);
+}
+
+extern "C" int mmt_rollout_f16(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* cw,
+                               int S, int N, int T, int P, float r2, float inv_2sigma2, float* params,
+                               int64_t* timeline, void* stream) {
+  using namespace mmt;
+  MMT_REQUIRE(S >= 0 && N >= 8 && N <= 128 && 128 % N == 0, "fused rollout needs N in {8,16,32,64,128}");
+  MMT_REQUIRE(T >= 1 && P >= 1, "need T >= 1, P >= 1");
+  if (S == 0) return MMT_OK;
+  MMT_REQUIRE(pos && vis && valid && cw && params, "pos/vis/valid/weights/params required");
+  MMT_REQUIRE(cw->U == 128 && cw->E == 64 && cw->W_h && cw->b_h && cw->W_packed_f16,
+              "needs U = 128, E = 64, head weights and W_packed_f16");
+  MMT_ALIGNED(pos);
+  MMT_ALIGNED(vis);
+  MMT_ALIGNED(params);
+  return launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, r2, inv_2sigma2, params,
+                           reinterpret_cast<long long*>(timeline), 1, (cudaStream_t)stream);
 }

@@ -80,9 +80,11 @@ constexpr uint32_t RT_MH = 256;       // mh accumulator (fp32, 128 columns): ali
 constexpr uint32_t RT_MC = 384;       // mc accumulator (fp32, 128 columns)
 constexpr uint32_t RT_HEAD = 352;     // 4 column slices x 8: head partial sums of a row, exchanged through TMEM
                                       // (the 32 columns of the mh accumulator beyond accumulator 1: free after the conversion)
-constexpr uint32_t kIdescGate = make_idesc_bf16(128, RO_N);
-constexpr uint32_t kIdescAggMN = make_idesc_bf16(128, 128) | (1u << 16);   // B operand MN-major
-constexpr uint32_t kIdescAgg256 = make_idesc_bf16(128, 256) | (1u << 16);  // [h | c] in one MMA
+// F16 = the operand format of every MMA of the kernel: bf16 (MMT_PREC_BF16) or fp16 (MMT_PREC_F16: three more mantissa
+// bits in the A operand, the state images, the attention numerators and the packed weights; same instructions, same speed)
+template <bool F16> constexpr uint32_t kIdescGate = make_idesc_op<F16>(128, RO_N);
+template <bool F16> constexpr uint32_t kIdescAggMN = make_idesc_op<F16>(128, 128) | (1u << 16);   // B operand MN-major
+template <bool F16> constexpr uint32_t kIdescAgg256 = make_idesc_op<F16>(128, 256) | (1u << 16);  // [h | c] in one MMA
 
 struct RoArgs {
   const float* pos;      // [R, F, 2]
@@ -156,7 +158,7 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" 
 
 // DIAG = true compiles the timeline stamps and the timing-experiment flags in (scratch/ro_timeline.py); the production
 // instantiation carries none of it: a few extra instructions per chunk in the MMA-issuing warps cost 2.5 % of the kernel.
-template <bool DIAG>
+template <bool DIAG, bool F16>
 __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
   // 1024-byte alignment (SWIZZLE_128B atoms) requested from the toolchain instead of fixed up at run time: the base is
   // then a link-time constant and every barrier address / UMMA descriptor derived from it is uniform
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             const uint32_t acol = tmem_u + RT_A + (uint32_t)ro_perm(kcn) * 32u;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16_ts_elect(d_tmem, acol + ks * 8, db + (uint64_t)(ks * 2), kIdescGate, (kcn | ks) ? 1u : 0u);
+              umma_bf16_ts_elect(d_tmem, acol + ks * 8, db + (uint64_t)(ks * 2), kIdescGate<F16>, (kcn | ks) ? 1u : 0u);
             if (!(DIAG && (a.flags & 1)) || (a.flags & 256)) umma_commit_elect(W_EMPTY + 8 * s);
           };
           auto gate_pass = [&](auto p_tag) {   // passes 1-3: all five chunks back to back
@@ -341,19 +343,19 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16_elect(tmem_u + RT_MH, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_h + (uint64_t)(ks * 128),
-                        kIdescAgg256, ks ? 1u : 0u);
+                        kIdescAgg256<F16>, ks ? 1u : 0u);
             umma_commit_elect(AGG_FULL);
 #else
             // ---- aggregation: mh = att x h (committed first: its conversion is on the critical path), mc = att x c
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16_elect(tmem_u + RT_MH, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_h + (uint64_t)(ks * 128),
-                        kIdescAggMN, ks ? 1u : 0u);
+                        kIdescAggMN<F16>, ks ? 1u : 0u);
             umma_commit_elect(AGG_FULL);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
               umma_bf16_elect(tmem_u + RT_MC, (ks < 4 ? d_att0 : d_att1) + (uint64_t)((ks & 3) * 2), d_c + (uint64_t)(ks * 128),
-                        kIdescAggMN, ks ? 1u : 0u);
+                        kIdescAggMN<F16>, ks ? 1u : 0u);
 #endif
             if (DIAG && dbg) dbg[1] = clock64();
             mbar_wait_warp(E_READY, par, trap, RT_E_READY);
@@ -484,11 +486,18 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                 const float2 kern = make_float2(ex2_fast(ka.x), ex2_fast(ka.y));   // exp(-d2 / 2 sigma^2)
                 // exp(kern), kern in (0, 1]: cubic on the FMA pipe (max relative error 3.2e-4, below the bf16 rounding
                 // of the operand) instead of a second MUFU per pair
-                const float2 ek = ffma2(ffma2(ffma2(make_float2(0.27136664f, 0.27136664f), kern, make_float2(0.43417813f, 0.43417813f)),
-                                              kern, make_float2(1.01218117f, 1.01218117f)), kern, make_float2(0.99967653f, 0.99967653f));
+                // (fp16 operands round at 4.9e-4: there a quartic, 1.6e-5)
+                float2 ek;
+                if constexpr (F16)
+                  ek = ffma2(ffma2(ffma2(ffma2(make_float2(0.0679839998f, 0.0679839998f), kern, make_float2(0.143049359f, 0.143049359f)),
+                                         kern, make_float2(0.50812006f, 0.50812006f)), kern, make_float2(0.99906832f, 0.99906832f)),
+                             kern, make_float2(1.00001609f, 1.00001609f));
+                else
+                  ek = ffma2(ffma2(ffma2(make_float2(0.27136664f, 0.27136664f), kern, make_float2(0.43417813f, 0.43417813f)),
+                                   kern, make_float2(1.01218117f, 1.01218117f)), kern, make_float2(0.99967653f, 0.99967653f));
                 const float e0 = (v && d2.x < a.r2) ? ek.x : 0.f;                 // softmax numerator
                 const float e1 = (v && d2.y < a.r2) ? ek.y : 0.f;
-                pk[hq * 2 + pr] = pack_bf16x2(e0, e1);
+                pk[hq * 2 + pr] = pack_op2<F16>(e0, e1);
               }
             }
             if (j8 == jdiag8) {
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
               for (int w = 0; w < 4; ++w) pk[w] &= (w == dw) ? dm : 0xFFFFFFFFu;
             }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) sum += bf16_lo(pk[w]) + bf16_hi(pk[w]);   // normalise by what the MMA really sums
+            for (int w = 0; w < 4; ++w) sum += op_lo<F16>(pk[w]) + op_hi<F16>(pk[w]);   // normalise by what the MMA really sums
             const int jt = sb + j8;
             *reinterpret_cast<uint4*>(smem + RS_ATT + (jt >> 6) * RO_BLK + sw128_off(r, jt & 63)) =
                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -534,8 +543,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
             e1 = rok ? fmaxf(e1, 0.f) : 0.f;
             e2 = rok ? fmaxf(e2, 0.f) : 0.f;
             e3 = rok ? fmaxf(e3, 0.f) : 0.f;
-            pe[hq * 2] = pack_bf16x2(e0, e1);
-            pe[hq * 2 + 1] = pack_bf16x2(e2, e3);
+            pe[hq * 2] = pack_op2<F16>(e0, e1);
+            pe[hq * 2 + 1] = pack_op2<F16>(e2, e3);
           }
         }
         tmem_st8(t_row + RT_A + cs * 8, pe);
@@ -556,8 +565,8 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            pk[i] = pack_bf16x2(v0[2 * i] * inv, v0[2 * i + 1] * inv);
-            pk[4 + i] = pack_bf16x2(v1[2 * i] * inv, v1[2 * i + 1] * inv);
+            pk[i] = pack_op2<F16>(v0[2 * i] * inv, v0[2 * i + 1] * inv);
+            pk[4 + i] = pack_op2<F16>(v1[2 * i] * inv, v1[2 * i + 1] * inv);
           }
           tmem_st8(t_row + RT_A_MH + cs * 16 + ch * 4, pk);
         }
@@ -653,10 +662,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
                   }
                 }
               }
-              hw[hq * 2] = pack_bf16x2(ho[0], ho[1]);
-              hw[hq * 2 + 1] = pack_bf16x2(ho[2], ho[3]);
-              cw[hq * 2] = pack_bf16x2(c4.x, c4.y);
-              cw[hq * 2 + 1] = pack_bf16x2(c4.z, c4.w);
+              hw[hq * 2] = pack_op2<F16>(ho[0], ho[1]);
+              hw[hq * 2 + 1] = pack_op2<F16>(ho[2], ho[3]);
+              cw[hq * 2] = pack_op2<F16>(c4.x, c4.y);
+              cw[hq * 2 + 1] = pack_op2<F16>(c4.z, c4.w);
             }
             {
               // c', h' (bf16) -> shared-memory B operands of the next step's aggregation (its MMAs of this step are
@@ -734,11 +743,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_tc_kernel(RoArgs a) {
 
 // pos[R,F,2], vis[R,T,2], valid[R] -> params[R,P,5].  Requires 128 % N == 0, N >= 8, U = 128, E = 64.
 int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
-                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, cudaStream_t stream) {
+                      int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, int f16, cudaStream_t stream) {
   RoArgs a = {};
   a.pos = pos; a.vis = vis; a.valid = valid;
   a.W_e = w->W_e; a.b_e = w->b_e; a.b = w->b; a.w_If = w->w_If; a.w_It = w->w_It; a.w_Of = w->w_Of; a.w_Ot = w->w_Ot;
-  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
+  a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(f16 ? w->W_packed_f16 : w->W_packed_bf16);
   a.params = params;
   a.R = S * N; a.N = N; a.T = T; a.P = P; a.F = T + P;
   a.num_tiles = (a.R + 127) / 128;
@@ -748,16 +757,22 @@ int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, 
   // diagnostic switches of scratch/ro_*.py (timing experiments, fault injection): read once per process
   static std::atomic<int> env_flags{INT_MIN}, env_grid{INT_MIN};
   a.flags = env_int_once("MMT_RO_FLAGS", &env_flags);
-  static DeviceMask smem_opted[2];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<false>), RS_TOTAL + 1024, &smem_opted[0])) return rc;
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<true>), RS_TOTAL + 1024, &smem_opted[1])) return rc;
+  static DeviceMask smem_opted[4];   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<false, false>), RS_TOTAL + 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<true, false>), RS_TOTAL + 1024, &smem_opted[1])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<false, true>), RS_TOTAL + 1024, &smem_opted[2])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&rollout_tc_kernel<true, true>), RS_TOTAL + 1024, &smem_opted[3])) return rc;
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
   const int dgrid = env_int_once("MMT_RO_GRID", &env_grid);
   if (dgrid > 0 && dgrid < grid) grid = dgrid;
-  if (a.dbg || a.flags)
-    rollout_tc_kernel<true><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
-  else
-    rollout_tc_kernel<false><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  const bool diag = a.dbg || a.flags;
+  if (f16) {
+    if (diag) rollout_tc_kernel<true, true><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+    else rollout_tc_kernel<false, true><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  } else {
+    if (diag) rollout_tc_kernel<true, false><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+    else rollout_tc_kernel<false, false><<<grid, RO_THREADS, RS_TOTAL + 1024, stream>>>(a);
+  }
   count_launch();
   return check_launch("rollout_tc_kernel");
 }

@@ -1,6 +1,7 @@
 // PTX wrappers shared by the tcgen05 kernels (sm_100a): mbarrier, bulk copy, TMEM, UMMA descriptors.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace mmt {
@@ -214,6 +215,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// fp16 operands (MMT_PREC_F16: the same kernels with 10 instead of 7 stored mantissa bits; kind::f16 takes either format)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float f16_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float f16_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+// instruction descriptor with A = B = f16 (format code 0), D = f32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc_op(int M, int N) {
+  return F16 ? make_idesc_f16(M, N) : make_idesc_bf16(M, N);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi); else return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float op_lo(uint32_t w) {
+  if constexpr (F16) return f16_lo(w); else return bf16_lo(w);
+}
+template <bool F16>
+__device__ __forceinline__ float op_hi(uint32_t w) {
+  if constexpr (F16) return f16_hi(w); else return bf16_hi(w);
+}
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-PREC_F32, PREC_BF16, PREC_BF16_STEPWISE, PREC_BF16X3 = 0, 1, 2, 3
+PREC_F32, PREC_BF16, PREC_BF16_STEPWISE, PREC_BF16X3, PREC_F16 = 0, 1, 2, 3, 4
 
 
 def _p(t):
@@ -173,6 +173,7 @@ class CellParams:
     w_out: torch.Tensor = None; b_out: torch.Tensor = None
     W_packed: torch.Tensor = field(default=None, repr=False)
     W_packed_x3: torch.Tensor = field(default=None, repr=False)
+    W_packed_f16: torch.Tensor = field(default=None, repr=False)
 
     @property
     def E(self):
@@ -206,12 +207,26 @@ class CellParams:
                    "mmt_pack_gate_weights_bf16x3")
         return self
 
+    def pack_f16(self):
+        """fp16 operand image of W for PREC_F16 (mmt_pack_gate_weights_f16; same layout and size as the bf16 one)."""
+        lib = _lib.load()
+        nbytes = lib.mmt_gate_weights_packed_bytes(self.E, self.U)
+        if nbytes == 0:
+            raise RuntimeError("fp16 packing is built for E=64, U=128")
+        if self.W_packed_f16 is None:
+            self.W_packed_f16 = torch.empty((nbytes,), dtype=torch.uint8, device=self.W.device)
+        _lib.check(lib.mmt_pack_gate_weights_f16(_p(self.W), self.E, self.U, _p(self.W_packed_f16), _stream()),
+                   "mmt_pack_gate_weights_f16")
+        return self
+
     def repack(self):
         """After the weights changed (a training step): refresh the operand images that exist, in place."""
         if self.W_packed is not None:
             self.pack()
         if self.W_packed_x3 is not None:
             self.pack_x3()
+        if self.W_packed_f16 is not None:
+            self.pack_f16()
         return self
 
     def c_cell(self):
@@ -221,6 +236,7 @@ class CellParams:
             setattr(w, n, None if t is None else t.data_ptr())
         w.W_packed_bf16 = None if self.W_packed is None else self.W_packed.data_ptr()
         w.W_packed_bf16x3 = None if self.W_packed_x3 is None else self.W_packed_x3.data_ptr()
+        w.W_packed_f16 = None if self.W_packed_f16 is None else self.W_packed_f16.data_ptr()
         w.E, w.U = self.E, self.U
         return w
 
@@ -391,20 +407,28 @@ def scene_batch(frame_ids, frame_row_start, ped_id, xy, vis, win_start, N, F, fs
     return pos, vo, valid, slot
 
 
-def rollout_bf16(pos, vis, valid, params: CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, out=None, timeline=None):
-    """The T+P-1 step recurrence as one persistent tcgen05 kernel with the state on chip (mmt_rollout_bf16):
-    pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N] -> params[S,N,P,5].  N in {8,16,32,64,128}."""
+def rollout_bf16(pos, vis, valid, params: CellParams, T=8, P=12, r2=4.0, inv_2sigma2=0.5, out=None, timeline=None,
+                 f16=False):
+    """The T+P-1 step recurrence as one persistent tcgen05 kernel with the state on chip (mmt_rollout_bf16; f16=True:
+    mmt_rollout_f16, the same kernel with fp16 operands): pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N] -> params[S,N,P,5].
+    N in {8,16,32,64,128}."""
     lib = _lib.load()
     _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis"); _chk(valid, torch.uint8, "valid")
     S, N = valid.shape
-    if params.W_packed is None:
+    if f16 and params.W_packed_f16 is None:
+        params.pack_f16()
+    if not f16 and params.W_packed is None:
         params.pack()
     if out is None:
         out = torch.empty((S, N, P, 5), dtype=torch.float32, device=pos.device)
     cw = params.c_cell()
-    _lib.check(lib.mmt_rollout_bf16(_p(pos), _p(vis), _p(valid), C.byref(cw), S, N, T, P, r2, inv_2sigma2, _p(out),
-                                    _p(timeline), _stream()), "mmt_rollout_bf16")
+    fn, name = (lib.mmt_rollout_f16, "mmt_rollout_f16") if f16 else (lib.mmt_rollout_bf16, "mmt_rollout_bf16")
+    _lib.check(fn(_p(pos), _p(vis), _p(valid), C.byref(cw), S, N, T, P, r2, inv_2sigma2, _p(out), _p(timeline), _stream()), name)
     return out
+
+
+def rollout_f16(pos, vis, valid, params: CellParams, **kw):
+    return rollout_bf16(pos, vis, valid, params, f16=True, **kw)
 
 
 # --------------------------------------------------------------------------------------------
@@ -423,6 +447,11 @@ class Forecaster:
             params.pack()
         if prec == PREC_BF16X3 and params.W_packed_x3 is None:
             params.pack_x3()
+        if prec == PREC_F16:
+            if relational or N < 8 or N > 128 or 128 % N:
+                raise ValueError("PREC_F16 is the fused rollout with fp16 operands: g2k_lstm_mc, N in {8,16,32,64,128}")
+            if params.W_packed_f16 is None:
+                params.pack_f16()
         self.cfg = _lib.ForecastCfg(S, N, T, P, K, r2, inv_2sigma2, int(relational), prec, seed, agent_offset)
         He = params.W2.shape[0] if (relational and params.W2 is not None) else 0
         nbytes = self.lib.mmt_forecast_workspace_bytes(C.byref(self.cfg), params.U, He)

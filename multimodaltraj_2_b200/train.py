@@ -487,7 +487,7 @@ class Trainer:
 
 
 def _param_names(params):
-    return [k for k in params.__dataclass_fields__ if isinstance(getattr(params, k), torch.Tensor) and k not in ("W_packed", "W_packed_x3")]
+    return [k for k in params.__dataclass_fields__ if isinstance(getattr(params, k), torch.Tensor) and k not in ("W_packed", "W_packed_x3", "W_packed_f16")]
 
 
 def save_checkpoint(path, params: ops.CellParams, trainer: "Trainer" = None, global_step=None):

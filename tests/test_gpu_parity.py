@@ -455,6 +455,37 @@ def test_forecast_bf16_tensor_core(cuda, S, N):
            7e-4, "forecast_bf16.best_ade")
 
 
+@pytest.mark.parametrize("S,N", [(8, 64), (5, 16), (2, 128), (40, 8), (9, 32), (70, 64)])
+def test_forecast_f16_fused_rollout_meets_the_fp32_bar(cuda, S, N):
+    """MMT_PREC_F16: the fused tcgen05 rollout with fp16 operands (10 stored mantissa bits), fp32 accumulation and state.
+    The north_star bar of the fp32 mode -- ADE / FDE of every sample within 1e-3 of the fp32 oracle -- holds (the bf16
+    operands miss it at the benched size: bench.py modes{}); the mean trajectory is stated at 2x its measured error."""
+    T, P, K = 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0, ragged=True)
+    p = synth.init_params(seed=3)
+    eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
+    fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, prec=ops.PREC_F16, device=cuda, want_all=True)
+    o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+    torch.cuda.synchronize()
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P)
+    got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
+    within(np.abs(got_mean - want["pred_mean"]).max(), 1e-3, "forecast_f16.pred_mean")
+    within(np.abs(npy(o["ade"]) - want["ade"]).max(), 1e-3, "forecast_f16.ade")
+    within(np.abs(npy(o["fde"]) - want["fde"]).max(), 1e-3, "forecast_f16.fde")
+    # the same inputs through the bf16 operands of the same kernel: the f16 error is the smaller one
+    fb = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, prec=ops.PREC_BF16, device=cuda, want_all=True)
+    ob = fb(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+    assert np.abs(npy(o["ade"]) - want["ade"]).max() < np.abs(npy(ob["ade"]) - want["ade"]).max()
+
+
+def test_f16_mode_rejects_what_the_fused_kernel_does_not_cover(cuda):
+    p = ops.CellParams.from_numpy(synth.init_params(seed=3), cuda)
+    with pytest.raises(ValueError):
+        ops.Forecaster(p, 2, 256, prec=ops.PREC_F16, device=cuda)
+    with pytest.raises(ValueError):
+        ops.Forecaster(p, 2, 64, relational=True, prec=ops.PREC_F16, device=cuda)
+
+
 @pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
 def test_forecast_bf16_relational(cuda, S, N):
     """g2k_lstm_mcr in bf16 mode (tcgen05 edge MLP + tcgen05 cell, per-step kernels): mean trajectory vs the fp32 oracle.
@@ -637,8 +668,8 @@ def test_train_step_rmsprop_and_loss_decrease(cuda):
 @pytest.mark.parametrize("gemm,relational", [("fp32", False), ("tc", False), ("tc", True)])
 def test_train_step_cuda_graph_equals_eager(cuda, gemm, relational):
     """Trainer(graph=True): forward + BPTT replayed as one CUDA graph.  Same launches in the same order, so after three
-    steps (the weights change in place between replays) the losses match the eager trainer; the weights match to the
-    reordering of the atomic accumulations of the split-K weight-gradient GEMMs / edge scatter (fp32 mode: exactly)."""
+    steps (the weights change in place between replays) losses and weights match the eager trainer to the reordering of
+    the atomic accumulations (loss sum, peephole / bias gradients, split-K weight-gradient GEMMs, edge scatter)."""
     from multimodaltraj_2_b200.train import Trainer
     S, N = 6, 16
     pos, vis, valid = synth.make_crowd(S, N, seed=12, half_extent=2.0, ragged=True)
@@ -652,11 +683,8 @@ def test_train_step_cuda_graph_equals_eager(cuda, gemm, relational):
         out.append((losses, cp.W.clone(), ops.launch_count() - n0))
     (l_e, w_e, n_e), (l_g, w_g, n_g) = out
     assert n_g >= n_e > 0                                    # replayed launches are counted (+ the capture's warm-up)
-    if gemm == "fp32" and not relational:
-        assert l_e == l_g and torch.equal(w_e, w_g)
-    else:
-        assert np.allclose(l_e, l_g, rtol=0, atol=2e-4), (l_e, l_g)
-        assert (w_e - w_g).abs().max().item() < 2e-4
+    assert np.allclose(l_e, l_g, rtol=0, atol=2e-4), (l_e, l_g)
+    assert (w_e - w_g).abs().max().item() < 2e-4
 
 
 # ------------------------------------------------------------------------------------------------
