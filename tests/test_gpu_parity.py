@@ -469,9 +469,9 @@ def test_forecast_f16_fused_rollout_meets_the_fp32_bar(cuda, S, N):
     torch.cuda.synchronize()
     want = o_b.forecast(pos, vis, valid, p, eps, T, P)
     got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
-    within(np.abs(got_mean - want["pred_mean"]).max(), 1e-3, "forecast_f16.pred_mean")
-    within(np.abs(npy(o["ade"]) - want["ade"]).max(), 1e-3, "forecast_f16.ade")
-    within(np.abs(npy(o["fde"]) - want["fde"]).max(), 1e-3, "forecast_f16.fde")
+    within(np.abs(got_mean - want["pred_mean"]).max(), 2.6e-4, "forecast_f16.pred_mean")     # 2x measured; the bar is 1e-3
+    within(np.abs(npy(o["ade"]) - want["ade"]).max(), 2.6e-4, "forecast_f16.ade")
+    within(np.abs(npy(o["fde"]) - want["fde"]).max(), 2.6e-4, "forecast_f16.fde")
     # the same inputs through the bf16 operands of the same kernel: the f16 error is the smaller one
     fb = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, prec=ops.PREC_BF16, device=cuda, want_all=True)
     ob = fb(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
