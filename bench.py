@@ -171,7 +171,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def _oracle():
     sys.path.insert(0, str(ROOT / "oracle"))
-    import track_b as o_b  # oracle: bench's cpu_baseline / reference arm only
+    import track_b as o_b  # oracle: the checker of the parity sample, bench's cpu_baseline and the reference arm only
     return o_b
 
 
@@ -270,8 +270,12 @@ def parity_sample(ops, synth, params, dev, prec, variant, n_scenes, N):
         o_b = _oracle()
         pos, vis, valid = synth.make_crowd(n_scenes, N, seed=synth.SEED)
         eps = o_b.philox_eps(0xB200, n_scenes, N, K_SAMPLES, P_PRED)
-        _PARITY_CACHE[key] = (pos, vis, valid, eps, o_b.forecast(pos, vis, valid, synth.init_params(seed=0), eps, T_OBS, P_PRED,
-                                                                R2, INV_2SIGMA2, relational=(variant == "mcr")))
+        # forecast() = rollout + decode; the rollout is run with its trace for the adjacency masks of the predicted steps
+        ro = o_b.rollout(pos, vis, valid, synth.init_params(seed=0), T_OBS, P_PRED, R2, INV_2SIGMA2,
+                         relational=(variant == "mcr"), trace=True)
+        a_, f_, b_, bt_, _ = o_b.decode_score(ro["params"], eps, pos[:, :, T_OBS - 1], pos[:, :, T_OBS:T_OBS + P_PRED], valid)
+        adj_pred = np.stack(ro.pop("trace")["adj"][T_OBS:])          # [P-1, S, N, N]: steps T .. T+P-2 see predicted positions
+        _PARITY_CACHE[key] = (pos, vis, valid, eps, dict(ade=a_, fde=f_, best_k=b_, best_traj=bt_, adj_pred=adj_pred, **ro))
     pos, vis, valid, eps, want = _PARITY_CACHE[key]
     fc = ops.Forecaster(params, n_scenes, N, T_OBS, P_PRED, K_SAMPLES, R2, INV_2SIGMA2, relational=(variant == "mcr"),
                         prec=prec, device=dev, want_all=True)
@@ -286,9 +290,35 @@ def parity_sample(ops, synth, params, dev, prec, variant, n_scenes, N):
     g_ade, g_fde = (g["ade"] * g_best).sum(-1)[v], (g["fde"] * g_best).sum(-1)[v]
     # mean predicted trajectory (cumulative mu) of the rollout, relative to the largest displacement
     w_mu, g_mu = want["params"][..., :2].cumsum(2)[v], g["params"][..., :2].cumsum(2)[v]
+    # Which scenes saw a DIFFERENT neighbour set than the oracle?  The kernel's adjacency test (bit-exact arithmetic: tests)
+    # re-evaluated on ITS predicted positions (last observed point + running fp32 sum of the emitted means, the kernel's
+    # own order of additions) against the oracle's masks.  One flipped neighbour changes a softmax row by O(0.1): the
+    # recurrence is discontinuous there, and that scene's deviation says nothing about the arithmetic before the flip.
+    o_b = _oracle()
+    cur = pos[:, :, T_OBS - 1].astype(np.float32)
+    flip = np.zeros(n_scenes, bool)
+    for k in range(P_PRED - 1):
+        cur = (cur + g["params"][:, :, k, :2]).astype(np.float32)
+        flip |= (o_b.pairwise_adj(cur, valid, R2, INV_2SIGMA2)[1] != want["adj_pred"][k]).any((1, 2))
+    keep = v & ~flip[:, None]
+    d_ade, d_fde = np.abs(g["ade"][v] - want["ade"][v]), np.abs(g["fde"][v] - want["fde"][v])      # [agents, K]
+    nf_ade = float(np.abs(g["ade"][keep] - want["ade"][keep]).max()) if keep.any() else 0.0
+    nf_fde = float(np.abs(g["fde"][keep] - want["fde"][keep]).max()) if keep.any() else 0.0
+    over = (np.abs(g["ade"] - want["ade"]).max(-1) > 1e-3) | (np.abs(g["fde"] - want["fde"]).max(-1) > 1e-3)   # [S, N]
+    over &= v
     return {"sample": f"{n_scenes} scenes x {N} agents of the benched batch, fed noise",
-            "max_abs_d_ade": float(np.abs(g["ade"][v] - want["ade"][v]).max()),
-            "max_abs_d_fde": float(np.abs(g["fde"][v] - want["fde"][v]).max()),
+            "max_abs_d_ade": float(d_ade.max()),
+            "max_abs_d_fde": float(d_fde.max()),
+            # the distribution behind the maxima: the adjacency test d^2 < r^2 makes the recurrence discontinuous, so in a
+            # large enough sample any arithmetic that is not bit-identical flips a neighbour somewhere
+            "quantiles_abs_d_ade": {q: float(np.quantile(d_ade, float(q))) for q in ("0.5", "0.99", "0.9999")},
+            "quantiles_abs_d_fde": {q: float(np.quantile(d_fde, float(q))) for q in ("0.5", "0.99", "0.9999")},
+            "frac_samples_within_1e-3": float(((d_ade <= 1e-3) & (d_fde <= 1e-3)).mean()),
+            "agents_over_1e-3": int(over.sum()), "scenes_with_an_agent_over_1e-3": int(over.any(1).sum()),
+            "scenes_with_a_flipped_neighbour": int(flip.sum()),
+            "scenes_over_1e-3_without_a_flip": int((over.any(1) & ~flip).sum()),
+            "max_abs_d_ade_where_adjacency_agrees": nf_ade, "max_abs_d_fde_where_adjacency_agrees": nf_fde,
+            "within_1e-3_where_adjacency_agrees": bool(nf_ade <= 1e-3 and nf_fde <= 1e-3),
             "d_mean_best_ade": float(abs(g_ade.mean() - w_ade.mean())), "d_mean_best_fde": float(abs(g_fde.mean() - w_fde.mean())),
             "oracle_mean_best_ade": float(w_ade.mean()), "oracle_mean_best_fde": float(w_fde.mean()),
             "best_k_equal_frac": float((g["best_k"][v] == want["best_k"][v]).mean()),
@@ -568,6 +598,13 @@ def run_ours(args, rank, world, local_rank):
             m["max_abs_d_fde_vs_oracle"] = delta[name]["max_abs_d_fde"]
             m["pos_rel_err_vs_oracle"] = delta[name]["pos_rel_err"]
             m["within_1e-3"] = delta[name]["within_1e-3"]
+            m["frac_samples_within_1e-3"] = delta[name]["frac_samples_within_1e-3"]
+            m["p9999_abs_d_fde_vs_oracle"] = delta[name]["quantiles_abs_d_fde"]["0.9999"]
+            m["scenes_with_an_agent_over_1e-3"] = delta[name]["scenes_with_an_agent_over_1e-3"]
+            m["scenes_with_a_flipped_neighbour"] = delta[name]["scenes_with_a_flipped_neighbour"]
+            m["within_1e-3_where_adjacency_agrees"] = delta[name]["within_1e-3_where_adjacency_agrees"]
+            m["max_abs_d_ade_where_adjacency_agrees"] = delta[name]["max_abs_d_ade_where_adjacency_agrees"]
+            m["max_abs_d_fde_where_adjacency_agrees"] = delta[name]["max_abs_d_fde_where_adjacency_agrees"]
         stage("cpu baseline")
         cores = os.cpu_count() or 1
         # CPU baseline on a bounded sample of the same workload: a small probe sizes it for ~10 s of CPU work
