@@ -123,20 +123,14 @@ __host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  //
   return ((size_t)(tile * (TC_U / 8) + (u >> 3)) * TC_M + r) * 8;
 }
 
-// WIDE (bf16 kernel, blocked state): ONE CTA per SM with 16 worker warps and FOUR weight stages instead of two CTAs with 8 warps
-// and two stages each -- the configuration the split-bf16 kernel and the fused rollout arrived at: with 8 warps the epilogue ran
-// at two warps per scheduler and a pass waited on 24 KB of weights in flight (49 k clk per tile and CTA, measured through the
-// per-step g2k_lstm_mcr / N = 256 paths: 173 us per C3 step).  Stages 2 and 3 sit behind the region where the split-bf16 kernel
-// keeps A_lo (SM_W23); that region itself carries the head partial sums of column slices 1-3.
-template <int LAY, bool X3 = false, bool WIDE = false>
-__global__ void __launch_bounds__((X3 || WIDE) ? TC_THREADS_X3 : TC_THREADS, (X3 || WIDE) ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
+template <int LAY, bool X3 = false>
+__global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
   constexpr bool BF = LAY != 0;
   static_assert(!X3 || LAY == 0, "split-bf16 mode takes the fp32 state layout");
-  static_assert(!WIDE || (LAY == 2 && !X3), "the wide configuration is built for the blocked bf16 state");
   constexpr int NKC = X3 ? TC_X3_NKC : TC_NKC;
-  constexpr int NSTAGE = X3 ? TC_NSTAGE_X3 : (WIDE ? 4 : TC_NSTAGE);
+  constexpr int NSTAGE = X3 ? TC_NSTAGE_X3 : TC_NSTAGE;
   constexpr bool STG = X3 && TC_X3_STAGING;
-  constexpr int NWT = (X3 || WIDE) ? TC_WORKERS_X3 : TC_WORKERS;   // worker threads
+  constexpr int NWT = X3 ? TC_WORKERS_X3 : TC_WORKERS;   // worker threads
   constexpr int NW = NWT / 32;                            // worker warps: 8 or 16; producer = warp NW, MMA issuer = warp NW + 1
   constexpr int NTHR = NWT + 64;
   constexpr int NH = NW / 4;                              // column slices of a pass (one per group of four warps)
@@ -320,16 +314,14 @@ __global__ void __launch_bounds__((X3 || WIDE) ? TC_THREADS_X3 : TC_THREADS, (X3
         const uint4* hsrc = reinterpret_cast<const uint4*>(a.hb + (size_t)tile * TC_M * TC_U);
         const uint4* msrc = reinterpret_cast<const uint4*>(a.mhb + (size_t)tile * TC_M * TC_U);
 #pragma unroll
-        constexpr int NPC = 2048 / NWT;   // 16-byte pieces per thread and array: 8 or 4
-#pragma unroll
         for (int arr = 0; arr < 2; ++arr) {
           const uint4* src = arr ? msrc : hsrc;
-          uint4 v8[NPC];
+          uint4 v8[8];
 #pragma unroll
-          for (int k = 0; k < NPC; ++k) v8[k] = src[tid + NWT * k];
+          for (int k = 0; k < 8; ++k) v8[k] = src[tid + 256 * k];
 #pragma unroll
-          for (int k = 0; k < NPC; ++k) {
-            const int pidx = tid + NWT * k, g = pidx >> 7, rr = pidx & 127;
+          for (int k = 0; k < 8; ++k) {
+            const int pidx = tid + 256 * k, g = pidx >> 7, rr = pidx & 127;
             const uint32_t off = (uint32_t)rr * 128u + (uint32_t)(((g & 7) ^ (rr & 7)) << 4);
             *reinterpret_cast<uint4*>(smem + SM_A + (1 + 2 * arr + (g >> 3)) * TC_A_BLOCK + off) = v8[k];
           }
@@ -614,7 +606,7 @@ __global__ void __launch_bounds__((X3 || WIDE) ? TC_THREADS_X3 : TC_THREADS, (X3
       if (a.params_out) {
         // slices 1 .. NH-1 hand their partial sums to slice 0.  The split-bf16 kernel has three of them: they go through the
         // A_lo operand region, free once the last pass has completed (every worker has seen its ACC_FULL) until the next build
-        float* const s_part = (X3 || WIDE) ? reinterpret_cast<float*>(smem + SM_ALO) : s_head;
+        float* const s_part = X3 ? reinterpret_cast<float*>(smem + SM_ALO) : s_head;
         if (hsel >= 1) {
 #pragma unroll
           for (int z = 0; z < 5; ++z) s_part[((hsel - 1) * TC_M + r) * 5 + z] = y[z];
@@ -691,16 +683,15 @@ static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
   a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
 }
 
-template <int LAY, bool X3 = false, bool WIDE = false>
+template <int LAY, bool X3 = false>
 static int tc_launch(TcArgs& a, cudaStream_t stream) {
   a.num_tiles = (a.R + TC_M - 1) / TC_M;
   a.trap = trap_record();
-  constexpr int kSmem = (X3 ? SM_TOTAL_X3 : WIDE ? SM_W23 + 2 * TC_STAGE_BYTES : SM_TOTAL) + 1024, kPerSM = (X3 || WIDE) ? 1 : 2;
-  static_assert(kSmem <= 227 * 1024, "shared memory of the cell kernel");
+  constexpr int kSmem = (X3 ? SM_TOTAL_X3 : SM_TOTAL) + 1024, kPerSM = X3 ? 1 : 2;
   static DeviceMask smem_opted[1];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3, WIDE>), kSmem, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3>), kSmem, &smem_opted[0])) return rc;
   const int grid = a.num_tiles < kPerSM * num_sms() ? a.num_tiles : kPerSM * num_sms();
-  gsk_cell_tc_kernel<LAY, X3, WIDE><<<grid, (X3 || WIDE) ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);
+  gsk_cell_tc_kernel<LAY, X3><<<grid, X3 ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);
   count_launch();
   return check_launch(X3 ? "gsk_cell_tc_kernel<x3>" : "gsk_cell_tc_kernel");
 }
@@ -719,12 +710,7 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
   tc_fill_weights(a, w);
   a.c_out = c_out; a.cur_pos = cur_pos; a.params_out = params_out; a.next_pos = next_pos;
   a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = params_stride;
-  // blocked state: the wide configuration once there is more than a tile per SM (fewer tiles: two CTAs per SM spread them
-  // wider).  MMT_CELL_WIDE (read once per process; tests and A/B timing): 1 = always wide, -1 = never.
-  static std::atomic<int> env_wide{INT_MIN};
-  const int force = env_int_once("MMT_CELL_WIDE", &env_wide);
-  const bool wide = force > 0 || (force == 0 && a.R > 128 * num_sms());
-  return blocked ? (wide ? tc_launch<2, false, true>(a, stream) : tc_launch<2>(a, stream)) : tc_launch<1>(a, stream);
+  return blocked ? tc_launch<2>(a, stream) : tc_launch<1>(a, stream);
 }
 
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,

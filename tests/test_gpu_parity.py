@@ -486,26 +486,6 @@ def test_f16_mode_rejects_what_the_fused_kernel_does_not_cover(cuda):
         ops.Forecaster(p, 2, 64, relational=True, prec=ops.PREC_F16, device=cuda)
 
 
-def test_blocked_cell_kernel_wide_equals_narrow(cuda, tmp_path):
-    """The blocked bf16 cell kernel has two launch configurations (two CTAs per SM x 8 worker warps x 2 weight stages; one CTA
-    x 16 warps x 4 stages, taken when there is more than a tile per SM).  Same arithmetic in the same order: the per-step
-    paths that use it (stepwise g2k_lstm_mc, g2k_lstm_mcr, N = 256) give bit-identical forecasts in both."""
-    import os
-    import subprocess
-    import sys
-    outs = {}
-    for force in ("1", "-1"):
-        f = tmp_path / f"cell_{force}.pt"
-        r = subprocess.run([sys.executable, str(ROOT / "tests" / "_cell_config.py"), str(f)], env=dict(os.environ, MMT_CELL_WIDE=force),
-                           capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0 and "CELL_CONFIG_OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
-        outs[force] = torch.load(f)
-    for name, a in outs["1"].items():
-        for k, v in a.items():
-            assert torch.equal(v, outs["-1"][name][k]), (name, k)
-        assert torch.isfinite(a["params"]).all() and a["params"].abs().sum() > 0
-
-
 @pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
 def test_forecast_bf16_relational(cuda, S, N):
     """g2k_lstm_mcr in bf16 mode (tcgen05 edge MLP + tcgen05 cell, per-step kernels): mean trajectory vs the fp32 oracle.
