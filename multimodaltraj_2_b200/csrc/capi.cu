@@ -133,7 +133,8 @@ extern "C" int mmt_gsk_cell(const float* x, const float* h, const float* c, cons
   MMT_REQUIRE(w->W_e && w->b_e && w->W && w->b && w->w_If && w->w_It && w->w_Of && w->w_Ot, "cell weights required");
   MMT_REQUIRE(R >= 0, "R must be >= 0");
   MMT_REQUIRE(w->E == 64 && w->U == 128, "cell is built for E = 64, U = 128");
-  MMT_REQUIRE(prec == MMT_PREC_F32 || prec == MMT_PREC_BF16 || prec == MMT_PREC_BF16X3, "unknown precision mode");
+  MMT_REQUIRE(prec == MMT_PREC_F32 || prec == MMT_PREC_BF16 || prec == MMT_PREC_BF16X3 || prec == MMT_PREC_F16,
+              "unknown precision mode");
   MMT_REQUIRE(!params_out || (w->W_h && w->b_h && cur_pos && params_stride >= 5), "head needs W_h, b_h, cur_pos");
   MMT_REQUIRE(h_out != h && c_out != c, "outputs must not alias the input state (rows are re-read by other CTAs)");
   MMT_ALIGNED(x); MMT_ALIGNED(h); MMT_ALIGNED(c); MMT_ALIGNED(mh); MMT_ALIGNED(mc);
@@ -147,9 +148,9 @@ extern "C" int mmt_gsk_cell(const float* x, const float* h, const float* c, cons
     if (params_out) rc = launch_head(h_out, U, mf_out, U, valid, w, R, cur_pos, params_out, params_stride, next_pos, st);
     return rc;
   }
-  const int x3 = prec == MMT_PREC_BF16X3;
-  MMT_REQUIRE(x3 ? w->W_packed_bf16x3 != nullptr : w->W_packed_bf16 != nullptr,
-              "bf16 modes need the packed operand image (mmt_pack_gate_weights_bf16 / _bf16x3)");
+  const int x3 = prec == MMT_PREC_BF16X3 ? 1 : prec == MMT_PREC_F16 ? 2 : 0;   // operand mode of launch_cell_tc
+  MMT_REQUIRE(x3 == 1 ? w->W_packed_bf16x3 != nullptr : x3 == 2 ? w->W_packed_f16 != nullptr : w->W_packed_bf16 != nullptr,
+              "tensor-core modes need the packed operand image (mmt_pack_gate_weights_bf16 / _bf16x3 / _f16)");
   return launch_cell_tc(x, h, c, mh, mc, U, valid, w, R, h_out, c_out, mf_out, U, cur_pos, params_out, params_stride,
                         next_pos, x3, st);
 }

@@ -62,7 +62,6 @@ constexpr int SM_HEAD = SM_WE + (256 + 64) * 4;               // head partials [
 constexpr int SM_TOTAL = SM_HEAD + 128 * 5 * 4;
 static_assert(SM_TOTAL + 1024 <= 113 * 1024, "two CTAs per SM must fit");
 
-constexpr uint32_t kIdesc = make_idesc_bf16(TC_M, TC_N);
 
 // Split-bf16 ("bf16x3") mode: the fp32 operands are split a = a_hi + a_lo, w = w_hi + w_lo (bf16 each: 16 mantissa bits
 // together) and the product is taken as a_hi w_hi + a_lo w_hi + a_hi w_lo in the fp32 accumulator (the dropped a_lo w_lo
@@ -123,10 +122,14 @@ __host__ __device__ __forceinline__ size_t blk_off(int tile, int r, int u) {  //
   return ((size_t)(tile * (TC_U / 8) + (u >> 3)) * TC_M + r) * 8;
 }
 
-template <int LAY, bool X3 = false>
+// F16: fp16 instead of bf16 in every 16-bit operand and state word of the kernel (MMT_PREC_F16; the "bf16" state buffers of
+// LAY 1 / 2 then hold fp16 bits -- producers and consumers of a forecast all run in the same mode).
+template <int LAY, bool X3 = false, bool F16 = false>
 __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) gsk_cell_tc_kernel(TcArgs a) {
   constexpr bool BF = LAY != 0;
   static_assert(!X3 || LAY == 0, "split-bf16 mode takes the fp32 state layout");
+  static_assert(!(X3 && F16), "the split mode is built on bf16 pairs");
+  constexpr uint32_t kIdesc = make_idesc_op<F16>(TC_M, TC_N);
   constexpr int NKC = X3 ? TC_X3_NKC : TC_NKC;
   constexpr int NSTAGE = X3 ? TC_NSTAGE_X3 : TC_NSTAGE;
   constexpr bool STG = X3 && TC_X3_STAGING;
@@ -271,8 +274,7 @@ __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) g
               s = fmaf(xv.w, s_we[192 + k], s);
               e2[z] = ok ? fmaxf(s, 0.f) : 0.f;
             }
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(e2[0], e2[1]);
-            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
+            pk[j >> 1] = pack_op2<F16>(e2[0], e2[1]);
             if constexpr (X3) pl[j >> 1] = pack_bf16x2_lo(e2[0], e2[1], pk[j >> 1]);
           }
           *reinterpret_cast<uint4*>(smem + SM_A + sw128_off(r, k0 + kk)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -372,8 +374,8 @@ __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) g
             const int rr = r8 + NW * i;
             const int k = lane * 4;  // 0..124 within the 128-wide part
             const int blk = k >> 6, kk = k & 63;
-            const uint2 hh = make_uint2(pack_bf16x2(hv[i].x, hv[i].y), pack_bf16x2(hv[i].z, hv[i].w));
-            const uint2 mm = make_uint2(pack_bf16x2(mv[i].x, mv[i].y), pack_bf16x2(mv[i].z, mv[i].w));
+            const uint2 hh = make_uint2(pack_op2<F16>(hv[i].x, hv[i].y), pack_op2<F16>(hv[i].z, hv[i].w));
+            const uint2 mm = make_uint2(pack_op2<F16>(mv[i].x, mv[i].y), pack_op2<F16>(mv[i].z, mv[i].w));
             *reinterpret_cast<uint2*>(smem + SM_A + (1 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = hh;
             *reinterpret_cast<uint2*>(smem + SM_A + (3 + blk) * TC_A_BLOCK + sw128_off(rr, kk)) = mm;
             if constexpr (X3) {
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) g
             float4 m4;
             if constexpr (BF) {
               const uint32_t w0 = hq ? cur.m.z : cur.m.x, w1 = hq ? cur.m.w : cur.m.y;
-              m4 = make_float4(bf16_lo(w0), bf16_hi(w0), bf16_lo(w1), bf16_hi(w1));
+              m4 = make_float4(op_lo<F16>(w0), op_hi<F16>(w0), op_lo<F16>(w1), op_hi<F16>(w1));
             } else {
               m4 = hq ? cur.mf1 : cur.mf0;
             }
@@ -536,8 +538,8 @@ __global__ void __launch_bounds__(X3 ? TC_THREADS_X3 : TC_THREADS, X3 ? 1 : 2) g
           cp[1] = make_float4(co[4], co[5], co[6], co[7]);
           if constexpr (BF) {
             *reinterpret_cast<uint4*>(a.hb_out + so) =
-                make_uint4(pack_bf16x2(ho[0], ho[1]), pack_bf16x2(ho[2], ho[3]), pack_bf16x2(ho[4], ho[5]),
-                           pack_bf16x2(ho[6], ho[7]));
+                make_uint4(pack_op2<F16>(ho[0], ho[1]), pack_op2<F16>(ho[2], ho[3]), pack_op2<F16>(ho[4], ho[5]),
+                           pack_op2<F16>(ho[6], ho[7]));
           } else {
             float4* hp = reinterpret_cast<float4*>(a.h_out + (size_t)gr * a.ld + u);
             hp[0] = make_float4(ho[0], ho[1], ho[2], ho[3]);
@@ -683,15 +685,15 @@ static void tc_fill_weights(TcArgs& a, const mmt_cell_weights* w) {
   a.W_h = w->W_h; a.b_h = w->b_h; a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16);
 }
 
-template <int LAY, bool X3 = false>
+template <int LAY, bool X3 = false, bool F16 = false>
 static int tc_launch(TcArgs& a, cudaStream_t stream) {
   a.num_tiles = (a.R + TC_M - 1) / TC_M;
   a.trap = trap_record();
   constexpr int kSmem = (X3 ? SM_TOTAL_X3 : SM_TOTAL) + 1024, kPerSM = X3 ? 1 : 2;
   static DeviceMask smem_opted[1];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3>), kSmem, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&gsk_cell_tc_kernel<LAY, X3, F16>), kSmem, &smem_opted[0])) return rc;
   const int grid = a.num_tiles < kPerSM * num_sms() ? a.num_tiles : kPerSM * num_sms();
-  gsk_cell_tc_kernel<LAY, X3><<<grid, X3 ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);
+  gsk_cell_tc_kernel<LAY, X3, F16><<<grid, X3 ? TC_THREADS_X3 : TC_THREADS, kSmem, stream>>>(a);
   count_launch();
   return check_launch(X3 ? "gsk_cell_tc_kernel<x3>" : "gsk_cell_tc_kernel");
 }
@@ -699,7 +701,7 @@ static int tc_launch(TcArgs& a, cudaStream_t stream) {
 // bf16-state variant used by the rollout: h, mh, mc as bf16 [R,U]; c fp32 [R,U]
 int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
                         const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
-                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
+                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked, int f16,
                         cudaStream_t stream) {
   TcArgs a = {};
   a.x = x; a.c = c; a.valid = valid;
@@ -710,20 +712,25 @@ int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const vo
   tc_fill_weights(a, w);
   a.c_out = c_out; a.cur_pos = cur_pos; a.params_out = params_out; a.next_pos = next_pos;
   a.R = R; a.ld = TC_U; a.ld_mf = TC_U; a.params_stride = params_stride;
+  if (f16) {
+    a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_f16);
+    return blocked ? tc_launch<2, false, true>(a, stream) : tc_launch<1, false, true>(a, stream);
+  }
   return blocked ? tc_launch<2>(a, stream) : tc_launch<1>(a, stream);
 }
 
 int launch_cell_tc(const float* x, const float* h, const float* c, const float* mh, const float* mc, int ld,
                    const uint8_t* valid, const mmt_cell_weights* w, int R, float* h_out, float* c_out, float* mf_out,
-                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos, int x3,
-                   cudaStream_t stream) {
+                   int ld_mf, const float* cur_pos, float* params_out, int params_stride, float* next_pos,
+                   int x3 /* 0: bf16 operands, 1: split bf16, 2: fp16 operands */, cudaStream_t stream) {
   TcArgs a = {};
   a.x = x; a.h = h; a.c = c; a.mh = mh; a.mc = mc; a.valid = valid;
   tc_fill_weights(a, w);
-  if (x3) a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16x3);
+  if (x3 == 1) a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_bf16x3);
+  if (x3 == 2) a.Wp = reinterpret_cast<const uint8_t*>(w->W_packed_f16);
   a.h_out = h_out; a.c_out = c_out; a.mf_out = mf_out; a.cur_pos = cur_pos; a.params_out = params_out;
   a.next_pos = next_pos; a.R = R; a.ld = ld; a.ld_mf = ld_mf; a.params_stride = params_stride;
-  return x3 ? tc_launch<0, true>(a, stream) : tc_launch<0>(a, stream);
+  return x3 == 1 ? tc_launch<0, true>(a, stream) : x3 == 2 ? tc_launch<0, false, true>(a, stream) : tc_launch<0>(a, stream);
 }
 
 }  // namespace mmt

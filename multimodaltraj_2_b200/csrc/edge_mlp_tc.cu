@@ -22,18 +22,22 @@ constexpr int EM_BLK = 128 * 128;              // A operand k-block: [128 rows][
 
 // ------------------------------------------------------------------------------------------------
 // packing: W1[2U,He], W2[He,He] fp32 row-major -> bf16 K-major SWIZZLE_128B operand images
+template <bool F16>
 __global__ void pack_edge_weights_kernel(const float* __restrict__ W1, const float* __restrict__ W2,
                                          uint8_t* __restrict__ out) {
+  auto put = [](uint8_t* p, float w) {
+    if constexpr (F16) *reinterpret_cast<__half*>(p) = __float2half_rn(w);
+    else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(w);
+  };
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < 256 * 128) {
     const int n = idx >> 7, k = idx & 127;   // output column n of [a | b], input unit k
     const float w = n < 128 ? W1[(size_t)k * EM_HE + n] : W1[(size_t)(EM_U + k) * EM_HE + (n - 128)];
-    *reinterpret_cast<__nv_bfloat16*>(out + (k >> 6) * (256 * 128) + sw128_off(n, k & 63)) = __float2bfloat16_rn(w);
+    put(out + (k >> 6) * (256 * 128) + sw128_off(n, k & 63), w);
   } else if (idx < 256 * 128 + 128 * 128) {
     const int i2 = idx - 256 * 128;
     const int n = i2 >> 7, k = i2 & 127;
-    *reinterpret_cast<__nv_bfloat16*>(out + EM_W1_BYTES + (k >> 6) * EM_BLK + sw128_off(n, k & 63)) =
-        __float2bfloat16_rn(W2[(size_t)k * EM_HE + n]);
+    put(out + EM_W1_BYTES + (k >> 6) * EM_BLK + sw128_off(n, k & 63), W2[(size_t)k * EM_HE + n]);
   }
 }
 
@@ -44,12 +48,12 @@ constexpr int NP_SM_B = 0;                          // 64 KB
 constexpr int NP_SM_A = NP_SM_B + EM_W1_BYTES;      // 32 KB
 constexpr int NP_SM_BAR = NP_SM_A + 34 * 1024;      // A block (32 KB); the epilogue staging [8][32][33] floats needs 33 KB
 constexpr int NP_SM_TOTAL = NP_SM_BAR + 32;
-constexpr uint32_t kIdescNP = make_idesc_bf16(128, 256);
+template <bool F16> constexpr uint32_t kIdescNP = make_idesc_op<F16>(128, 256);
 
 // BLOCKED: h is the tile-blocked bf16 state of the per-step fast path (cell_tc.cu: piece (g, r) = units 8g..8g+7 of
 // row r of a 128-row tile, 16 bytes at ((tile 16 + g) 128 + r) 16) -- each piece is one 16-byte chunk of the K-major
 // SWIZZLE_128B operand, copied as it is.
-template <bool BLOCKED>
+template <bool BLOCKED, bool F16 = false>
 __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __restrict__ h, int ld_h, int R,
                                                               const uint8_t* __restrict__ Wp, __nv_bfloat16* __restrict__ out,
                                                               int num_tiles, uint32_t* trap) {
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
       if (g < R) hv = __ldg(reinterpret_cast<const float4*>(h + (size_t)g * ld_h) + lane);
       const int k = lane * 4;
       *reinterpret_cast<uint2*>(smem + NP_SM_A + (k >> 6) * EM_BLK + sw128_off(rr, k & 63)) =
-          make_uint2(pack_bf16x2(hv.x, hv.y), pack_bf16x2(hv.z, hv.w));
+          make_uint2(pack_op2<F16>(hv.x, hv.y), pack_op2<F16>(hv.z, hv.w));
     }
     fence_proxy_async();
     __syncthreads();
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
       for (int ks = 0; ks < 8; ++ks) {
         const uint64_t da = make_desc_sw128(sbase + NP_SM_A + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
         const uint64_t db = make_desc_sw128(sbase + NP_SM_B + (ks >> 2) * (256 * 128)) + (uint64_t)((ks & 3) * 2);
-        umma_bf16(tmem_base, da, db, kIdescNP, ks ? 1u : 0u);
+        umma_bf16(tmem_base, da, db, kIdescNP<F16>, ks ? 1u : 0u);
       }
       umma_commit(bar_mma);
     }
@@ -129,7 +133,11 @@ __global__ void __launch_bounds__(256, 2) node_proj_tc_kernel(const float* __res
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
           const int g = row0 + q * 32 + rr;
-          if (g < R) out[(size_t)g * 256 + half * 128 + cb * 32 + lane] = __float2bfloat16_rn(stg[rr * 33 + lane]);
+          if (g < R) {
+            const float pv = stg[rr * 33 + lane];
+            if constexpr (F16) reinterpret_cast<__half*>(out)[(size_t)g * 256 + half * 128 + cb * 32 + lane] = __float2half_rn(pv);
+            else out[(size_t)g * 256 + half * 128 + cb * 32 + lane] = __float2bfloat16_rn(pv);
+          }
         }
         __syncwarp();
       }
@@ -150,10 +158,11 @@ constexpr int EE_SM_PAR = EE_SM_LIST + (EE_LIST + 128) * 8; // b1[128] b2[128] w
 constexpr int EE_SM_PART = EE_SM_PAR + 3 * 128 * 4; // float[128]: partial sums of the upper column half
 constexpr int EE_SM_BAR = EE_SM_PART + 512;
 constexpr int EE_SM_TOTAL = EE_SM_BAR + 48 + 32;
-constexpr uint32_t kIdescEE = make_idesc_bf16(128, 128);
+template <bool F16> constexpr uint32_t kIdescEE = make_idesc_op<F16>(128, 128);
 
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_fast(x * 1.4426950408889634f) - 1.0f; }
 
+template <bool F16>
 __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16* __restrict__ nab,   // [R, 256] = [a | b]
                                                              const uint8_t* __restrict__ adj, const uint8_t* __restrict__ Wp,
                                                              const float* __restrict__ b1, const float* __restrict__ b2,
@@ -223,10 +232,10 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
             for (int u = 0; u < 8; ++u) {
               const int e = warp * 16 + e0 + u;   // rows beyond nt get elu(b1): finite, never read back
               *reinterpret_cast<uint2*>(blk + e * 128 + ((chunk ^ (e & 7)) << 4)) =
-                  make_uint2(pack_bf16x2(elu_fast(bf16_lo(av[u].x) + bf16_lo(bv[u].x) + c4.x),
-                                         elu_fast(bf16_hi(av[u].x) + bf16_hi(bv[u].x) + c4.y)),
-                             pack_bf16x2(elu_fast(bf16_lo(av[u].y) + bf16_lo(bv[u].y) + c4.z),
-                                         elu_fast(bf16_hi(av[u].y) + bf16_hi(bv[u].y) + c4.w)));
+                  make_uint2(pack_op2<F16>(elu_fast(op_lo<F16>(av[u].x) + op_lo<F16>(bv[u].x) + c4.x),
+                                           elu_fast(op_hi<F16>(av[u].x) + op_hi<F16>(bv[u].x) + c4.y)),
+                             pack_op2<F16>(elu_fast(op_lo<F16>(av[u].y) + op_lo<F16>(bv[u].y) + c4.z),
+                                           elu_fast(op_hi<F16>(av[u].y) + op_hi<F16>(bv[u].y) + c4.w)));
             }
           }
         }
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t da = make_desc_sw128(sbase + EE_SM_A + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
             const uint64_t db = make_desc_sw128(sbase + EE_SM_W2 + (ks >> 2) * EM_BLK) + (uint64_t)((ks & 3) * 2);
-            umma_bf16(tmem_base, da, db, kIdescEE, ks ? 1u : 0u);
+            umma_bf16(tmem_base, da, db, kIdescEE<F16>, ks ? 1u : 0u);
           }
           umma_commit(bar_mma);
         }
@@ -358,26 +367,33 @@ __global__ void __launch_bounds__(256, 2) edge_mlp_tc_kernel(const __nv_bfloat16
 
 // h[R, U] (row stride ld_h) -> score[S,N,N] on the edges of adj; nab: >= R*256 floats of scratch.
 // ld_h < 0: h is the tile-blocked bf16 state (rows padded to whole tiles) instead of fp32 rows.
-int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
-                       int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
+template <bool F16>
+static int edge_mlp_tc_run(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
+                           int N, float* score, float* nab, int zero_fill, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   static DeviceMask smem_opted[3];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<false>), NP_SM_TOTAL + 1024, &smem_opted[0])) return rc;
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<true>), NP_SM_TOTAL + 1024, &smem_opted[1])) return rc;
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&edge_mlp_tc_kernel), EE_SM_TOTAL + 1024, &smem_opted[2])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<false, F16>), NP_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&node_proj_tc_kernel<true, F16>), NP_SM_TOTAL + 1024, &smem_opted[1])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&edge_mlp_tc_kernel<F16>), EE_SM_TOTAL + 1024, &smem_opted[2])) return rc;
   const uint8_t* Wp = reinterpret_cast<const uint8_t*>(packed);
   int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
-  __nv_bfloat16* nabh = reinterpret_cast<__nv_bfloat16*>(nab);   // R x 256 bf16 inside the R x 256 float scratch
-  if (ld_h < 0) node_proj_tc_kernel<true><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nabh, tiles, trap_record());
-  else node_proj_tc_kernel<false><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nabh, tiles, trap_record());
+  __nv_bfloat16* nabh = reinterpret_cast<__nv_bfloat16*>(nab);   // R x 256 16-bit words inside the R x 256 float scratch
+  if (ld_h < 0) node_proj_tc_kernel<true, F16><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, 0, R, Wp, nabh, tiles, trap_record());
+  else node_proj_tc_kernel<false, F16><<<grid, 256, NP_SM_TOTAL + 1024, stream>>>(h, ld_h, R, Wp, nabh, tiles, trap_record());
   count_launch();
   int rc = check_launch("node_proj_tc_kernel");
   if (rc) return rc;
   grid = S < 2 * num_sms() ? S : 2 * num_sms();
-  edge_mlp_tc_kernel<<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nabh, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
-                                                                zero_fill, trap_record());
+  edge_mlp_tc_kernel<F16><<<grid, 256, EE_SM_TOTAL + 1024, stream>>>(nabh, adj, Wp, w->b1, w->b2, w->w_out, w->b_out, S, N, score,
+                                                                     zero_fill, trap_record());
   count_launch();
   return check_launch("edge_mlp_tc_kernel");
+}
+
+int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
+                       int N, float* score, float* nab, int zero_fill, int f16, cudaStream_t stream) {
+  return f16 ? edge_mlp_tc_run<true>(h, ld_h, adj, packed, w, S, N, score, nab, zero_fill, stream)
+             : edge_mlp_tc_run<false>(h, ld_h, adj, packed, w, S, N, score, nab, zero_fill, stream);
 }
 
 // node projections only (the backward kernel of edge_mlp_bwd_tc.cu gathers the same [a | b] rows)
@@ -392,9 +408,10 @@ int launch_node_proj_tc(const float* h, int ld_h, const void* packed, int R, __n
   return check_launch("node_proj_tc_kernel");
 }
 
-int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream) {
+int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, int f16, cudaStream_t stream) {
   const int n = 256 * 128 + 128 * 128;
-  pack_edge_weights_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W1, W2, reinterpret_cast<uint8_t*>(packed));
+  if (f16) pack_edge_weights_kernel<true><<<(n + 255) / 256, 256, 0, stream>>>(W1, W2, reinterpret_cast<uint8_t*>(packed));
+  else pack_edge_weights_kernel<false><<<(n + 255) / 256, 256, 0, stream>>>(W1, W2, reinterpret_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_edge_weights_kernel");
 }
@@ -411,7 +428,7 @@ extern "C" int mmt_pack_edge_weights_bf16(const float* W1, const float* W2, int 
   MMT_REQUIRE(W1 && W2 && packed, "W1/W2/packed must not be NULL");
   MMT_REQUIRE(U == EM_U && He == EM_HE, "packing is built for U = 128, He = 128");
   MMT_ALIGNED(packed);
-  return launch_pack_edge_weights(W1, W2, packed, (cudaStream_t)stream);
+  return launch_pack_edge_weights(W1, W2, packed, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mmt_edge_mlp_bf16(const float* h, const uint8_t* adj, const void* packed, const float* b1, const float* b2,
@@ -431,5 +448,5 @@ extern "C" int mmt_edge_mlp_bf16(const float* h, const uint8_t* adj, const void*
     return MMT_EWORKSPACE;
   }
   mmt_edge_weights w{nullptr, b1, nullptr, b2, w_out, b_out, He};
-  return launch_edge_mlp_tc(h, U, adj, packed, &w, S, N, score, work, 1, (cudaStream_t)stream);
+  return launch_edge_mlp_tc(h, U, adj, packed, &w, S, N, score, work, 1, 0, (cudaStream_t)stream);
 }

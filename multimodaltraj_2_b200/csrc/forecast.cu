@@ -26,20 +26,20 @@ int launch_decode(const float* params, const float* eps, uint64_t seed, uint64_t
 
 int launch_cell_tc_bf16(const float* x, const void* hb, const float* c, const void* mhb, const void* mcb,
                         const uint8_t* valid, const mmt_cell_weights* w, int R, void* hb_out, float* c_out,
-                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked,
+                        const float* cur_pos, float* params_out, int params_stride, float* next_pos, int blocked, int f16,
                         cudaStream_t stream);
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
                                int S, int N,
-                               float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+                               float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream);
 int launch_edge_mlp_tc(const float* h, int ld_h, const uint8_t* adj, const void* packed, const mmt_edge_weights* w, int S,
-                       int N, float* score, float* nab, int zero_fill, cudaStream_t stream);
-int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, cudaStream_t stream);
+                       int N, float* score, float* nab, int zero_fill, int f16, cudaStream_t stream);
+int launch_pack_edge_weights(const float* W1, const float* W2, void* packed, int f16, cudaStream_t stream);
 int launch_rollout_tc(const float* pos, const float* vis, const uint8_t* valid, const mmt_cell_weights* w, int S, int N,
                       int T, int P, float r2, float inv_2sigma2, float* params, long long* dbg, int f16, cudaStream_t stream);
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
-                                   float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+                                   float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream);
 int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
-                                int U, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream);
+                                int U, float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream);
 
 // x = [cur - prev | vis_t]; for observed frames cur is gathered from pos[:, :, t]
 __global__ void __launch_bounds__(256) prep_step_kernel(const float* __restrict__ pos, const float* __restrict__ vis,
@@ -91,17 +91,12 @@ static Workspace carve(char* base, const mmt_forecast_cfg* cfg, int U, int He) {
   // MMA kernel (blocked layout, N >= 16): edge scores are added to the logits inside graph_aggregate_mma_kernel
   const bool tileable = 128 % cfg->N == 0 || (cfg->N % 128 == 0 && cfg->N <= 1024);
   const bool rel_fast = cfg->relational && U == 128 && He == 128 && tileable && cfg->N >= 16;
-  w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE) && (!cfg->relational || rel_fast);
+  w.fast = (cfg->prec == MMT_PREC_BF16 || cfg->prec == MMT_PREC_BF16_STEPWISE || cfg->prec == MMT_PREC_F16) &&
+           (!cfg->relational || rel_fast);
   for (int i = 0; i < 3; ++i) w.pbuf[i] = (float*)take(R * 2 * 4);
   w.x = (float*)take(R * 4 * 4);
   w.blocked = w.fast && tileable;
-  if (cfg->prec == MMT_PREC_F16) {
-    // fused rollout only: the state never leaves the chip, no per-step buffers
-    for (int i = 0; i < 2; ++i) { w.hb[i] = nullptr; w.cf[i] = nullptr; w.hc[i] = nullptr; }
-    w.mhb = w.mcb = nullptr;
-    w.mhc = w.mf = w.kern = nullptr;
-    w.adj = nullptr;
-  } else if (w.fast) {
+  if (w.fast) {
     const size_t Rp = (R + 127) / 128 * 128;   // state rows padded to whole 128-row tiles
     for (int i = 0; i < 2; ++i) {
       w.hb[i] = take(Rp * U * 2);
@@ -149,8 +144,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
                   cfg->prec == MMT_PREC_BF16X3 || cfg->prec == MMT_PREC_F16,
               "unknown precision mode");
   const bool f16 = cfg->prec == MMT_PREC_F16;
-  MMT_REQUIRE(!f16 || (cw->W_packed_f16 && !cfg->relational && cfg->N >= 8 && cfg->N <= 128 && 128 % cfg->N == 0),
-              "MMT_PREC_F16 is the fused rollout with fp16 operands: needs W_packed_f16, g2k_lstm_mc, N in {8,16,32,64,128}");
+  MMT_REQUIRE(!f16 || cw->W_packed_f16, "f16 mode needs W_packed_f16");
   MMT_REQUIRE(cfg->prec == MMT_PREC_F32 || cfg->prec == MMT_PREC_BF16X3 || f16 || cw->W_packed_bf16, "bf16 mode needs W_packed_bf16");
   MMT_REQUIRE(cfg->prec != MMT_PREC_BF16X3 || cw->W_packed_bf16x3, "bf16x3 mode needs W_packed_bf16x3");
   MMT_ALIGNED(pos);
@@ -171,7 +165,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
 
   // bf16, non-relational, whole scenes per 128-row tile: the entire recurrence is one persistent kernel with the
   // state on chip (rollout_tc.cu).  MMT_PREC_BF16_STEPWISE keeps the per-step kernels (A/B checks, other N).
-  const bool fused = f16 || (w.fast && w.blocked && N >= 8 && N <= 128 && cfg->prec == MMT_PREC_BF16 && !cfg->relational);
+  const bool fused = w.fast && w.blocked && N >= 8 && N <= 128 && (cfg->prec == MMT_PREC_BF16 || f16) && !cfg->relational;
   if (fused) {
     if ((rc0 = launch_rollout_tc(pos, vis, valid, cw, S, N, T, P, cfg->r2, cfg->inv_2sigma2, par, nullptr, f16, stream)))
       return rc0;
@@ -186,7 +180,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
   int rc;
   // relational bf16 modes: the edge MLP runs on the tensor cores (edge_mlp_tc.cu); weights packed once per call
   const bool edge_tc = cfg->relational && cfg->prec != MMT_PREC_F32 && cfg->prec != MMT_PREC_BF16X3 && U == 128 && He == 128;
-  if (edge_tc && (rc = launch_pack_edge_weights(ew->W1, ew->W2, w.epacked, stream))) return rc;
+  if (edge_tc && (rc = launch_pack_edge_weights(ew->W1, ew->W2, w.epacked, f16, stream))) return rc;
   for (int t = 0; t < (fused ? 0 : T + P - 1); ++t) {
     prep_step_kernel<<<(R + 255) / 256, 256, 0, stream>>>(pos, vis, R, F, T, t, w.pbuf[ic], w.pbuf[ip], w.x);
     count_launch();
@@ -201,23 +195,23 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
         if ((rc = mmt_pairwise_adj_f32(w.pbuf[ic], valid, S, N, cfg->r2, cfg->inv_2sigma2, nullptr, w.adj, nullptr, stream)))
           return rc;
         if ((rc = launch_edge_mlp_tc(reinterpret_cast<const float*>(w.hb[hb]), -1, w.adj, w.epacked, ew, S, N, w.score,
-                                     w.ework, 0, stream)))
+                                     w.ework, 0, f16, stream)))
           return rc;
         esc = w.score;
       }
       if (w.blocked && N >= 16)
         rc = launch_graph_aggregate_mma(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], esc, S, N, cfg->r2, cfg->inv_2sigma2, w.mhb,
-                                        w.mcb, stream);
+                                        w.mcb, f16, stream);
       else if (w.blocked)
         rc = launch_graph_aggregate_blocked(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, cfg->r2, cfg->inv_2sigma2,
-                                            w.mhb, w.mcb, stream);
+                                            w.mhb, w.mcb, f16, stream);
       else
         rc = launch_graph_aggregate_bf16(w.pbuf[ic], valid, w.hb[hb], w.cf[hb], S, N, U, cfg->r2, cfg->inv_2sigma2,
-                                         w.mhb, w.mcb, stream);
+                                         w.mhb, w.mcb, f16, stream);
       if (rc) return rc;
       if ((rc = launch_cell_tc_bf16(w.x, w.hb[hb], w.cf[hb], w.mhb, w.mcb, valid, cw, R, w.hb[hb ^ 1], w.cf[hb ^ 1],
                                     w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr,
-                                    w.blocked ? 1 : 0, stream)))
+                                    w.blocked ? 1 : 0, f16, stream)))
         return rc;
       hb ^= 1;
       const int old_p = ip;
@@ -235,7 +229,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
     const float* l2 = nullptr;
     if (cfg->relational) {
       // (the aggregation reads the scores only on the edges: no zero fill needed here)
-      if (edge_tc) rc = launch_edge_mlp_tc(w.hc[hb], 2 * U, w.adj, w.epacked, ew, S, N, w.score, w.ework, 0, stream);
+      if (edge_tc) rc = launch_edge_mlp_tc(w.hc[hb], 2 * U, w.adj, w.epacked, ew, S, N, w.score, w.ework, 0, f16, stream);
       else rc = launch_edge_mlp_f32(w.hc[hb], 2 * U, w.adj, ew, S, N, U, w.score, w.ework, stream);
       if (rc) return rc;
       l2 = w.score;
@@ -256,7 +250,7 @@ extern "C" int mmt_forecast_f32(const float* pos, const float* vis, const uint8_
       float* hco = w.hc[hb ^ 1];
       if ((rc = launch_cell_tc(w.x, hc, hc + U, w.mhc, w.mhc + U, 2 * U, valid, cw, R, hco, hco + U, nullptr, 0,
                                w.pbuf[ic], emit ? po : nullptr, P * 5, emit ? w.pbuf[in] : nullptr,
-                               cfg->prec == MMT_PREC_BF16X3, stream)))
+                               cfg->prec == MMT_PREC_BF16X3 ? 1 : f16 ? 2 : 0, stream)))
         return rc;
     }
     hb ^= 1;

@@ -7,12 +7,37 @@
 // come from L2), writes 512 B/agent.
 #include <cuda_bf16.h>
 
+#include <cuda_fp16.h>
+
 #include "mmt_common.cuh"
 
 namespace mmt {
 
 constexpr int kGaWarps = 8;
 
+// 16-bit state words: bf16 (MMT_PREC_BF16*) or fp16 (MMT_PREC_F16) -- two per 32-bit word, low half first
+template <bool F16>
+__device__ __forceinline__ float st_lo(uint32_t w) {
+  if constexpr (F16) return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
+  else return __uint_as_float(w << 16);
+}
+template <bool F16>
+__device__ __forceinline__ float st_hi(uint32_t w) {
+  if constexpr (F16) return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+  else return __uint_as_float(w & 0xffff0000u);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t st_pack(float lo, float hi) {
+  if constexpr (F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&b);
+  }
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(kGaWarps * 32) graph_aggregate_bf16_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
     const float* __restrict__ c, int rows, int N, int U, float r2, float inv_2sigma2,
@@ -67,27 +92,23 @@ __global__ void __launch_bounds__(kGaWarps * 32) graph_aggregate_bf16_kernel(
       const size_t jr = sbase + nb_idx[k];
       const uint2 hv = __ldg(reinterpret_cast<const uint2*>(hb + jr * U) + lane);
       const float4 cv = __ldg(reinterpret_cast<const float4*>(c + jr * U) + lane);
-      ah[0] = fmaf(w, __uint_as_float(hv.x << 16), ah[0]);
-      ah[1] = fmaf(w, __uint_as_float(hv.x & 0xffff0000u), ah[1]);
-      ah[2] = fmaf(w, __uint_as_float(hv.y << 16), ah[2]);
-      ah[3] = fmaf(w, __uint_as_float(hv.y & 0xffff0000u), ah[3]);
+      ah[0] = fmaf(w, st_lo<F16>(hv.x), ah[0]);
+      ah[1] = fmaf(w, st_hi<F16>(hv.x), ah[1]);
+      ah[2] = fmaf(w, st_lo<F16>(hv.y), ah[2]);
+      ah[3] = fmaf(w, st_hi<F16>(hv.y), ah[3]);
       ac[0] = fmaf(w, cv.x, ac[0]);
       ac[1] = fmaf(w, cv.y, ac[1]);
       ac[2] = fmaf(w, cv.z, ac[2]);
       ac[3] = fmaf(w, cv.w, ac[3]);
     }
-    __nv_bfloat162 h01 = __floats2bfloat162_rn(ah[0], ah[1]), h23 = __floats2bfloat162_rn(ah[2], ah[3]);
-    __nv_bfloat162 c01 = __floats2bfloat162_rn(ac[0], ac[1]), c23 = __floats2bfloat162_rn(ac[2], ac[3]);
-    reinterpret_cast<uint2*>(mhb + (size_t)r * U)[lane] =
-        make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-    reinterpret_cast<uint2*>(mcb + (size_t)r * U)[lane] =
-        make_uint2(*reinterpret_cast<uint32_t*>(&c01), *reinterpret_cast<uint32_t*>(&c23));
+    reinterpret_cast<uint2*>(mhb + (size_t)r * U)[lane] = make_uint2(st_pack<F16>(ah[0], ah[1]), st_pack<F16>(ah[2], ah[3]));
+    reinterpret_cast<uint2*>(mcb + (size_t)r * U)[lane] = make_uint2(st_pack<F16>(ac[0], ac[1]), st_pack<F16>(ac[2], ac[3]));
     __syncwarp();
   }
 }
 
 int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
-                                int U, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
+                                int U, float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream) {
   if (U != 128) {
     set_error("graph_aggregate_bf16: built for U = 128");
     return MMT_EARG;
@@ -96,9 +117,14 @@ int launch_graph_aggregate_bf16(const float* pos, const uint8_t* valid, const vo
   long blocks = (rows + kGaWarps - 1) / kGaWarps;
   int grid = blocks < (long)num_sms() * 8 ? (int)blocks : num_sms() * 8;
   const size_t smem = (size_t)kGaWarps * N * 8;
-  graph_aggregate_bf16_kernel<<<grid, kGaWarps * 32, smem, stream>>>(
-      pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, (int)rows, N, U, r2, inv_2sigma2,
-      reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb));
+  if (f16)
+    graph_aggregate_bf16_kernel<true><<<grid, kGaWarps * 32, smem, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, (int)rows, N, U, r2, inv_2sigma2,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb));
+  else
+    graph_aggregate_bf16_kernel<false><<<grid, kGaWarps * 32, smem, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, (int)rows, N, U, r2, inv_2sigma2,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb));
   count_launch();
   return check_launch("graph_aggregate_bf16_kernel");
 }
@@ -116,6 +142,7 @@ constexpr int GB_THREADS = 256;
 constexpr int GB_HROW = 128 + 8;    // bf16 elements per staged h row (+16 B pad: conflict-free 16 B stores)
 constexpr int GB_CROW = 128 + 4;    // floats per staged c row (+16 B pad)
 
+template <bool F16>
 __global__ void __launch_bounds__(GB_THREADS, 2) graph_aggregate_blocked_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
     const float* __restrict__ c, int R, int N, float r2, float inv_2sigma2, __nv_bfloat16* __restrict__ mhb,
@@ -209,21 +236,19 @@ __global__ void __launch_bounds__(GB_THREADS, 2) graph_aggregate_blocked_kernel(
         const int j = nb_idx[k];
         const uint2 hv = *reinterpret_cast<const uint2*>(sh + j * GB_HROW + lane * 4);
         const float4 cv = *reinterpret_cast<const float4*>(sc + j * GB_CROW + lane * 4);
-        ah[0] = fmaf(w, __uint_as_float(hv.x << 16), ah[0]);
-        ah[1] = fmaf(w, __uint_as_float(hv.x & 0xffff0000u), ah[1]);
-        ah[2] = fmaf(w, __uint_as_float(hv.y << 16), ah[2]);
-        ah[3] = fmaf(w, __uint_as_float(hv.y & 0xffff0000u), ah[3]);
+        ah[0] = fmaf(w, st_lo<F16>(hv.x), ah[0]);
+        ah[1] = fmaf(w, st_hi<F16>(hv.x), ah[1]);
+        ah[2] = fmaf(w, st_lo<F16>(hv.y), ah[2]);
+        ah[3] = fmaf(w, st_hi<F16>(hv.y), ah[3]);
         ac[0] = fmaf(w, cv.x, ac[0]);
         ac[1] = fmaf(w, cv.y, ac[1]);
         ac[2] = fmaf(w, cv.z, ac[2]);
         ac[3] = fmaf(w, cv.w, ac[3]);
       }
-      __nv_bfloat162 h01 = __floats2bfloat162_rn(ah[0], ah[1]), h23 = __floats2bfloat162_rn(ah[2], ah[3]);
-      __nv_bfloat162 c01 = __floats2bfloat162_rn(ac[0], ac[1]), c23 = __floats2bfloat162_rn(ac[2], ac[3]);
       // blocked store: lane's 4 units live in group g = lane/2, half (lane&1)
       const size_t o = ((size_t)(tile * 16 + (lane >> 1)) * 128 + rr) * 8 + (lane & 1) * 4;
-      *reinterpret_cast<uint2*>(mhb + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-      *reinterpret_cast<uint2*>(mcb + o) = make_uint2(*reinterpret_cast<uint32_t*>(&c01), *reinterpret_cast<uint32_t*>(&c23));
+      *reinterpret_cast<uint2*>(mhb + o) = make_uint2(st_pack<F16>(ah[0], ah[1]), st_pack<F16>(ah[2], ah[3]));
+      *reinterpret_cast<uint2*>(mcb + o) = make_uint2(st_pack<F16>(ac[0], ac[1]), st_pack<F16>(ac[2], ac[3]));
       __syncwarp();
     }
     __syncthreads();
@@ -231,15 +256,21 @@ __global__ void __launch_bounds__(GB_THREADS, 2) graph_aggregate_blocked_kernel(
 }
 
 int launch_graph_aggregate_blocked(const float* pos, const uint8_t* valid, const void* hb, const float* c, int S, int N,
-                                   float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
+                                   float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
   const size_t smem = 128 * GB_HROW * 2 + 128 * GB_CROW * 4 + 128 * 8 + (size_t)8 * N * 8 + 128 + 16;
-  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_blocked_kernel), 112 * 1024, &smem_opted[0])) return rc;
+  static DeviceMask smem_opted[2];   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_blocked_kernel<false>), 112 * 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_blocked_kernel<true>), 112 * 1024, &smem_opted[1])) return rc;
   const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
-  graph_aggregate_blocked_kernel<<<grid, GB_THREADS, smem, stream>>>(
-      pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, R, N, r2, inv_2sigma2,
-      reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);
+  if (f16)
+    graph_aggregate_blocked_kernel<true><<<grid, GB_THREADS, smem, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, R, N, r2, inv_2sigma2,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);
+  else
+    graph_aggregate_blocked_kernel<false><<<grid, GB_THREADS, smem, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, R, N, r2, inv_2sigma2,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles);
   count_launch();
   return check_launch("graph_aggregate_blocked_kernel");
 }

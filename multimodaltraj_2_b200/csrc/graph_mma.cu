@@ -30,7 +30,7 @@ constexpr int GM_SM_SUM = GM_SM_POS + GM_MAXN * 8;   // float[2][128] partial ro
 constexpr int GM_SM_VAL = GM_SM_SUM + 1024;      // u8[max(128, N)]
 constexpr int GM_SM_BAR = GM_SM_VAL + GM_MAXN;   // mbarrier + tmem ptr
 constexpr int GM_SM_TOTAL = GM_SM_BAR + 32;
-constexpr uint32_t kIdescAggMN256 = make_idesc_bf16(128, 256) | (1u << 16);   // B operand MN-major
+template <bool F16> constexpr uint32_t kIdescAggMN256 = make_idesc_op<F16>(128, 256) | (1u << 16);   // B operand MN-major
 
 __device__ __forceinline__ uint64_t gm_desc_mn(uint32_t smem_addr) {   // LBO = one block, SBO = 8 agents x 128 B
   uint64_t d = 0;
@@ -42,6 +42,8 @@ __device__ __forceinline__ uint64_t gm_desc_mn(uint32_t smem_addr) {   // LBO = 
   return d;
 }
 
+// F16: fp16 instead of bf16 operands / state words (MMT_PREC_F16), see cell_tc.cu
+template <bool F16>
 __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
     const float* __restrict__ pos, const uint8_t* __restrict__ valid, const __nv_bfloat16* __restrict__ hb,
     const float* __restrict__ c, const float* __restrict__ score, int R, int N, float r2, float neg_inv_log2e,
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
         for (int k = 0; k < 8; ++k) {
           const int qd = tid + 256 * (k + 8 * half), piece = qd >> 1, hf = qd & 1;
           const int g = piece >> 7, r = piece & 127;
-          const uint32_t w0 = pack_bf16x2(__uint_as_float(cv[k].x), __uint_as_float(cv[k].y));
-          const uint32_t w1 = pack_bf16x2(__uint_as_float(cv[k].z), __uint_as_float(cv[k].w));
+          const uint32_t w0 = pack_op2<F16>(__uint_as_float(cv[k].x), __uint_as_float(cv[k].y));
+          const uint32_t w1 = pack_op2<F16>(__uint_as_float(cv[k].z), __uint_as_float(cv[k].w));
           *reinterpret_cast<uint2*>(smem + GM_SM_B + (2 + (g >> 3)) * GM_BLK + r * 128 + (((g & 7) ^ (r & 7)) << 4) + hf * 8) =
               make_uint2(w0, w1);
         }
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
               const float kern = ex2_fast(d2 * neg_inv_log2e);     // exp(-d2 / 2 sigma^2)
               e2[z] = a ? ex2_fast((kern + sc8[q + z]) * LOG2E) : 0.f;   // exp(logit); softmax numerator
             }
-            pk[q >> 1] = pack_bf16x2(e2[0], e2[1]);
-            sum += bf16_lo(pk[q >> 1]) + bf16_hi(pk[q >> 1]);      // normalise by what the MMA really sums
+            pk[q >> 1] = pack_op2<F16>(e2[0], e2[1]);
+            sum += op_lo<F16>(pk[q >> 1]) + op_hi<F16>(pk[q >> 1]);      // normalise by what the MMA really sums
           }
           const int jt = (multi ? 0 : sb) + j8;                    // column inside the K block
           *reinterpret_cast<uint4*>(smem + GM_SM_A + (jt >> 6) * GM_BLK + sw128_off(i, jt & 63)) =
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t da = make_desc_sw128(sbase + GM_SM_A + (ks >> 2) * GM_BLK) + (uint64_t)((ks & 3) * 2);
-          umma_bf16(tmem_base, da, gm_desc_mn(sbase + GM_SM_B + ks * 2048), kIdescAggMN256, (kh | ks) ? 1u : 0u);
+          umma_bf16(tmem_base, da, gm_desc_mn(sbase + GM_SM_B + ks * 2048), kIdescAggMN256<F16>, (kh | ks) ? 1u : 0u);
         }
         umma_commit(bar);
       }
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
         tmem_wait_ld();
         const size_t o0 = ((size_t)(tile * 16 + ch) * 128 + r) * 8;
         *reinterpret_cast<uint4*>(outp + o0) =
-            make_uint4(pack_bf16x2(v0[0] * inv, v0[1] * inv), pack_bf16x2(v0[2] * inv, v0[3] * inv),
-                       pack_bf16x2(v0[4] * inv, v0[5] * inv), pack_bf16x2(v0[6] * inv, v0[7] * inv));
+            make_uint4(pack_op2<F16>(v0[0] * inv, v0[1] * inv), pack_op2<F16>(v0[2] * inv, v0[3] * inv),
+                       pack_op2<F16>(v0[4] * inv, v0[5] * inv), pack_op2<F16>(v0[6] * inv, v0[7] * inv));
         *reinterpret_cast<uint4*>(outp + o0 + 128 * 8) =
-            make_uint4(pack_bf16x2(v1[0] * inv, v1[1] * inv), pack_bf16x2(v1[2] * inv, v1[3] * inv),
-                       pack_bf16x2(v1[4] * inv, v1[5] * inv), pack_bf16x2(v1[6] * inv, v1[7] * inv));
+            make_uint4(pack_op2<F16>(v1[0] * inv, v1[1] * inv), pack_op2<F16>(v1[2] * inv, v1[3] * inv),
+                       pack_op2<F16>(v1[4] * inv, v1[5] * inv), pack_op2<F16>(v1[6] * inv, v1[7] * inv));
       }
     }
     tc_fence_before();
@@ -210,14 +212,20 @@ __global__ void __launch_bounds__(GM_THREADS, 2) graph_aggregate_mma_kernel(
 
 // score: NULL (g2k_lstm_mc) or [S,N,N] edge scores added to the logits on the edges (g2k_lstm_mcr)
 int launch_graph_aggregate_mma(const float* pos, const uint8_t* valid, const void* hb, const float* c, const float* score,
-                               int S, int N, float r2, float inv_2sigma2, void* mhb, void* mcb, cudaStream_t stream) {
+                               int S, int N, float r2, float inv_2sigma2, void* mhb, void* mcb, int f16, cudaStream_t stream) {
   const int R = S * N, tiles = (R + 127) / 128;
-  static DeviceMask smem_opted[1];   // per kernel: devices already opted in
-  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_mma_kernel), GM_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  static DeviceMask smem_opted[2];   // per kernel: devices already opted in
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_mma_kernel<false>), GM_SM_TOTAL + 1024, &smem_opted[0])) return rc;
+  if (int rc = opt_in_smem(reinterpret_cast<const void*>(&graph_aggregate_mma_kernel<true>), GM_SM_TOTAL + 1024, &smem_opted[1])) return rc;
   const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
-  graph_aggregate_mma_kernel<<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(
-      pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, score, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
-      reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles, trap_record());
+  if (f16)
+    graph_aggregate_mma_kernel<true><<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, score, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles, trap_record());
+  else
+    graph_aggregate_mma_kernel<false><<<grid, GM_THREADS, GM_SM_TOTAL + 1024, stream>>>(
+        pos, valid, reinterpret_cast<const __nv_bfloat16*>(hb), c, score, R, N, r2, -inv_2sigma2 * 1.4426950408889634f,
+        reinterpret_cast<__nv_bfloat16*>(mhb), reinterpret_cast<__nv_bfloat16*>(mcb), tiles, trap_record());
   count_launch();
   return check_launch("graph_aggregate_mma_kernel");
 }

@@ -275,6 +275,8 @@ def gsk_cell(x, h, c, mh, mc, valid, params: CellParams, prec=PREC_F32, cur_pos=
         params.pack()
     if prec == PREC_BF16X3 and params.W_packed_x3 is None:
         params.pack_x3()
+    if prec == PREC_F16 and params.W_packed_f16 is None:
+        params.pack_f16()
     w = params.c_cell()
     _lib.check(lib.mmt_gsk_cell(_p(x), _p(h), _p(c), _p(mh), _p(mc), _p(valid), C.byref(w), R, prec, _p(h_out),
                                 _p(c_out), _p(mf), _p(cur_pos), _p(par), 5, _p(nxt), _stream()), "mmt_gsk_cell")
@@ -447,11 +449,8 @@ class Forecaster:
             params.pack()
         if prec == PREC_BF16X3 and params.W_packed_x3 is None:
             params.pack_x3()
-        if prec == PREC_F16:
-            if relational or N < 8 or N > 128 or 128 % N:
-                raise ValueError("PREC_F16 is the fused rollout with fp16 operands: g2k_lstm_mc, N in {8,16,32,64,128}")
-            if params.W_packed_f16 is None:
-                params.pack_f16()
+        if prec == PREC_F16 and params.W_packed_f16 is None:
+            params.pack_f16()
         self.cfg = _lib.ForecastCfg(S, N, T, P, K, r2, inv_2sigma2, int(relational), prec, seed, agent_offset)
         He = params.W2.shape[0] if (relational and params.W2 is not None) else 0
         nbytes = self.lib.mmt_forecast_workspace_bytes(C.byref(self.cfg), params.U, He)

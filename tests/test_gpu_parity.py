@@ -277,6 +277,27 @@ def test_gsk_cell_bf16_tensor_core(cuda, R):
     within(np.abs(npy(par) - oy).max(), 3e-4, "cell_bf16.head")
 
 
+@pytest.mark.parametrize("R", [200, 128 * 300 + 17])
+def test_gsk_cell_f16_tensor_core(cuda, R):
+    """The same tcgen05 cell with fp16 operands (mmt_gsk_cell, prec = MMT_PREC_F16): three more mantissa bits in the
+    GEMM operands; what is left is the approximate tanh of the epilogue.  Stated separately, 2x measured."""
+    p = synth.init_params(seed=1)
+    x, h, c, mh, mc, valid, cur = _cell_inputs(R, seed=R + 1)
+    P = ops.CellParams.from_numpy(p, cuda)
+    ho, co, mf, par, nxt = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, ops.PREC_F16,
+                                        cur_pos=dev(cur, cuda), want_head=True)
+    hb, cb, *_ = ops.gsk_cell(*(dev(a, cuda) for a in (x, h, c, mh, mc, valid)), P, ops.PREC_BF16,
+                              cur_pos=dev(cur, cuda), want_head=True)
+    torch.cuda.synchronize()
+    oh, oc, of = o_b.gsk_cell(x[None], h[None], c[None], mh[None], mc[None], valid[None], p)
+    e16 = max(np.abs(npy(got) - want[0]).max() for got, want in ((ho, oh), (co, oc), (mf, of)))
+    eb = max(np.abs(npy(got) - want[0]).max() for got, want in ((hb, oh), (cb, oc)))
+    within(e16, 2e-3, "cell_f16.state_vs_fp32_oracle")
+    assert e16 < eb                                          # and better than the bf16 operands on the same inputs
+    oy = o_b.head(oh, of, p)[0] * valid[:, None]
+    within(np.abs(npy(par) - oy).max(), 3e-4, "cell_f16.head")
+
+
 def test_gridlstm_reference_instantiation(cuda):
     """GridLSTMCell exactly as helper.py:31-39 builds it (U=2, F = D/4) with the checkpoint's parameters."""
     g = np.load(GOLD / "track_a_ckpt.npz")
@@ -478,12 +499,26 @@ def test_forecast_f16_fused_rollout_meets_the_fp32_bar(cuda, S, N):
     assert np.abs(npy(o["ade"]) - want["ade"]).max() < np.abs(npy(ob["ade"]) - want["ade"]).max()
 
 
-def test_f16_mode_rejects_what_the_fused_kernel_does_not_cover(cuda):
-    p = ops.CellParams.from_numpy(synth.init_params(seed=3), cuda)
-    with pytest.raises(ValueError):
-        ops.Forecaster(p, 2, 256, prec=ops.PREC_F16, device=cuda)
-    with pytest.raises(ValueError):
-        ops.Forecaster(p, 2, 64, relational=True, prec=ops.PREC_F16, device=cuda)
+@pytest.mark.parametrize("S,N,relational", [(3, 12, False), (2, 256, False), (2, 384, False), (1, 24, False),
+                                            (6, 64, True), (10, 16, True), (2, 256, True), (5, 12, True), (7, 8, True)])
+def test_forecast_f16_per_step_kernels(cuda, S, N, relational):
+    """MMT_PREC_F16 where the fused kernel does not apply (other N, g2k_lstm_mcr): the per-step tensor-core kernels
+    (graph MMA / SIMT graph step, edge MLP, cell) with fp16 operands and fp16 state words.  Mean trajectory against the
+    fp32 oracle, and never worse than the bf16 operands of the same kernels on the same inputs."""
+    T, P, K = 8, 12, 20
+    pos, vis, valid = synth.make_crowd(S, N, seed=78, half_extent=4.0 if N < 100 else 8.0, ragged=True)
+    p = synth.init_params(seed=3)
+    eps = np.random.default_rng(9).standard_normal((S, N, K, P, 2)).astype(np.float32)
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P, relational=relational)
+    err = {}
+    for name, prec in (("f16", ops.PREC_F16), ("bf16", ops.PREC_BF16)):
+        fc = ops.Forecaster(ops.CellParams.from_numpy(p, cuda), S, N, T, P, K, relational=relational, prec=prec, device=cuda)
+        o = fc(dev(pos, cuda), dev(vis, cuda), dev(valid, cuda), eps=dev(eps, cuda))
+        torch.cuda.synchronize()
+        got_mean = np.cumsum(npy(o["params"])[..., :2], 2) + pos[:, :, T - 1:T]
+        err[name] = np.abs(got_mean - want["pred_mean"]).max()
+    within(err["f16"], 4e-4, "forecast_f16_per_step.pred_mean")
+    assert err["f16"] <= err["bf16"] * 1.05 + 2e-5, err
 
 
 @pytest.mark.parametrize("S,N", [(6, 64), (10, 16), (2, 256), (5, 12), (7, 8)])
