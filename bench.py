@@ -872,8 +872,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--prec", default=None, choices=["f16", "bf16", "f32", "bf16-stepwise", "bf16x3"],
-                    help="default: f16 (fused rollout with fp16 tensor-core operands: inside the 1e-3 ADE/FDE bar, same speed as "
-                         "bf16) where the fused kernel applies (g2k_lstm_mc, inference), else bf16")
+                    help="default: f16 (fp16 tensor-core operands and state words, fp32 accumulation: inside the 1e-3 ADE/FDE bar "
+                         "at the speed of bf16)")
     ap.add_argument("--variant", default=None, choices=["mc", "mcr"], help="default: mc (mcr for --config c2)")
     ap.add_argument("--scenes", type=int, default=4096)
     ap.add_argument("--agents", type=int, default=64)
@@ -892,8 +892,7 @@ def main():
     if args.variant is None:
         args.variant = "mcr" if args.config == "c2" else "mc"
     if args.prec is None:
-        args.prec = "f16" if (args.variant == "mc" and args.mode == "infer" and args.config != "c2" and args.impl == "ours"
-                              and 128 % args.agents == 0 and args.agents >= 8) else "bf16"
+        args.prec = "f16" if (args.mode == "infer" and args.config != "c2" and args.impl == "ours") else "bf16"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -41,9 +41,9 @@ extern "C" {
                              (a_hi w_hi + a_lo w_hi + a_hi w_lo, fp32 accumulate in TMEM: 16 operand mantissa bits),
                              tanhf / expf in the epilogue -- the north_star's 1e-4 / 1e-3 tolerance on tcgen05      */
 
-#define MMT_PREC_F16 4 /* the fused rollout of MMT_PREC_BF16 with fp16 operands (10 stored mantissa bits instead of 7; fp32
-                          accumulate in TMEM): same kernel and speed, ADE / FDE inside the 1e-3 bar that bf16 misses.
-                          g2k_lstm_mc, N in {8,16,32,64,128}; operands must stay inside the fp16 range (|x| < 65504)  */
+#define MMT_PREC_F16 4 /* the kernels of MMT_PREC_BF16 with fp16 operands and fp16 state words (10 stored mantissa bits
+                          instead of 7; fp32 accumulate in TMEM): same kernels and speed, ADE / FDE inside the 1e-3 bar that
+                          bf16 misses.  Needs W_packed_f16; operands must stay inside the fp16 range (|x| < 65504)          */
 
 int mmt_version(void);
 const char* mmt_last_error(void);
