@@ -29,7 +29,7 @@ class ArgsParser():
     parser.add_argument('--lambda_param', type=float, default=0.0005)
     # additions of the batched B200 path
     parser.add_argument('--K', type=int, default=20, help='samples per agent for best-of-K')
-    parser.add_argument('--precision', type=str, default='bf16', choices=['fp32', 'bf16'])
+    parser.add_argument('--precision', type=str, default='fp16', choices=['fp32', 'fp16', 'bf16', 'bf16x3'])
     parser.add_argument('--world_size', type=int, default=1)
     parser.add_argument('--variant', type=str, default='mcr', choices=['mc', 'mcr'],
                         help='model of the batched path: g2k_lstm_mcr (the reference driver\'s, relational) or g2k_lstm_mc')

@@ -71,12 +71,12 @@ class g2k_lstm_mcr():
     # ------------------------------------------------------------------------------------------
     relational = True          # g2k_lstm_mcr: edge-MLP scores join the attention logits (nri_learned.py:5-28)
 
-    def forecast_batched(self, pos, vis, valid, params, K=20, r2=4.0, inv_2sigma2=0.5, prec=ops.PREC_BF16, seed=0,
+    def forecast_batched(self, pos, vis, valid, params, K=20, r2=4.0, inv_2sigma2=0.5, prec=ops.PREC_F16, seed=0,
                          agent_offset=0, eps=None, use_graph=False):
         """The north_star path behind the drop-in class: all scenes of a batch through pairwise kernel -> [edge MLP]
         -> aggregation -> gate update for obs_len + pred_len - 1 frames, then K-sample decode + ADE/FDE + best-of-K
         (``mmt_forecast_f32``).  pos[S,N,T+P,2], vis[S,N,T,2], valid[S,N]; ``params``: ops.CellParams.
-        g2k_lstm_mc in bf16 mode with 128 % N == 0 runs the fused persistent rollout kernel; g2k_lstm_mcr the
+        g2k_lstm_mc in the f16 (default) / bf16 modes with 128 % N == 0 runs the fused persistent rollout kernel; g2k_lstm_mcr the
         relational per-step tensor-core kernels.  The forecaster (workspace, CUDA graphs) is cached per shape."""
         S, N = valid.shape
         T = pos.shape[2] - self.pred_len

@@ -14,14 +14,14 @@ from ._weights import size0
 
 class gsk_lstm_cell():
     def __init__(self, in_features, out_size, obs_len, num_nodes, lambda_reg, params: ops.CellParams = None,
-                 precision="bf16", device="cuda"):
+                 precision="fp16", device="cuda"):
         self.out_size = int(num_nodes)
         self.hidden_size = int(out_size)
         self.obs_len = int(obs_len)
         self.lambda_reg = float(lambda_reg)
         self.in_size = size0(in_features)
         self.device = torch.device(device)
-        self.prec = ops.PREC_BF16 if precision == "bf16" else ops.PREC_F32
+        self.prec = ops.prec_from_name(precision)
         self.params = params if params is not None else ops.CellParams.from_numpy(
             synth.init_params(seed=0, U=self.hidden_size), self.device)
         self.pred_path_band = None

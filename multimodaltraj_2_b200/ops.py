@@ -16,6 +16,15 @@ from . import _lib
 PREC_F32, PREC_BF16, PREC_BF16_STEPWISE, PREC_BF16X3, PREC_F16 = 0, 1, 2, 3, 4
 
 
+def prec_from_name(name):
+    """--precision of the drivers (argParser.py) -> MMT_PREC_*: 'fp16' (default: fp16 tensor-core operands, inside the 1e-3
+    ADE / FDE bar), 'bf16', 'bf16x3' (split bf16, fp32-grade), 'fp32' (CUDA-core parity mode)."""
+    table = {"fp16": PREC_F16, "f16": PREC_F16, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp32": PREC_F32, "f32": PREC_F32}
+    if name not in table:
+        raise ValueError(f"unknown precision {name!r}: one of {sorted(table)}")
+    return table[name]
+
+
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 

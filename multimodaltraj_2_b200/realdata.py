@@ -66,7 +66,7 @@ def scene_windows(args, d, part="val", device="cuda", N=None, hop=1, data_root=N
                 slot_ped=slot[keep].contiguous(), N=N, loader=dl, windows=int(pos.shape[0]))
 
 
-def evaluate_split(args, d, params, part="val", prec=ops.PREC_BF16, relational=False, rank=0, world=1, device="cuda",
+def evaluate_split(args, d, params, part="val", prec=ops.PREC_F16, relational=False, rank=0, world=1, device="cuda",
                    seed=None, eps=None, data_root=None, scenes=None):
     """Best-of-K ADE / FDE of one split on this rank's scene shard, combined over the ranks.
     eps: optional fed noise [S,N,K,P,2] for the WHOLE split (parity runs); otherwise in-kernel Philox keyed by the global

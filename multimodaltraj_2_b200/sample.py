@@ -47,7 +47,7 @@ def main(argv=None, params=None, device=None, results_path=None):
     l = args.leaveDataset
     p = params if params is not None else ops.CellParams.from_numpy(
         synth.init_params(seed=0, E=args.embedding_size, U=args.rnn_size), device)
-    prec = ops.PREC_BF16 if getattr(args, "precision", "bf16") == "bf16" else ops.PREC_F32
+    prec = ops.prec_from_name(getattr(args, "precision", "fp16"))
     t0 = time.time()
     sc = realdata.scene_windows(args, l, "val", device)
     torch.cuda.synchronize()

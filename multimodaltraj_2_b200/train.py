@@ -34,7 +34,7 @@ def train(args, params=None, datasets=(2, 3, 4), rank=None, world=None, device=N
     world = int(os.environ.get("WORLD_SIZE", getattr(args, "world_size", 1))) if world is None else world
     device = device or torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     dist = torch.distributed if (world > 1 and torch.distributed.is_initialized()) else None
-    prec = ops.PREC_BF16 if getattr(args, "precision", "bf16") == "bf16" else ops.PREC_F32
+    prec = ops.prec_from_name(getattr(args, "precision", "fp16"))
     p = params if params is not None else ops.CellParams.from_numpy(
         synth.init_params(seed=0, E=args.embedding_size, U=args.rnn_size), device)
     save_dir = getattr(args, "save_dir", None)
@@ -174,7 +174,7 @@ def validate(args, params=None, l=None, rank=None, world=None, device=None, sess
     if rank == 0:
         print('Cross-Validation total mean error (ADE) for dataset {0} = '.format(l), res["cv_ade"])       # :688
         print('Cross-Validation total final error (FDE) for dataset {0} = '.format(l), res["cv_fde"])      # :689
-    prec = ops.PREC_BF16 if getattr(args, "precision", "bf16") == "bf16" else ops.PREC_F32
+    prec = ops.prec_from_name(getattr(args, "precision", "fp16"))
     p = params if params is not None else ops.CellParams.from_numpy(
         synth.init_params(seed=0, E=args.embedding_size, U=args.rnn_size), device)
     res["best_of_k"] = realdata.public(realdata.evaluate_split(args, l, p, part="val", prec=prec, rank=rank, world=world,

@@ -56,7 +56,8 @@ def test_scene_windows_match_oracle_batching(cuda, d):
     assert int(sc["valid"].sum(1).max()) <= sc["N"]
 
 
-@pytest.mark.parametrize("d,prec,tol", [(1, ops.PREC_F32, 1e-3), (2, ops.PREC_F32, 1e-3), (1, ops.PREC_BF16, 1e-3)])
+@pytest.mark.parametrize("d,prec,tol", [(1, ops.PREC_F32, 1e-3), (2, ops.PREC_F32, 1e-3), (1, ops.PREC_BF16, 1e-3), (1, ops.PREC_F16, 2e-4),
+                                        (2, ops.PREC_F16, 2e-4)])
 def test_best_of_k_on_real_split_matches_oracle(cuda, d, prec, tol):
     """C1: forward + best-of-20 ADE/FDE on a real split against the oracle with the same fed noise (fp32 mode: the
     north_star's 1e-3; bf16 stated separately), in the table's units and -- ETH -- in metres."""
@@ -151,11 +152,12 @@ def test_drop_in_model_classes_reach_the_batched_path(cuda):
     p = ops.CellParams.from_numpy(synth.init_params(seed=0), cuda)
     m = mc.g2k_lstm_mc(in_features=torch.zeros((16, 16)), out_size=128, obs_len=8, num_nodes=N, lambda_reg=0.0005)
     got = m.forecast_batched(pos, vis, valid, p, seed=3)
-    want = ops.rollout_bf16(pos, vis, valid, p)
-    assert torch.equal(got["params"], want)                              # the fused kernel, bit for bit
+    want = ops.rollout_f16(pos, vis, valid, p)
+    assert torch.equal(got["params"], want)                              # the fused kernel (default mode: f16), bit for bit
+    assert torch.equal(m.forecast_batched(pos, vis, valid, p, seed=3, prec=ops.PREC_BF16)["params"], ops.rollout_bf16(pos, vis, valid, p))
     r = mcr.g2k_lstm_mcr(in_features=torch.zeros((16, 16)), hidden_size=128, obs_len=8, num_nodes=N, lambda_reg=0.0005)
     got_r = r.forecast_batched(pos, vis, valid, p, seed=3)
-    ref = ops.Forecaster(p, S, N, 8, 12, 20, relational=True, prec=ops.PREC_BF16, seed=3, device=cuda)(pos, vis, valid)
+    ref = ops.Forecaster(p, S, N, 8, 12, 20, relational=True, prec=ops.PREC_F16, seed=3, device=cuda)(pos, vis, valid)
     assert torch.equal(got_r["best_k"], ref["best_k"]) and not torch.equal(got_r["params"], got["params"])
 
 
