@@ -757,7 +757,7 @@ def run_c2(args, rank, world, local_rank):
     held = realdata.scene_windows(a, leave, "all", dev)
 
     def evaluate():
-        r = realdata.evaluate_split(a, leave, params, part="all", prec=ops.PREC_BF16, relational=relational, rank=rank,
+        r = realdata.evaluate_split(a, leave, params, part="all", prec=ops.PREC_F16, relational=relational, rank=rank,
                                     world=world, device=dev, scenes=held, seed=11)
         return realdata.public(r)
     before = evaluate()
