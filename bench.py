@@ -748,7 +748,8 @@ def run_c2(args, rank, world, local_rank):
     relational = args.variant != "mc"            # configs[1] names g2k_lstm_mcr: the default of this config
     params = ops.CellParams.from_numpy(synth.init_params(seed=0), dev)
     leave, train_sets = 2, [3, 4]
-    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational)
+    tr = Trainer(params, T_OBS, P_PRED, R2, INV_2SIGMA2, lr=1e-3, gemm=args.train_gemm, relational=relational,
+                 graph=args.train_graph)
     shards = {}
     for d in train_sets:
         sc = realdata.scene_windows(a, d, "train", dev)
@@ -790,7 +791,7 @@ def run_c2(args, rank, world, local_rank):
               "dtype": "f32 state; contractions " + args.train_gemm, "data": "ETH/UCY tables under data/ (real)",
               "config": {"workload": "C2: g2k_lstm_%s training step, UCY zara1 leave-one-out (train: zara02 + ucy/univ, all obs+pred windows "
                                      "of the training columns per step; held out: zara01)" % ("mcr" if relational else "mc"),
-                         "contractions": args.train_gemm, "lr": 1e-3, "collective": "one all-reduce (SUM) of the gradient bucket per step" if world > 1 else "none (1 GPU)"},
+                         "contractions": args.train_gemm, "cuda_graph": bool(args.train_graph), "lr": 1e-3, "collective": "one all-reduce (SUM) of the gradient bucket per step" if world > 1 else "none (1 GPU)"},
               "per_table": per, "loss_first": losses[0], "loss_last": losses[-1],
               "held_out_zara01_best_of_20": {"before": before, "after": after,
                                              "note": "normalised (z-scored) units; random init -> after %d steps per table" % (args.warmup + steps)}})

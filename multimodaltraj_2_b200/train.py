@@ -276,7 +276,7 @@ class Trainer:
         # graph: step() replays the forward + BPTT of one shard (~1000 launches, no host synchronisation, fixed shapes) as ONE
         # CUDA graph, captured on the first step of each input shape; all-reduce, clipping and RMSProp stay outside it.
         self.graph = bool(graph)
-        self._captured = None                                          # (key, CUDAGraph, static inputs, static outputs)
+        self._captured = {}                                            # input shapes -> (CUDAGraph, static inputs, outputs, launches)
         self.keys = TRAIN_KEYS + (EDGE_KEYS if self.relational else ())
         self.p, self.T, self.P, self.r2, self.inv = params, T, P, r2, inv_2sigma2
         self.lam, self.lr, self.decay, self.clip = lam, lr, decay, clip
@@ -450,7 +450,9 @@ class Trainer:
         """loss_and_grad_sums through a CUDA graph (captured once per input shape; the weights are updated in place, so a
         replay reads the current ones).  The outputs are the graph's own buffers: consumed before the next replay."""
         key = (tuple(pos.shape), tuple(vis.shape), tuple(valid.shape), pos.device)
-        if self._captured is None or self._captured[0] != key:
+        if key not in self._captured:
+            if len(self._captured) >= 8:                               # a handful of batch shapes (one per training table)
+                self._captured.pop(next(iter(self._captured)))
             static = tuple(t.clone() for t in (pos, vis, valid))
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -463,14 +465,14 @@ class Trainer:
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):
                 out = self.loss_and_grad_sums(*static)
-            self.graph_launches = ops.launch_count() - n0              # this library's kernels inside one replay
-            self._captured = (key, cg, static, out)
-        _, cg, static, out = self._captured
+            self.graph_launches = ops.launch_count() - n0              # this library's kernels inside one replay (last capture)
+            self._captured[key] = (cg, static, out, self.graph_launches)
+        cg, static, out, n_launches = self._captured[key]
         for dst, src in zip(static, (pos, vis, valid)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src)
         cg.replay()
-        ops._graph_launches += self.graph_launches                    # replayed launches, for ops.launch_count()
+        ops._graph_launches += n_launches                             # replayed launches, for ops.launch_count()
         return out
 
     def step(self, pos, vis, valid):
