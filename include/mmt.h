@@ -350,6 +350,36 @@ int mmt_gsk_cell_backward_f32(const float* z, const float* c, const float* mc, c
                               float* dc, float* dmc, float* dpeep, float* db /* [3U] += column sums of dz, or NULL */,
                               void* stream);
 
+/* Packed training path (Trainer(gemm="tc")): the same two kernels on PACKED rows, and the element-wise glue between this
+ * library's kernels of one frame of the teacher-forced step (what the per-frame loop of train.py:161-254 does in Python /
+ * TensorFlow ops, plus its adjoint), so that no library slicing / concatenation / broadcast kernel runs between them.
+ *   hc[R,2U] = [h | c], mhc[R,2U] = [mh | mc] (mmt_aggregate_f32 on hc), A[R,E+2U] = [e | h | mh], z[R,3U] = A W (NO bias).
+ * mmt_train_frame_inputs_f32:   cur[R,2] = pos[:, t]; x[R,4] = [cur - pos[:, t-1] (0 at t = 0) | vis[:, min(t, T-1)]];
+ *                               target[R,2] = pos[:, t+1] - cur (target may be NULL).  pos[R,F,2], vis[R,T,2].
+ * mmt_train_gate_input_f32:     A[r] = [relu(x_r W_e + b_e) | hc[r,:U] | mhc[r,:U]].
+ * mmt_gsk_gates_packed_f32:     mmt_gsk_gates_f32 on z + b with c = hc[:,U:], mc = mhc[:,U:]; writes hc_out[R,2U] = [h' | c'],
+ *                               h_out[R,U] = h' (contiguous copy for the head) and mf_out[R,U].
+ * mmt_gsk_cell_backward_packed_f32: mmt_gsk_cell_backward_f32 on z + b and the packed c / mc; d_head[R,2U] (NULL or the
+ *                               head's gradient w.r.t. [m_t | m_f]) is added to d_mt / taken as d_mf; d mc goes to dmhc[:,U:].
+ * mmt_train_backward_split_f32: from dA[R,E+2U] = dz W^T: dpre[R,E] = dA[:,:E] * (A[:,:E] > 0), gbe[E] += its column sums
+ *                               (gbe may be NULL), dmhc[:,:U] = dA[:,E+U:].
+ * mmt_train_backward_merge_f32: from back[R,2U] = att^T dmhc: Gh[R,U] = dA[:,E:E+U] + back[:,:U], Gc[R,U] = dc + back[:,U:]. */
+int mmt_train_frame_inputs_f32(const float* pos, const float* vis, int R, int F, int T, int t, float* cur, float* x,
+                               float* target, void* stream);
+int mmt_train_gate_input_f32(const float* x, const float* hc, const float* mhc, const float* W_e, const float* b_e, int R,
+                             int E, int U, float* A, void* stream);
+int mmt_gsk_gates_packed_f32(const float* z, const float* b, const float* hc, const float* mhc, const uint8_t* valid,
+                             const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot, int R, int U,
+                             float* hc_out, float* h_out, float* mf_out, void* stream);
+int mmt_gsk_cell_backward_packed_f32(const float* z, const float* b, const float* hc, const float* mhc, const uint8_t* valid,
+                                     const float* w_If, const float* w_It, const float* w_Of, const float* w_Ot,
+                                     const float* d_mt, const float* d_head, const float* d_ct, int R, int U, float* dz,
+                                     float* dc, float* dmhc, float* dpeep, float* db, void* stream);
+int mmt_train_backward_split_f32(const float* dA, const float* A, int R, int E, int U, float* dpre, float* dmhc, float* gbe,
+                                 void* stream);
+int mmt_train_backward_merge_f32(const float* dA, const float* back, const float* dc, int R, int E, int U, float* Gh,
+                                 float* Gc, void* stream);
+
 /* number of kernel launches issued by this process through the library (bench's gpu_launches) */
 uint64_t mmt_launch_count(void);
 

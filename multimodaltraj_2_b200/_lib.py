@@ -58,6 +58,12 @@ SIGNATURES = {
     "mmt_pack_edge_weights_bf16": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     "mmt_edge_mlp_bf16": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_size_t,
                                     vp]),
+    "mmt_train_frame_inputs_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "mmt_train_gate_input_f32": (C.c_int, [vp] * 5 + [C.c_int] * 3 + [vp, vp]),
+    "mmt_gsk_gates_packed_f32": (C.c_int, [vp] * 9 + [C.c_int] * 2 + [vp] * 4),
+    "mmt_gsk_cell_backward_packed_f32": (C.c_int, [vp] * 12 + [C.c_int] * 2 + [vp] * 6),
+    "mmt_train_backward_split_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "mmt_train_backward_merge_f32": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "mmt_attention_score_grad_f32": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "mmt_edge_mlp_backward_f32": (C.c_int, [vp] * 9 + [C.c_int] * 4 + [vp] * 7 + [C.c_size_t, vp]),
     "mmt_edge_mlp_backward_bf16": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp] * 6 + [C.c_size_t, vp]),

@@ -319,6 +319,90 @@ def gsk_gates(z, c, mc, valid, params: "CellParams"):
     return h_out, c_out, mf
 
 
+# ---- packed training path (Trainer(gemm="tc")): hc = [h | c], mhc = [mh | mc], A = [e | h | mh], z = A W without bias
+def train_frame_inputs(pos, vis, t, want_target):
+    """Teacher-forced inputs of frame t (mmt_train_frame_inputs_f32): cur[S,N,2], x[R,4], target[R,2] or None."""
+    lib = _lib.load()
+    _chk(pos, torch.float32, "pos"); _chk(vis, torch.float32, "vis")
+    S, N, F, _ = pos.shape
+    T = vis.shape[2]
+    R = S * N
+    cur = torch.empty((S, N, 2), dtype=torch.float32, device=pos.device)
+    x = torch.empty((R, 4), dtype=torch.float32, device=pos.device)
+    target = torch.empty((R, 2), dtype=torch.float32, device=pos.device) if want_target else None
+    _lib.check(lib.mmt_train_frame_inputs_f32(_p(pos), _p(vis), R, F, T, int(t), _p(cur), _p(x), _p(target), _stream()),
+               "mmt_train_frame_inputs_f32")
+    return cur, x, target
+
+
+def train_gate_input(x, hc, mhc, params: "CellParams"):
+    """A[R,E+2U] = [relu(x W_e + b_e) | h | mh] from the packed rows (mmt_train_gate_input_f32)."""
+    lib = _lib.load()
+    for n, t in dict(x=x, hc=hc, mhc=mhc).items():
+        _chk(t, torch.float32, n)
+    R, U, E = x.shape[0], params.U, params.E
+    A = torch.empty((R, E + 2 * U), dtype=torch.float32, device=x.device)
+    _lib.check(lib.mmt_train_gate_input_f32(_p(x), _p(hc), _p(mhc), _p(params.W_e), _p(params.b_e), R, E, U, _p(A), _stream()),
+               "mmt_train_gate_input_f32")
+    return A
+
+
+def gsk_gates_packed(z, hc, mhc, valid, params: "CellParams"):
+    """Gate update from z (no bias: params.b is added in the kernel) on packed rows -> (hc' [R,2U], h' [R,U], m_f [R,U])."""
+    lib = _lib.load()
+    for n, t in dict(z=z, hc=hc, mhc=mhc).items():
+        _chk(t, torch.float32, n)
+    _chk(valid, torch.uint8, "valid")
+    R, U = z.shape[0], params.U
+    hc_out = torch.empty((R, 2 * U), dtype=torch.float32, device=z.device)
+    h_out = torch.empty((R, U), dtype=torch.float32, device=z.device)
+    mf = torch.empty((R, U), dtype=torch.float32, device=z.device)
+    _lib.check(lib.mmt_gsk_gates_packed_f32(_p(z), _p(params.b), _p(hc), _p(mhc), _p(valid), _p(params.w_If), _p(params.w_It),
+                                            _p(params.w_Of), _p(params.w_Ot), R, U, _p(hc_out), _p(h_out), _p(mf), _stream()),
+               "mmt_gsk_gates_packed_f32")
+    return hc_out, h_out, mf
+
+
+def gsk_cell_backward_packed(z, hc, mhc, valid, params: "CellParams", d_mt, d_head, d_ct, dpeep, db):
+    """mmt_gsk_cell_backward_packed_f32 -> (dz[R,3U], dc[R,U], dmhc[R,2U] with its d mc half written)."""
+    lib = _lib.load()
+    for n, t in dict(z=z, hc=hc, mhc=mhc, d_mt=d_mt, dpeep=dpeep, db=db).items():
+        _chk(t, torch.float32, n)
+    R, U = z.shape[0], params.U
+    dz = torch.empty_like(z)
+    dc = torch.empty((R, U), dtype=torch.float32, device=z.device)
+    dmhc = torch.empty((R, 2 * U), dtype=torch.float32, device=z.device)
+    _lib.check(lib.mmt_gsk_cell_backward_packed_f32(_p(z), _p(params.b), _p(hc), _p(mhc), _p(valid), _p(params.w_If),
+                                                    _p(params.w_It), _p(params.w_Of), _p(params.w_Ot), _p(d_mt), _p(d_head),
+                                                    _p(d_ct), R, U, _p(dz), _p(dc), _p(dmhc), _p(dpeep), _p(db), _stream()),
+               "mmt_gsk_cell_backward_packed_f32")
+    return dz, dc, dmhc
+
+
+def train_backward_split(dA, A, dmhc, gbe, params: "CellParams"):
+    """dpre[R,E] = dA[:, :E] * (e > 0) (column sums accumulated into gbe); dmhc[:, :U] = dA[:, E+U:] (in place)."""
+    lib = _lib.load()
+    for n, t in dict(dA=dA, A=A, dmhc=dmhc, gbe=gbe).items():
+        _chk(t, torch.float32, n)
+    R, U, E = dA.shape[0], params.U, params.E
+    dpre = torch.empty((R, E), dtype=torch.float32, device=dA.device)
+    _lib.check(lib.mmt_train_backward_split_f32(_p(dA), _p(A), R, E, U, _p(dpre), _p(dmhc), _p(gbe), _stream()),
+               "mmt_train_backward_split_f32")
+    return dpre
+
+
+def train_backward_merge(dA, back, dc, params: "CellParams"):
+    """(Gh, Gc) = (dA[:, E:E+U] + back[:, :U], dc + back[:, U:]) (mmt_train_backward_merge_f32)."""
+    lib = _lib.load()
+    for n, t in dict(dA=dA, back=back, dc=dc).items():
+        _chk(t, torch.float32, n)
+    R, U, E = dA.shape[0], params.U, params.E
+    Gh, Gc = torch.empty_like(dc), torch.empty_like(dc)
+    _lib.check(lib.mmt_train_backward_merge_f32(_p(dA), _p(back), _p(dc), R, E, U, _p(Gh), _p(Gc), _stream()),
+               "mmt_train_backward_merge_f32")
+    return Gh, Gc
+
+
 def gsk_cell_backward(z, c, mc, valid, params: "CellParams", d_mt, d_mf, d_ct, dpeep, db=None):
     """Backward of the gate update from the saved pre-activations (mmt_gsk_cell_backward_f32):
     returns (dz[R,3U], dc[R,U], dmc[R,U]); dpeep[4,U] and (if given) db[3U], the gate-bias gradient, are accumulated in place."""

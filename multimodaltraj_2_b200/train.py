@@ -295,7 +295,83 @@ class Trainer:
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32_was
 
+    def _packed_step(self, pos, vis, valid):
+        """gemm = "tc": forward + BPTT of the shard on PACKED rows (hc = [h | c], mhc = [mh | mc], A = [e | h | mh], z without
+        bias) -- every kernel between the frame's inputs and its gradients is this library's, the element-wise glue included
+        (mmt_train_frame_inputs_f32, mmt_train_gate_input_f32, mmt_gsk_gates_packed_f32, mmt_gsk_cell_backward_packed_f32,
+        mmt_train_backward_split_f32 / _merge_f32).  Left to the library: dy W_h^T (inner dimension 5), two [R,5] reductions,
+        and, for g2k_lstm_mcr, the addition of the edge scores to the logits."""
+        p, T, P = self.p, self.T, self.P
+        S, N = valid.shape
+        R, U, E = S * N, p.U, p.E
+        dev = pos.device
+        vflat = valid.reshape(-1).contiguous()
+        hc = torch.zeros((R, 2 * U), device=dev)
+        saved = []
+        loss_sum = torch.zeros((1,), device=dev)
+        edge_packed = None
+        if self.relational and U == 128 and p.W2.shape[0] == 128:
+            edge_packed = ops.pack_edge_weights(p.W1, p.W2)
+        for t in range(T + P - 1):
+            cur, x, target = ops.train_frame_inputs(pos, vis, t, t >= T - 1)
+            kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
+            rec = dict(x=x, hc=hc)
+            if self.relational:
+                rec["h"] = hc[:, :U].contiguous()
+                kern = kern + ops.edge_mlp(rec["h"].view(S, N, U), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out,
+                                           ops.PREC_BF16 if edge_packed is not None else ops.PREC_F32, edge_packed)
+                rec["adj"] = adj
+            att, mhc = ops.aggregate(kern, adj, hc.view(S, N, 2 * U))
+            mhc = mhc.view(R, 2 * U)
+            A = ops.train_gate_input(x, hc, mhc, p)
+            z = ops.gemm_tf32(A, p.W)                                   # pre-activations without the bias (added in the kernels)
+            hc_next, hn, mf = ops.gsk_gates_packed(z, hc, mhc, vflat, p)
+            rec.update(att=att, mhc=mhc, A=A, z=z, hn=hn, mf=mf)
+            if t >= T - 1:
+                rec["dy"] = ops.head_nll(hn, mf, vflat, p.W_h, p.b_h, target, 1.0, loss_sum)
+            saved.append(rec)
+            hc = hc_next
+        # ---- back-propagation through time
+        g = {k: torch.zeros_like(getattr(p, k)) for k in self.keys}
+        dpeep = torch.zeros((4, U), device=dev)
+        Gh, Gc = torch.zeros((R, U), device=dev), None
+        gWh8 = torch.zeros((2 * U, 8), device=dev)                      # head-weight gradient, 8-column rows (ld % 4 == 0)
+        node = None
+        if self.relational:
+            He = p.W2.shape[0]
+            node = dict(W1cat=torch.cat([p.W1[:U], p.W1[U:]], 1).contiguous(), gW1=torch.zeros((U, 2 * He), device=dev),
+                        packed=edge_packed)
+        for t in reversed(range(T + P - 1)):
+            r = saved[t]
+            d_head = None
+            if "dy" in r:
+                dy = r["dy"]
+                dy8 = torch.nn.functional.pad(dy, (0, 3))
+                ops.gemm_tf32(r["hn"], dy8, transA=True, out=gWh8[:U], accumulate=True)
+                ops.gemm_tf32(r["mf"], dy8, transA=True, out=gWh8[U:], accumulate=True)
+                g["b_h"] += dy.sum(0)
+                d_head = dy @ p.W_h.t()                                 # [R, 2U]: gradient w.r.t. [m_t | m_f]
+            A, z = r.pop("A"), r.pop("z")
+            dz, dc, dmhc = ops.gsk_cell_backward_packed(z, r["hc"], r["mhc"], vflat, p, Gh, d_head, Gc, dpeep, g["b"])
+            ops.gemm_tf32(A, dz, transA=True, out=g["W"], accumulate=True)      # dW += A^T dz  (K = all agent rows)
+            dA = ops.gemm_tf32(dz, p.W, transB=True)                           # dA  = dz W^T
+            dpre = ops.train_backward_split(dA, A, dmhc, g["b_e"], p)          # relu mask, b_e gradient, d mh into dmhc
+            ops.gemm_tf32(r["x"], dpre, transA=True, out=g["W_e"], accumulate=True)
+            back = ops.aggregate_transpose(r["att"], dmhc.view(S, N, 2 * U)).view(R, 2 * U)
+            Gh, Gc = ops.train_backward_merge(dA, back, dc, p)
+            if self.relational:
+                Gh = Gh + self._edge_backward(r, dmhc.view(S, N, 2 * U), g, S, N, node)
+        g["W_h"] += gWh8[:, :5]
+        if self.relational:
+            He = p.W2.shape[0]
+            g["W1"][:U] += node["gW1"][:, :He]
+            g["W1"][U:] += node["gW1"][:, He:]
+        g["w_If"], g["w_It"], g["w_Of"], g["w_Ot"] = dpeep[0], dpeep[1], dpeep[2], dpeep[3]
+        return loss_sum, valid.sum().float() * P, g
+
     def _loss_and_grad_sums(self, pos, vis, valid):
+        if self.gemm == "tc":
+            return self._packed_step(pos, vis, valid)
         p, T, P = self.p, self.T, self.P
         S, N = valid.shape
         R, U, E = S * N, p.U, p.E
@@ -428,7 +504,7 @@ class Trainer:
         p = self.p
         U, He = p.U, p.W2.shape[0]
         h = r["h"]
-        hc = torch.cat([h, r["c"]], -1).view(S, N, 2 * U)
+        hc = (r["hc"] if "hc" in r else torch.cat([h, r["c"]], -1)).view(S, N, 2 * U)
         dlog = ops.attention_score_grad(r["att"], r["adj"], dmhc, hc)
         packed = node["packed"]
         dab = ops.edge_mlp_backward(h.view(S, N, U), r["adj"], dlog, p, g, ops.PREC_BF16 if packed is not None else ops.PREC_F32,

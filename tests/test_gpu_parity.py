@@ -700,6 +700,52 @@ def test_train_step_rmsprop_and_loss_decrease(cuda):
     assert losses[-1] < losses[0] - 0.05, losses
 
 
+def test_training_glue_kernels_match_their_tensor_expressions(cuda):
+    """The element-wise kernels of the packed training path against the slicing / concatenation expressions they replace."""
+    S, N, T, F, U, E = 5, 12, 8, 20, 128, 64
+    R = S * N
+    g = torch.Generator(device="cpu").manual_seed(3)
+    rnd = lambda *sh: torch.randn(*sh, generator=g).to(cuda)   # noqa: E731
+    pos, vis = rnd(S, N, F, 2), rnd(S, N, T, 2)
+    p = ops.CellParams.from_numpy(synth.init_params(seed=4), cuda)
+    for t in (0, 3, T - 1, T + 4, F - 2):
+        cur, x, target = ops.train_frame_inputs(pos, vis, t, True)
+        assert torch.equal(cur, pos[:, :, t])
+        disp = pos[:, :, t] - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
+        assert torch.equal(x, torch.cat([disp, vis[:, :, min(t, T - 1)]], -1).reshape(R, 4))
+        assert torch.equal(target, (pos[:, :, t + 1] - pos[:, :, t]).reshape(R, 2))
+    x, hc, mhc = rnd(R, 4), rnd(R, 2 * U), rnd(R, 2 * U)
+    A = ops.train_gate_input(x, hc, mhc, p)
+    e = torch.relu(x.double() @ p.W_e.double() + p.b_e.double()).float()
+    assert torch.equal(A[:, E:E + U], hc[:, :U]) and torch.equal(A[:, E + U:], mhc[:, :U])
+    assert (A[:, :E] - e).abs().max().item() < 1e-5 and torch.equal(A[:, :E] > 0, e > 0)
+    dA, dc, back = rnd(R, E + 2 * U), rnd(R, U), rnd(R, 2 * U)
+    dmhc = rnd(R, 2 * U)
+    keep = dmhc[:, U:].clone()
+    gbe = torch.ones(E, device=cuda)
+    dpre = ops.train_backward_split(dA, A, dmhc, gbe, p)
+    want = dA[:, :E] * (A[:, :E] > 0)
+    assert torch.equal(dpre, want) and torch.equal(dmhc[:, :U], dA[:, E + U:]) and torch.equal(dmhc[:, U:], keep)
+    assert (gbe - 1.0 - want.double().sum(0).float()).abs().max().item() < 1e-3
+    Gh, Gc = ops.train_backward_merge(dA, back, dc, p)
+    assert torch.equal(Gh, dA[:, E:E + U] + back[:, :U]) and torch.equal(Gc, dc + back[:, U:])
+    # packed gate update / backward == the unpacked kernels on the same numbers
+    valid = (torch.rand(R, generator=g) > 0.2).to(torch.uint8).to(cuda)
+    z = rnd(R, 3 * U) * 0.5
+    zb = z + p.b
+    hcn, hn, mf = ops.gsk_gates_packed(z, hc, mhc, valid, p)
+    h2, c2, f2 = ops.gsk_gates(zb, hc[:, U:].contiguous(), mhc[:, U:].contiguous(), valid, p)
+    assert torch.equal(hn, h2) and torch.equal(hcn[:, :U], h2) and torch.equal(hcn[:, U:], c2) and torch.equal(mf, f2)
+    d_mt, d_head, d_ct = rnd(R, U), rnd(R, 2 * U), rnd(R, U)
+    dp1, dp2 = torch.zeros((4, U), device=cuda), torch.zeros((4, U), device=cuda)
+    db1, db2 = torch.zeros(3 * U, device=cuda), torch.zeros(3 * U, device=cuda)
+    dz, dcc, dm = ops.gsk_cell_backward_packed(z, hc, mhc, valid, p, d_mt, d_head, d_ct, dp1, db1)
+    dz2, dc2, dmc2 = ops.gsk_cell_backward(zb, hc[:, U:].contiguous(), mhc[:, U:].contiguous(), valid, p,
+                                           (d_mt + d_head[:, :U]).contiguous(), d_head[:, U:].contiguous(), d_ct, dp2, db=db2)
+    assert torch.equal(dz, dz2) and torch.equal(dcc, dc2) and torch.equal(dm[:, U:], dmc2)
+    assert (dp1 - dp2).abs().max().item() < 1e-3 and (db1 - db2).abs().max().item() < 1e-3
+
+
 @pytest.mark.parametrize("gemm,relational", [("fp32", False), ("tc", False), ("tc", True)])
 def test_train_step_cuda_graph_equals_eager(cuda, gemm, relational):
     """Trainer(graph=True): forward + BPTT replayed as one CUDA graph.  Same launches in the same order, so after three
