@@ -261,9 +261,9 @@ class Trainer:
         #   "tc"   this library's own contractions: mmt_gemm_tf32 (TMA tensor maps -> tcgen05.mma.kind::tf32 -> TMEM; split-K
         #          with red.add for the weight gradients) for the gate GEMM forward, A^T dz and dz W^T -- 97 % of the step's
         #          FLOPs -- the head-weight and embedding-weight gradients ([hn|mf]^T dy, x^T dpre: K = all agent rows too),
-        #          mmt_aggregate_transpose_f32 for att^T [d mh | d mc], the bias gradient inside gsk_cell_backward_kernel; same
-        #          tolerance as "tf32".  Left as library calls: the two products with a 4- / 5-long inner dimension
-        #          (x W_e, dy W_h^T: 0.3 % of the FLOPs) and the elementwise glue.
+        #          mmt_aggregate_transpose_f32 for att^T [d mh | d mc], the bias gradients inside the backward kernels, and the
+        #          element-wise glue between them on packed rows (_packed_step); same tolerance as "tf32".  Left as library
+        #          calls: dy W_h^T (inner dimension 5) and two [R,5] reductions.
         if gemm not in ("fp32", "tf32", "tc"):
             raise ValueError("gemm must be 'fp32', 'tf32' or 'tc'")
         self.gemm = gemm
@@ -381,31 +381,19 @@ class Trainer:
         c = torch.zeros((S, N, U), device=dev)
         saved = []
         loss_sum = torch.zeros((1,), device=dev)
-        edge_packed = None
-        if self.relational and self.gemm == "tc" and U == 128 and p.W2.shape[0] == 128:
-            edge_packed = ops.pack_edge_weights(p.W1, p.W2)
-        for t in range(T + P - 1):
+        for t in range(T + P - 1):                                     # fp32 / tf32 (library GEMM) modes: tensors per quantity
             cur = pos[:, :, t].contiguous()
             disp = cur - pos[:, :, t - 1] if t > 0 else torch.zeros_like(cur)
             x = torch.cat([disp, vis[:, :, min(t, T - 1)]], -1).reshape(R, 4).contiguous()
             kern, adj, _ = ops.pairwise_adj(cur, valid, self.r2, self.inv, want_deg=False)
             if self.relational:
-                # "tc" with U = He = 128: the tcgen05 edge MLP (bf16 operands); its backward recomputes the same values
-                kern = kern + ops.edge_mlp(h.contiguous(), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out,
-                                           ops.PREC_BF16 if edge_packed is not None else ops.PREC_F32, edge_packed)
+                kern = kern + ops.edge_mlp(h.contiguous(), adj, p.W1, p.b1, p.W2, p.b2, p.w_out, p.b_out)
             att, mhc = ops.aggregate(kern, adj, torch.cat([h, c], -1).contiguous())
             mh, mc = mhc[..., :U].reshape(R, U).contiguous(), mhc[..., U:].reshape(R, U).contiguous()
             rec = dict(x=x, h=h.reshape(R, U), c=c.reshape(R, U), att=att, mh=mh, mc=mc)
             if self.relational:
                 rec["adj"] = adj
-            if self.gemm == "tc":
-                # gate GEMM on this library's tcgen05 tf32 GEMM + mmt_gsk_gates_f32; A, z are kept for the backward
-                e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
-                A = torch.cat([e, rec["h"], mh], -1)
-                z = ops.gemm_tf32(A, p.W).add_(p.b)
-                hn, cn, mf = ops.gsk_gates(z, rec["c"], mc, vflat, p)
-                rec["e"], rec["z"], rec["A"] = e, z, A
-            elif self.gemm == "tf32":
+            if self.gemm == "tf32":
                 # gate GEMM on the tensor cores (library GEMM) + mmt_gsk_gates_f32; z and e are kept for the backward
                 e = torch.relu(torch.addmm(p.b_e, x, p.W_e))
                 z = torch.addmm(p.b, torch.cat([e, rec["h"], mh], -1), p.W)
@@ -420,9 +408,9 @@ class Trainer:
             saved.append(rec)
             h, c = hn.view(S, N, U), cn.view(S, N, U)
         # ---- back-propagation through time
-        return self._backward(saved, loss_sum, valid, vflat, S, N, edge_packed)
+        return self._backward(saved, loss_sum, valid, vflat, S, N)
 
-    def _backward(self, saved, loss_sum, valid, vflat, S, N, edge_packed=None):
+    def _backward(self, saved, loss_sum, valid, vflat, S, N):
         p, T, P = self.p, self.T, self.P
         R, U, E = S * N, p.U, p.E
         dev = vflat.device
@@ -430,63 +418,38 @@ class Trainer:
         dpeep = torch.zeros((4, U), device=dev)
         Gh = torch.zeros((R, U), device=dev)
         Gc = None
-        tc = self.gemm == "tc"
-        gWh8 = torch.zeros((2 * U, 8), device=dev) if tc else None     # head-weight gradient, 8-column rows (ld % 4 == 0)
         node = None
         if self.relational:                                            # node level of the edge MLP: [a | b] = h [W1a | W1b]
             He = p.W2.shape[0]
             node = dict(W1cat=torch.cat([p.W1[:U], p.W1[U:]], 1).contiguous(), gW1=torch.zeros((U, 2 * He), device=dev),
-                        packed=edge_packed)
+                        packed=None)
         for t in reversed(range(T + P - 1)):
             r = saved[t]
             d_mf = None
             if "dy" in r:
                 dy = r["dy"]
-                if tc:
-                    # [hn | mf]^T dy (K = all agent rows) on mmt_gemm_tf32, split over K; dy padded to 8 columns for the tensor map
-                    dy8 = torch.nn.functional.pad(dy, (0, 3))
-                    ops.gemm_tf32(r["hn"], dy8, transA=True, out=gWh8[:U], accumulate=True)
-                    ops.gemm_tf32(r["mf"], dy8, transA=True, out=gWh8[U:], accumulate=True)
-                else:
-                    g["W_h"] += torch.cat([r["hn"], r["mf"]], -1).t() @ dy
+                g["W_h"] += torch.cat([r["hn"], r["mf"]], -1).t() @ dy
                 g["b_h"] += dy.sum(0)
                 dhm = dy @ p.W_h.t()
                 Gh = Gh + dhm[:, :U]
                 d_mf = dhm[:, U:].contiguous()
             e = r["e"] if "e" in r else torch.relu(r["x"] @ p.W_e + p.b_e)
-            A = r.pop("A") if "A" in r else torch.cat([e, r["h"], r["mh"]], -1)
+            A = torch.cat([e, r["h"], r["mh"]], -1)
             z = r.pop("z") if "z" in r else torch.addmm(p.b, A, p.W)
-            # "tc": the bias gradient (column sums of dz) comes out of the same kernel, no separate reduction over dz
-            dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep,
-                                                db=g["b"] if tc else None)
-            if tc:
-                ops.gemm_tf32(A, dz, transA=True, out=g["W"], accumulate=True)      # dW += A^T dz  (K = all agent rows)
-                dA = ops.gemm_tf32(dz, p.W, transB=True)                           # dA  = dz W^T
-            else:
-                g["W"] += A.t() @ dz
-                dA = dz @ p.W.t()
-            if not tc:
-                g["b"] += dz.sum(0)
+            dz, dc, dmc = ops.gsk_cell_backward(z, r["c"], r["mc"], vflat, p, Gh.contiguous(), d_mf, Gc, dpeep)
+            g["W"] += A.t() @ dz
+            dA = dz @ p.W.t()
+            g["b"] += dz.sum(0)
             dpre = dA[:, :E] * (e > 0)
-            if tc:
-                ops.gemm_tf32(r["x"], dpre.contiguous(), transA=True, out=g["W_e"], accumulate=True)
-            else:
-                g["W_e"] += r["x"].t() @ dpre
+            g["W_e"] += r["x"].t() @ dpre
             g["b_e"] += dpre.sum(0)
             d_mh = dA[:, E + U:].reshape(S, N, U)
-            dmhc = torch.cat([d_mh, dmc.view(S, N, U)], -1).contiguous() if (tc or self.relational) else None
-            if tc:
-                back = ops.aggregate_transpose(r["att"], dmhc).reshape(R, 2 * U)
-                Gh = dA[:, E:E + U] + back[:, :U]
-                Gc = (dc + back[:, U:]).contiguous()
-            else:
-                attT = r["att"].transpose(1, 2)
-                Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
-                Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
+            attT = r["att"].transpose(1, 2)
+            Gh = dA[:, E:E + U] + torch.bmm(attT, d_mh).reshape(R, U)
+            Gc = (dc + torch.bmm(attT, dmc.view(S, N, U)).reshape(R, U)).contiguous()
             if self.relational:
+                dmhc = torch.cat([d_mh, dmc.view(S, N, U)], -1).contiguous()
                 Gh = Gh + self._edge_backward(r, dmhc, g, S, N, node)
-        if tc:
-            g["W_h"] += gWh8[:, :5]
         if self.relational:
             He = p.W2.shape[0]
             g["W1"][:U] += node["gW1"][:, :He]
