@@ -245,3 +245,39 @@ def test_bench_prints_one_json_line_on_stdout():
     assert r.returncode == 0, r.stderr
     assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"metric": "m", "value": 1.5}
     assert "library noise" in r.stderr and "raw noise" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------
+def test_operand_rounding_emulation_explains_the_bf16_error_and_what_fp16_leaves():
+    """DESIGN.md section 5, on the CPU: the oracle's rollout with its GEMM / aggregation operands rounded the way the fused
+    tensor-core kernel rounds them.  No rounding reproduces the oracle; bf16 operands move ADE / FDE by what the GPU's bf16 mode
+    measures; operands with 11 significand bits (fp16 = the MMT_PREC_F16 mode; tf32, the same significand with the fp32
+    exponent, gives the same numbers to 5e-6) leave several times less."""
+    import operand_rounding as o_r
+    import track_b as o_b
+    from multimodaltraj_2_b200 import synth
+    S, N, T, P, K = 6, 64, 8, 12, 20
+    p = synth.init_params(seed=0)
+    pos, vis, valid = synth.make_crowd(S, N, seed=synth.SEED)
+    eps = o_b.philox_eps(0xB200, S, N, K, P)
+    want = o_b.forecast(pos, vis, valid, p, eps, T, P)
+    v = valid.astype(bool)
+    err = {}
+    for name, rnd in (("none", o_r.r_none), ("bf16", o_r.r_bf16), ("tf32", o_r.r_tf32), ("f16", o_r.r_f16)):
+        par = o_r.rollout(pos, vis, valid, p, rnd)
+        ade, fde, *_ = o_b.decode_score(par, eps, pos[:, :, T - 1], pos[:, :, T:T + P], valid)
+        err[name] = (float(np.abs(ade[v] - want["ade"][v]).max()), float(np.abs(fde[v] - want["fde"][v]).max()))
+    assert err["none"][0] < 5e-6 and err["none"][1] < 5e-6          # the restructured softmax (numerators x 1/sum) is the oracle's
+    # the fp16 exponent range costs nothing that matters (only weights below 6e-5 lose bits to its subnormals)
+    assert abs(err["f16"][0] - err["tf32"][0]) < 5e-6 and abs(err["f16"][1] - err["tf32"][1]) < 5e-6
+    assert err["f16"][0] < 1e-4 and err["f16"][1] < 2e-4
+    assert err["bf16"][0] > 4 * err["f16"][0] and err["bf16"][1] > 4 * err["f16"][1]
+
+
+def test_precision_names_of_the_drivers():
+    from multimodaltraj_2_b200 import argParser, ops
+    assert ops.prec_from_name("fp16") == ops.PREC_F16 == 4 and ops.prec_from_name("bf16") == ops.PREC_BF16
+    assert ops.prec_from_name("fp32") == ops.PREC_F32 and ops.prec_from_name("bf16x3") == ops.PREC_BF16X3
+    with pytest.raises(ValueError):
+        ops.prec_from_name("int8")
+    assert argParser.ArgsParser.parser.parse_args([]).precision == "fp16"      # the drivers' default: inside the 1e-3 bar
